@@ -1,0 +1,152 @@
+/* rtr_b200 — C ABI of the B200-native point-projection path for RTRenderer.
+ *
+ * Drop-in boundary (SURVEY.md §8 b).  The reference exposes a C++ class, not an FFI:
+ *     class ProjectCloud            /root/reference/src/RTRenderer/include/project_cloud.h:11-60
+ *       ProjectCloud(grid, model)                 project_cloud.cu:189-251
+ *       computeRGBD(calib, w2c, color*, depth*)   project_cloud.cu:268-312
+ *       computeFilteredRGBD(...)                  project_cloud.cu:394-434
+ *       computeFull(...)  [projection+filter part, tensor hand-off]  project_cloud.cu:437-471
+ * Each entry point below names the reference member it replaces.  The header-only C++ adapter
+ * include/rtr_b200/project_cloud.hpp wraps these back into a class with the reference's method
+ * names; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions (same as the reference):
+ *   - pose / extrinsics = WORLD->CAMERA 4x4, row-major doubles (cv::Matx44d; example passes pose.inv()).
+ *   - colour is B,G,R interleaved uint8 (CV_8UC3), depth is float32 (CV_32F), both H*W, contiguous,
+ *     caller-allocated; either pointer may be NULL.
+ *   - return 1 on success (the reference's `return 1`), negative on error (never exit()).
+ *   - one renderer = one GPU = one CUDA stream; distinct renderers may be driven from distinct
+ *     threads/processes (frame sharding).  A renderer is not re-entrant.
+ * No CPU fallback exists: every call fails with RTR_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef RTR_B200_H
+#define RTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct rtr_renderer rtr_renderer;
+
+enum {
+    RTR_OK = 1,
+    RTR_ERR_ARG = -1,      /* bad argument (computeRGBD returns -1 when both outputs are NULL) */
+    RTR_ERR_CUDA = -2,     /* CUDA runtime / launch failure; see rtr_last_error() */
+    RTR_ERR_STATE = -3,    /* no cloud uploaded / no camera set */
+    RTR_ERR_UNSUPPORTED = -4,
+    RTR_ERR_COMM = -5      /* NCCL failure */
+};
+
+/* render stages for rtr_render_device() */
+enum {
+    RTR_STAGE_RGBD = 0,      /* clear + z-min + blend + resolve        == computeRGBDInternal   */
+    RTR_STAGE_FILTERED = 1   /* ... + depth prefilter + tensor write   == + applyDepthFilter     */
+};
+
+/* ---- lifetime.  Replaces ProjectCloud::ProjectCloud / ~ProjectCloud (project_cloud.cu:189-266). */
+int rtr_create(int device, rtr_renderer** out);
+void rtr_destroy(rtr_renderer* r);
+/* Last error text of this renderer (or of the failed rtr_create when r == NULL). */
+const char* rtr_last_error(const rtr_renderer* r);
+
+/* ---- cloud upload.  Replaces OctreeGrid::getVertexPositions/getVertexColors + the two cudaMemcpy
+ * in the constructor (Octreegrid.h:162-180, project_cloud.cu:191-206).  The cloud is repacked into
+ * 16-byte records {x, y, z, b|g<<8|r<<16|255<<24}; point order is irrelevant to every output. */
+int rtr_upload_cloud_xyz_bgr(rtr_renderer* r, const float* xyz, const uint8_t* bgr, uint64_t n_points);
+int rtr_upload_cloud_packed16(rtr_renderer* r, const void* host_records, uint64_t n_points);
+/* Zero-copy: use records already resident on this renderer's device (caller keeps ownership). */
+int rtr_adopt_device_cloud_packed16(rtr_renderer* r, void* device_records, uint64_t n_points);
+/* Fill the cloud on the device with the deterministic synthetic hall (bench/test support; same
+ * generator as oracle/rtr_oracle.c:rtro_synth_packed).  Points [first, first+count) of n_total. */
+int rtr_synth_cloud(rtr_renderer* r, uint64_t seed, uint64_t n_total, uint64_t first, uint64_t count,
+                    int lx_q, int ly_q, int lz_q, int n_boxes);
+uint64_t rtr_cloud_size(const rtr_renderer* r);
+/* Copy records [first, first+count) back to the host (tests). */
+int rtr_download_cloud_packed16(rtr_renderer* r, uint64_t first, uint64_t count, void* host_records);
+
+/* ---- camera.  Replaces the CameraCalibration argument (CameraCalibration.h:8-54: W, H, K; the
+ * reference ignores its distortion vector) and the extrinsics argument. */
+int rtr_set_intrinsics(rtr_renderer* r, int width, int height, double fx, double fy, double cx, double cy,
+                       double skew, const double* dist5 /* k1,k2,p1,p2,k3 or NULL */);
+int rtr_set_intrinsics_matrix(rtr_renderer* r, int width, int height, const double* K9_row_major,
+                              const double* dist5);
+int rtr_set_pose_w2c(rtr_renderer* r, const double* E16_row_major);
+/* Parity hook: bypass K*E and use this row-major float[16] camProj verbatim (project_cloud.cu:318-320). */
+int rtr_set_cam_proj_raw(rtr_renderer* r, const float* m16_row_major);
+/* The camProj the next frame will use (row-major float[16]). */
+int rtr_get_cam_proj(const rtr_renderer* r, float* m16_row_major);
+
+/* ---- render one frame, results to HOST buffers (synchronous, like the reference). */
+int rtr_render_rgbd(rtr_renderer* r, uint8_t* bgr, float* depth);      /* computeRGBD          */
+int rtr_render_filtered(rtr_renderer* r, uint8_t* bgr, float* depth);  /* computeFilteredRGBD  */
+/* computeFull's projection + prefilter; *device_fp16 receives the device pointer of the
+ * 1x5xHxW fp16 U-Net input (torch::from_blob it, project_cloud.cu:471).  Stream-synchronised. */
+int rtr_render_tensor(rtr_renderer* r, void** device_fp16);
+
+/* ---- device-resident / asynchronous variants (no host copies, no sync) */
+int rtr_render_device(rtr_renderer* r, int stage);
+int rtr_sync(rtr_renderer* r);
+/* Render n_frames poses (n_frames x 16 doubles, world->camera) back to back.  bgr/depth, when not
+ * NULL, receive n_frames images each (pinned or pageable host memory); copies overlap rendering.
+ * `stage` as above.  Returns after everything completed. */
+int rtr_render_trajectory(rtr_renderer* r, int stage, const double* poses_w2c, int n_frames, uint8_t* bgr,
+                          float* depth);
+
+typedef struct {
+    void* points;        /* n x 16 B records                                     */
+    uint32_t* zbuf;      /* W*H u32 depth bits (float view = depth; filtered: -1 where masked) */
+    uint32_t* accum;     /* W*H*4 u32 {sum b, sum g, sum r, count}               */
+    uint8_t* image;      /* W*H*3 u8 BGR                                         */
+    uint16_t* tensor;    /* 5*W*H fp16; planes packed at stride tensor_plane     */
+    uint32_t* minmax;    /* {min, max} depth bits over valid pixels              */
+    float* level[5];     /* pyramid levels (level[0] == zbuf)                    */
+    uint8_t* mask[4];    /* up-pass masks when option keep_masks=1, else NULL    */
+    int width, height;
+    int level_w[5], level_h[5];   /* true pyramid dims */
+    int up_w[5], up_h[5];         /* dims the up-pass uses (reference truncation) */
+    uint64_t tensor_plane;        /* up_w[0]*up_h[0] */
+    void* stream;                 /* cudaStream_t the renderer launches on */
+} rtr_device_buffers;
+int rtr_get_device_buffers(rtr_renderer* r, rtr_device_buffers* out);
+
+/* Copy a device buffer of the current frame to the host after syncing the stream (tests/taps).
+ * what: 0 zbuf  1 accum  2 image  3 tensor  4 minmax  5..8 level 1..4  9..12 mask 0..3 */
+int rtr_read_buffer(rtr_renderer* r, int what, void* dst, size_t bytes);
+/* Per-point projection tap: pix (int32, -1 = culled) and depth bits for every point (tests). */
+int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host);
+
+/* ---- options / introspection.  Known keys: "zmin_variant" (bit0 early test, bit1 warp
+ * aggregation, bit2 L1-cached test), "zmin_unroll", "blend_variant", "blend_unroll",
+ * "force_generic", "keep_masks", "timing", "key64". */
+int rtr_set_option(rtr_renderer* r, const char* key, int64_t value);
+int64_t rtr_get_option(const rtr_renderer* r, const char* key);
+/* With option timing=1: CUDA-event ms of the last frame's stages
+ * {clear, zmin, blend, resolve+pyramid, up-pass, total}. */
+int rtr_get_stage_ms(rtr_renderer* r, float* ms6);
+/* Number of kernel launches issued by this renderer since creation. */
+uint64_t rtr_launch_count(const rtr_renderer* r);
+
+/* ---- point-sharded multi-GPU (one process per GPU; plumbing by the caller, e.g. torch.distributed).
+ * rtr_comm_unique_id fills a 128-byte NCCL id on rank 0; broadcast it, then every rank calls
+ * rtr_comm_init.  With a communicator attached, rendering merges the per-GPU z-buffers with
+ * ncclAllReduce(min) and the colour sums with ncclAllReduce(sum) so every rank holds the result a
+ * single GPU with all points would produce (bit-identical: integer min / integer add). */
+int rtr_comm_unique_id(void* id128);
+int rtr_comm_init(rtr_renderer* r, const void* id128, int rank, int n_ranks);
+int rtr_comm_destroy(rtr_renderer* r);
+
+const char* rtr_version(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTR_B200_H */

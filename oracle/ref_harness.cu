@@ -1,0 +1,184 @@
+// TEST INFRASTRUCTURE — GPU oracle.  Not part of the product; nothing under the package links this.
+//
+// C-ABI shim around the UNMODIFIED reference renderer.  oracle/Makefile compiles the reference's
+// own translation units where they lie under /root/reference/src/RTRenderer/src
+// (render.cu, project_cloud.cu, CameraCalibration.cpp) against the stand-in glm/OpenCV headers in
+// oracle/stubs/, and links them with this file into oracle/_ref/libref_rtrenderer.so.
+// Everything that is computed here is computed by the reference's own code:
+//   ProjectCloud::ProjectCloud            project_cloud.cu:189-251
+//   ProjectCloud::computeRGBD             project_cloud.cu:268-312
+//   ProjectCloud::computeFilteredRGBD     project_cloud.cu:394-434
+//   minDepthPass / accumulatePass / ...   render.cu:53-163   (for per-kernel timing)
+// This file only (a) builds the `unordered_map<int, OctreeGrid::Block>` the constructor wants,
+// (b) copies the reference object's private device buffers out for stage-by-stage comparison and
+// (c) times the reference kernels with CUDA events using the reference's own launch geometry.
+#include <cuda_runtime.h>
+#include <torch/script.h>
+#include <torch/cuda.h>
+
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <unordered_map>
+#include <vector>
+
+#include "opencv2/core.hpp"
+
+// The reference keeps its device buffers private; the oracle needs to read them.
+#define private public
+#include "project_cloud.h"
+#undef private
+#include "render.cuh"
+
+// cv::Mat::convertTo stand-in: the one conversion computeFull performs (project_cloud.cu:480),
+// CV_16FC3 -> CV_8UC3 with scale alpha, OpenCV semantics = saturate_cast<uchar>(cvRound(v*alpha)).
+void cv::Mat::convertTo(cv::Mat& dst, int rtype, double alpha) const {
+    if (type_ != CV_16FC3 || rtype != CV_8UC3) return;
+    if (dst.rows != rows || dst.cols != cols || dst.type_ != rtype) dst = cv::Mat(cv::Size(cols, rows), rtype);
+    const at::Half* s = ptr<at::Half>();
+    uint8_t* d = dst.ptr<uint8_t>();
+    for (size_t i = 0; i < size_t(rows) * cols * 3; ++i) {
+        double v = double(float(s[i])) * alpha;
+        long r = lrint(v);  // round-half-even, like cvRound
+        d[i] = uint8_t(r < 0 ? 0 : r > 255 ? 255 : r);
+    }
+}
+
+extern "C" cudaError_t rtr_ref_zero_malloc(void** p, size_t bytes) {
+#undef cudaMalloc
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess && bytes) e = cudaMemset(*p, 0, bytes);
+    return e;
+}
+
+namespace {
+struct RefHandle {
+    ProjectCloud* pc = nullptr;
+    size_t n = 0;
+};
+
+CameraCalibration make_calib(int W, int H, const double* K9) {
+    CameraCalibration c;
+    cv::Matx33d K;
+    for (int i = 0; i < 9; ++i) K.val[i] = K9[i];
+    c.setIntrinsicsMatrix(K);
+    c.setWidth(W);
+    c.setHeight(H);
+    return c;
+}
+cv::Matx44d make_E(const double* E16) {
+    cv::Matx44d E;
+    for (int i = 0; i < 16; ++i) E.val[i] = E16[i];
+    return E;
+}
+}  // namespace
+
+extern "C" {
+
+// xyz: n*3 float32, bgr: n*3 uint8 (the order OctreeGrid::Block::colors holds, cloudreader.cpp:168).
+// The whole cloud goes into one Block so the flattened order equals the input order
+// (Octreegrid.h:162-180 iterates blocks, then points).
+void* ref_create(const float* xyz, const uint8_t* bgr, size_t n) {
+    std::unordered_map<int, OctreeGrid::Block> grid;
+    OctreeGrid::Block& b = grid[0];
+    b.positions.resize(n);
+    b.colors.resize(n);
+    std::memcpy(static_cast<void*>(b.positions.data()), xyz, n * 3 * sizeof(float));
+    std::memcpy(static_cast<void*>(b.colors.data()), bgr, n * 3);
+    // The constructor chats on stdout/stderr (project_cloud.cu:219-250); keep our stdout clean.
+    std::ostringstream sink;
+    std::streambuf* o = std::cout.rdbuf(sink.rdbuf());
+    std::streambuf* e = std::cerr.rdbuf(sink.rdbuf());
+    RefHandle* h = new RefHandle;
+    h->pc = new ProjectCloud(grid, std::string(""));
+    h->n = n;
+    std::cout.rdbuf(o);
+    std::cerr.rdbuf(e);
+    return h;
+}
+
+void ref_destroy(void* hv) {
+    RefHandle* h = static_cast<RefHandle*>(hv);
+    if (!h) return;
+    delete h->pc;
+    delete h;
+}
+
+int ref_block_size(void* hv) { return static_cast<RefHandle*>(hv)->pc->block_size; }
+
+// color: H*W*3 uint8 or null, depth: H*W float or null.  Returns the reference's return value.
+int ref_compute_rgbd(void* hv, int W, int H, const double* K9, const double* E16, uint8_t* color, float* depth) {
+    RefHandle* h = static_cast<RefHandle*>(hv);
+    CameraCalibration c = make_calib(W, H, K9);
+    cv::Mat mc(H, W, CV_8UC3, color), md(H, W, CV_32F, depth);
+    return h->pc->computeRGBD(c, make_E(E16), color ? &mc : nullptr, depth ? &md : nullptr);
+}
+
+int ref_compute_filtered(void* hv, int W, int H, const double* K9, const double* E16, uint8_t* color, float* depth) {
+    RefHandle* h = static_cast<RefHandle*>(hv);
+    CameraCalibration c = make_calib(W, H, K9);
+    cv::Mat mc(H, W, CV_8UC3, color), md(H, W, CV_32F, depth);
+    return h->pc->computeFilteredRGBD(c, make_E(E16), color ? &mc : nullptr, depth ? &md : nullptr);
+}
+
+// Copy one of the reference object's device buffers to host.
+// what: 0 zbuf/depth (P u32)  1 accum (4P u32)  2 image (3P u8)  3 tensor (5P f16)
+//       4 cam_proj (16 f32)   5 final_min (u32) 6 final_max (u32)
+int ref_read(void* hv, int what, void* dst, size_t bytes) {
+    ProjectCloud* p = static_cast<RefHandle*>(hv)->pc;
+    const void* src = nullptr;
+    switch (what) {
+        case 0: src = p->d_output_depth; break;
+        case 1: src = p->d_output_color; break;
+        case 2: src = p->d_image; break;
+        case 3: src = p->tensorPtr; break;
+        case 4: src = p->d_cam_proj; break;
+        case 5: src = p->d_final_min; break;
+        case 6: src = p->d_final_max; break;
+        default: return -1;
+    }
+    cudaDeviceSynchronize();
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : -2;
+}
+
+// Override the camera matrix the NEXT direct kernel launches use (row-major float[16]); lets the
+// parity tests feed both implementations the same raw matrix.
+int ref_set_cam_proj_raw(void* hv, const float* m16) {
+    ProjectCloud* p = static_cast<RefHandle*>(hv)->pc;
+    return cudaMemcpy(p->d_cam_proj, m16, 64, cudaMemcpyHostToDevice) == cudaSuccess ? 1 : -2;
+}
+
+// Launch the reference's point kernels directly (same geometry as project_cloud.cu:316-325) on the
+// buffers of an object that has already rendered one frame at W x H, `iters` times, and report
+// the mean CUDA-event time of each kernel in ms:
+//   ms[0] fillBuffer+memset  ms[1] minDepthPass  ms[2] accumulatePass  ms[3] resolvePass
+int ref_time_point_kernels(void* hv, int W, int H, int iters, float* ms) {
+    ProjectCloud* p = static_cast<RefHandle*>(hv)->pc;
+    if (p->image_size.x != unsigned(W) || p->image_size.y != unsigned(H)) return -1;
+    cudaEvent_t ev[5];
+    for (auto& e : ev) cudaEventCreate(&e);
+    double acc[4] = {0, 0, 0, 0};
+    for (int it = 0; it < iters; ++it) {
+        cudaEventRecord(ev[0]);
+        fillBuffer<<<p->grid_dim, p->block_dim>>>(p->d_output_depth, 0x7F7FFFFF, W * H);
+        cudaMemsetAsync(p->d_output_color, 0, size_t(W) * H * 4 * sizeof(uint32_t));
+        cudaEventRecord(ev[1]);
+        minDepthPass<<<p->numBlocksPCDLevel, p->block_size>>>(p->d_output_depth, p->d_vertices_data, (float*)p->d_cam_proj, p->image_size, p->data_size);
+        cudaEventRecord(ev[2]);
+        accumulatePass<<<p->numBlocksPCDLevel, p->block_size>>>(p->d_vertices_data, p->d_color_data, p->data_size, p->image_size, (float*)p->d_cam_proj, p->d_output_depth, p->d_output_color);
+        cudaEventRecord(ev[3]);
+        resolvePass<<<p->grid_dim, p->block_dim>>>(p->d_image, p->d_output_color, W * H);
+        cudaEventRecord(ev[4]);
+        if (cudaEventSynchronize(ev[4]) != cudaSuccess) return -2;
+        for (int k = 0; k < 4; ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+            acc[k] += t;
+        }
+    }
+    for (int k = 0; k < 4; ++k) ms[k] = float(acc[k] / iters);
+    for (auto& e : ev) cudaEventDestroy(e);
+    return cudaGetLastError() == cudaSuccess ? 1 : -3;
+}
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+// stand-in: see glm/glm.hpp in this directory
+#pragma once
+#include "glm/glm.hpp"

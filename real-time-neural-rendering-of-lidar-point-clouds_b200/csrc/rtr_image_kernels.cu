@@ -1,0 +1,357 @@
+// Image-space kernels of the hot path, hand-written for sm_100a.
+//
+// The reference runs 1 resolve + 18 filter launches with a cudaMalloc/cudaFree pair and a
+// cudaDeviceSynchronize around nearly every one (project_cloud.cu:325, 331-392).  Here:
+//
+//   resolve_pyramid_kernel   resolvePass (render.cu:132-163)
+//                          + reduce x4   (project_cloud.cu:28-53)
+//                          + find_local/overall_minmax (render.cu:168-240)          -> 1 launch
+//   up_level_kernel<false>   laplacianKernel + compareImgsKernel + resizeKernel
+//                            (project_cloud.cu:55-161), levels 4->3, 3->2, 2->1      -> 3 launches
+//   up_level_kernel<true>    laplacianKernel + compareImgsKernel + removeMask
+//                            (project_cloud.cu:55-126, 163-187), level 1->0          -> 1 launch
+//
+// All on persistent scratch, no allocation, no host sync.  Arithmetic follows the reference's
+// compiled op order (see rtr_common.cuh header and DESIGN.md); indexing follows its FLAT,
+// truncated-dims semantics, so 1920x1080 behaves exactly as the reference does
+// under zero-initialised buffers.  The fused resolve/pyramid kernel needs W % 16 == 0 (then every
+// level width is an exact half and the flat pyramid is a true 2-D pyramid); other widths take the
+// generic one-kernel-per-reference-kernel path, which is also the cross-check in the tests.
+#include <cuda_fp16.h>
+
+#include "rtr_kernels.h"
+
+namespace rtr {
+
+__device__ __forceinline__ float sel_min(float a, float b) { return a < b ? a : b; }  // project_cloud.cu:46-49
+
+__device__ __forceinline__ void resolve_px(const uint4 a, uint8_t& b, uint8_t& g, uint8_t& r) {
+    if (a.w == 0u) { b = g = r = 0; return; }  // render.cu:147-154
+    b = uint8_t(a.x / a.w);
+    g = uint8_t(a.y / a.w);
+    r = uint8_t(a.z / a.w);
+}
+
+// ---------------------------------------------------------------- fused resolve + pyramid + min/max
+// One CTA = 256 threads = a 64 x 16 tile of level 0 = 32 x 8 of L1 = 16 x 4 of L2 = 8 x 2 of L3 =
+// 4 x 1 of L4.  Thread (tx, ty) owns the 2x2 quad of level-0 pixels under L1 pixel (tx, ty).
+// Tiles cover rows [0, 16*floor(H/16)): exactly resolvePass's / the min-max's coverage when
+// W % 16 == 0, and every pyramid row the up-pass can read (uh[i] = 16*floor(H/16) >> i).
+template <bool PYRAMID, bool RESOLVE>
+__global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __restrict__ zbuf,
+                                                              const uint4* __restrict__ accum,
+                                                              uint8_t* __restrict__ image, float* __restrict__ l1,
+                                                              float* __restrict__ l2, float* __restrict__ l3,
+                                                              float* __restrict__ l4, uint32_t* __restrict__ minmax,
+                                                              int W) {
+    __shared__ float s1[8][33];
+    __shared__ float s2[4][17];
+    __shared__ float s3[2][9];
+    __shared__ uint32_t smin[8], smax[8];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int X1 = blockIdx.x * 32 + tx, Y1 = blockIdx.y * 8 + ty;
+    const int w1 = W >> 1;
+    const bool in = X1 < w1;
+    float v1 = __uint_as_float(kEmptyDepthBits);
+    uint32_t tmin = 0xFFFFFFFFu, tmax = 0u;
+    if (in) {
+        const size_t p0 = size_t(2 * Y1) * W + 2 * X1, p1 = p0 + W;
+        const uint2 z0 = *reinterpret_cast<const uint2*>(zbuf + p0);
+        const uint2 z1 = *reinterpret_cast<const uint2*>(zbuf + p1);
+        if constexpr (RESOLVE) {
+            const uint4 a00 = accum[p0], a01 = accum[p0 + 1], a10 = accum[p1], a11 = accum[p1 + 1];
+            uint8_t c[12];
+            resolve_px(a00, c[0], c[1], c[2]);
+            resolve_px(a01, c[3], c[4], c[5]);
+            resolve_px(a10, c[6], c[7], c[8]);
+            resolve_px(a11, c[9], c[10], c[11]);
+            uint16_t* o0 = reinterpret_cast<uint16_t*>(image + p0 * 3);  // p0 is even -> 2-byte aligned
+            uint16_t* o1 = reinterpret_cast<uint16_t*>(image + p1 * 3);
+            o0[0] = uint16_t(c[0] | (c[1] << 8)); o0[1] = uint16_t(c[2] | (c[3] << 8)); o0[2] = uint16_t(c[4] | (c[5] << 8));
+            o1[0] = uint16_t(c[6] | (c[7] << 8)); o1[1] = uint16_t(c[8] | (c[9] << 8)); o1[2] = uint16_t(c[10] | (c[11] << 8));
+        }
+        if constexpr (PYRAMID) {
+            const uint32_t zz[4] = {z0.x, z0.y, z1.x, z1.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (zz[k] != kEmptyDepthBits) { tmin = min(tmin, zz[k]); tmax = max(tmax, zz[k]); }  // render.cu:181-184
+            v1 = sel_min(sel_min(__uint_as_float(z0.x), __uint_as_float(z0.y)),
+                         sel_min(__uint_as_float(z1.x), __uint_as_float(z1.y)));
+            l1[size_t(Y1) * w1 + X1] = v1;
+        }
+    }
+    if constexpr (!PYRAMID) return;
+    s1[ty][tx] = v1;
+    tmin = __reduce_min_sync(0xFFFFFFFFu, tmin);
+    tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+    if (tx == 0) { smin[ty] = tmin; smax[ty] = tmax; }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < 64) {
+        const int x = t & 15, y = t >> 4;
+        const float v = sel_min(sel_min(s1[2 * y][2 * x], s1[2 * y][2 * x + 1]), sel_min(s1[2 * y + 1][2 * x], s1[2 * y + 1][2 * x + 1]));
+        s2[y][x] = v;
+        const int X = blockIdx.x * 16 + x, w2 = W >> 2;
+        if (X < w2) l2[size_t(blockIdx.y * 4 + y) * w2 + X] = v;
+    }
+    if (t == 64) {
+        uint32_t mn = smin[0], mx = smax[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { mn = min(mn, smin[k]); mx = max(mx, smax[k]); }
+        if (mn != 0xFFFFFFFFu) {  // at least one valid pixel in the tile
+            atomicMin(minmax + 0, mn);
+            atomicMax(minmax + 1, mx);
+        }
+    }
+    __syncthreads();
+    if (t < 16) {
+        const int x = t & 7, y = t >> 3;
+        const float v = sel_min(sel_min(s2[2 * y][2 * x], s2[2 * y][2 * x + 1]), sel_min(s2[2 * y + 1][2 * x], s2[2 * y + 1][2 * x + 1]));
+        s3[y][x] = v;
+        const int X = blockIdx.x * 8 + x, w3 = W >> 3;
+        if (X < w3) l3[size_t(blockIdx.y * 2 + y) * w3 + X] = v;
+    }
+    __syncthreads();
+    if (t < 4) {
+        const float v = sel_min(sel_min(s3[0][2 * t], s3[0][2 * t + 1]), sel_min(s3[1][2 * t], s3[1][2 * t + 1]));
+        const int X = blockIdx.x * 4 + t, w4 = W >> 4;
+        if (X < w4) l4[size_t(blockIdx.y) * w4 + X] = v;
+    }
+}
+
+// ---------------------------------------------------------------- generic (any W, H) restatements
+__global__ void __launch_bounds__(256) resolve_generic_kernel(const uint4* __restrict__ accum,
+                                                              uint8_t* __restrict__ image, uint64_t cov) {
+    const uint64_t id = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (id >= cov) return;
+    uint8_t b, g, r;
+    resolve_px(accum[id], b, g, r);
+    image[id * 3 + 0] = b; image[id * 3 + 1] = g; image[id * 3 + 2] = r;
+}
+
+__global__ void __launch_bounds__(256) minmax_generic_kernel(const uint32_t* __restrict__ zbuf, uint64_t count,
+                                                             uint32_t* __restrict__ minmax) {
+    __shared__ uint32_t smin[8], smax[8];
+    uint32_t tmin = 0xFFFFFFFFu, tmax = 0u;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t v = zbuf[i];
+        if (v != kEmptyDepthBits) { tmin = min(tmin, v); tmax = max(tmax, v); }
+    }
+    tmin = __reduce_min_sync(0xFFFFFFFFu, tmin);
+    tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = tmin; smax[threadIdx.x >> 5] = tmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { tmin = min(tmin, smin[k]); tmax = max(tmax, smax[k]); }
+        if (tmin != 0xFFFFFFFFu) { atomicMin(minmax + 0, tmin); atomicMax(minmax + 1, tmax); }
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_generic_kernel(const float* __restrict__ hi, float* __restrict__ lo,
+                                                             int w, int h) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= w * h) return;
+    const int x = idx % w, y = idx / w, wh = w * 2;
+    const float* r0 = hi + size_t(2 * y) * wh + 2 * x;
+    const float* r1 = r0 + wh;
+    lo[idx] = sel_min(sel_min(r0[0], r0[1]), sel_min(r1[0], r1[1]));
+}
+
+// ---------------------------------------------------------------- up-pass, one level per launch
+__device__ __forceinline__ float lo_or_m1(const float* __restrict__ lo, int x, int y, int w, int h) {
+    return (x >= 0 && x < w && y >= 0 && y < h) ? lo[y * w + x] : -1.0f;  // getPixelValue, project_cloud.cu:81-86
+}
+
+// bilinear hole fill of one fine pixel (resizeKernel, project_cloud.cu:135-160; op order from SASS)
+__device__ __forceinline__ float bilinear_up(const float* __restrict__ lo, int lw, int lh, int x, int y) {
+    const float inX = __fmaf_rn(__fadd_rn(float(x), 0.5f), 0.5f, -0.5f);
+    const float inY = __fmaf_rn(__fadd_rn(float(y), 0.5f), 0.5f, -0.5f);
+    int x0 = __float2int_rd(inX), y0 = __float2int_rd(inY);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = x0 < 0 ? 0 : (x0 >= lw ? lw - 1 : x0);
+    x1 = x1 < 0 ? 0 : (x1 >= lw ? lw - 1 : x1);
+    y0 = y0 < 0 ? 0 : (y0 >= lh ? lh - 1 : y0);
+    y1 = y1 < 0 ? 0 : (y1 >= lh ? lh - 1 : y1);
+    const float wx = __fsub_rn(inX, float(x0)), wy = __fsub_rn(inY, float(y0));
+    const float omx = __fsub_rn(1.0f, wx);
+    const float v0 = __fmaf_rn(wx, lo[y0 * lw + x1], __fmul_rn(omx, lo[y0 * lw + x0]));
+    const float v1 = __fmaf_rn(wx, lo[y1 * lw + x1], __fmul_rn(omx, lo[y1 * lw + x0]));
+    return __fmaf_rn(v0, __fsub_rn(1.0f, wy), __fmul_rn(wy, v1));
+}
+
+__device__ __forceinline__ uint16_t h_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+// (c10::Half)v / d  ->  half( float(half(v)) / d )   (project_cloud.cu:181-185)
+__device__ __forceinline__ uint16_t half_div(float v, float d) {
+    return h_bits(__fdiv_rn(__half2float(__float2half_rn(v)), d));
+}
+
+// Each thread owns two horizontally adjacent fine pixels (2*lx, 2*lx+1) of row hy: they share the
+// coarse parent (lx, hy/2), its 3x3 neighbourhood, the Laplacian and all store vectorisation.
+// lo = L_i indexed with (lw, lh) = up-pass dims of level i; hi = L_{i-1} indexed with (2lw, 2lh).
+template <bool FINAL>
+__global__ void __launch_bounds__(256) up_level_kernel(const float* __restrict__ lo, int lw, int lh,
+                                                       float* __restrict__ hi, uint8_t* __restrict__ mask_tap,
+                                                       uint8_t* __restrict__ image, uint16_t* __restrict__ tensor,
+                                                       const uint32_t* __restrict__ minmax) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    const int hh = lh * 2, hw = lw * 2;
+    if (pair >= lw * hh) return;
+    const int lx = pair % lw, hy = pair / lw, ly = hy >> 1;
+    const size_t idx = size_t(hy) * hw + 2 * lx;
+    const float2 cur2 = *reinterpret_cast<const float2*>(hi + idx);
+    const float cur[2] = {cur2.x, cur2.y};
+    const float thr = __uint_as_float(kMaxFloatThresholdBits);
+    const bool cand[2] = {!(cur[0] >= thr), !(cur[1] >= thr)};  // `if (currentVal >= MAX_FLOAT) mask = 0`
+    bool keep[2] = {false, false};
+    if (cand[0] || cand[1]) {
+        const bool border = (lx == 0 || lx == lw - 1 || ly == 0 || ly == lh - 1);  // laplacianKernel border -> 0
+        bool edge = false;
+        float nb[9];
+        if (!border) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) nb[k] = lo[(ly + k / 3 - 1) * lw + (lx + k % 3 - 1)];
+            // sum += in[k] * laplaceKernel[k], k row-major, all nine taps, FMA-contracted (SASS)
+            float sum = 0.0f;
+            sum = __fmaf_rn(nb[0], 0.0f, sum);
+            sum = __fmaf_rn(nb[1], 1.0f, sum);
+            sum = __fmaf_rn(nb[2], 0.0f, sum);
+            sum = __fmaf_rn(nb[3], 1.0f, sum);
+            sum = __fmaf_rn(nb[4], -4.0f, sum);
+            sum = __fmaf_rn(nb[5], 1.0f, sum);
+            sum = __fmaf_rn(nb[6], 0.0f, sum);
+            sum = __fmaf_rn(nb[7], 1.0f, sum);
+            sum = __fmaf_rn(nb[8], 0.0f, sum);
+            edge = sum > kGradientFilter;
+        }
+        if (edge) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float lim = __fmul_rn(nb[k], kFilterStrength);
+                keep[0] = keep[0] || (cur[0] <= lim);
+                keep[1] = keep[1] || (cur[1] <= lim);
+            }
+        } else {
+            const float lim = __fmul_rn(lo_or_m1(lo, lx, ly, lw, lh), kFilterStrength);
+            keep[0] = cur[0] <= lim;
+            keep[1] = cur[1] <= lim;
+        }
+        keep[0] = keep[0] && cand[0];
+        keep[1] = keep[1] && cand[1];
+    }
+    if (mask_tap) *reinterpret_cast<uint16_t*>(mask_tap + idx) = uint16_t((keep[0] ? 0xFFu : 0u) | (keep[1] ? 0xFF00u : 0u));
+    if constexpr (!FINAL) {
+        if (keep[0] && keep[1]) return;
+        float2 out = cur2;
+        if (!keep[0]) out.x = bilinear_up(lo, lw, lh, 2 * lx, hy);
+        if (!keep[1]) out.y = bilinear_up(lo, lw, lh, 2 * lx + 1, hy);
+        *reinterpret_cast<float2*>(hi + idx) = out;
+    } else {
+        // removeMask (project_cloud.cu:163-187); tensor plane stride = hw*hh (the truncated dims).
+        const size_t plane = size_t(hw) * hh;
+        const float dmin = __uint_as_float(minmax[0]), dmax = __uint_as_float(minmax[1]);
+        const float range = __fsub_rn(dmax, dmin);
+        uint16_t* img2 = reinterpret_cast<uint16_t*>(image + idx * 3);  // idx even -> 2-byte aligned
+        const uint16_t i0 = img2[0], i1 = img2[1], i2 = img2[2];
+        uint8_t c[6] = {uint8_t(i0 & 0xFF), uint8_t(i0 >> 8), uint8_t(i1 & 0xFF), uint8_t(i1 >> 8), uint8_t(i2 & 0xFF), uint8_t(i2 >> 8)};
+        uint16_t t[5][2];
+        float2 dout = cur2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (!keep[j]) {
+                (j == 0 ? dout.x : dout.y) = -1.0f;
+                c[3 * j] = c[3 * j + 1] = c[3 * j + 2] = 0;
+                t[0][j] = t[1][j] = t[2][j] = t[3][j] = 0;
+                t[4][j] = 0xBC00u;  // -1.0h
+            } else {
+                t[0][j] = half_div(float(c[3 * j + 0]), 255.0f);
+                t[1][j] = half_div(float(c[3 * j + 1]), 255.0f);
+                t[2][j] = half_div(float(c[3 * j + 2]), 255.0f);
+                t[3][j] = half_div(255.0f, 255.0f);
+                t[4][j] = half_div(__fsub_rn(cur[j], dmin), range);
+            }
+        }
+        if (!(keep[0] && keep[1])) {
+            *reinterpret_cast<float2*>(hi + idx) = dout;
+            img2[0] = uint16_t(c[0] | (c[1] << 8)); img2[1] = uint16_t(c[2] | (c[3] << 8)); img2[2] = uint16_t(c[4] | (c[5] << 8));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            *reinterpret_cast<uint32_t*>(tensor + plane * k + idx) = uint32_t(t[k][0]) | (uint32_t(t[k][1]) << 16);
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+cudaError_t launch_resolve_pyramid(cudaStream_t s, const FrameBuffers& fb, int W, int H, const PyramidDims& d,
+                                   bool pyramid, bool resolve, bool force_generic) {
+    const uint64_t cov = clear_coverage(W, H);
+    if (cov == 0 || (!pyramid && !resolve)) return cudaSuccess;
+    const uint4* acc = reinterpret_cast<const uint4*>(fb.accum);
+    if ((W % 16) == 0 && !force_generic) {
+        dim3 grid((W + 63) / 64, H / 16);
+        if (pyramid && resolve)
+            resolve_pyramid_kernel<true, true><<<grid, 256, 0, s>>>(fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W);
+        else if (pyramid)
+            resolve_pyramid_kernel<true, false><<<grid, 256, 0, s>>>(fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W);
+        else
+            resolve_pyramid_kernel<false, true><<<grid, 256, 0, s>>>(fb.zbuf, acc, fb.image, nullptr, nullptr, nullptr, nullptr, fb.minmax, W);
+        return cudaGetLastError();
+    }
+    if (resolve) resolve_generic_kernel<<<unsigned((cov + 255) / 256), 256, 0, s>>>(acc, fb.image, cov);
+    if (pyramid) {
+        const uint64_t count = uint64_t(d.uw[0]) * d.uh[0];
+        const uint64_t mm_blocks = (count + 255) / 256;
+        if (count) minmax_generic_kernel<<<unsigned(mm_blocks < 148 * 8 ? mm_blocks : 148 * 8), 256, 0, s>>>(fb.zbuf, count, fb.minmax);
+        for (int i = 1; i <= 4; ++i) {
+            const int n = d.w[i] * d.h[i];
+            if (n) reduce_generic_kernel<<<(n + 255) / 256, 256, 0, s>>>(fb.level[i - 1], fb.level[i], d.w[i], d.h[i]);
+        }
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- 64-bit key mode (north_star variant)
+// zkey[p] = (depth bits << 32) | point index.  Splits the key back into the reference-identical
+// depth buffer and a NEAREST-point colour (not the reference's 2 cm average: opt-in, non-parity).
+__global__ void __launch_bounds__(256) clear_key64_kernel(unsigned long long* __restrict__ zkey, uint64_t cov) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cov; i += uint64_t(gridDim.x) * blockDim.x)
+        zkey[i] = (static_cast<unsigned long long>(kEmptyDepthBits) << 32) | 0xFFFFFFFFull;
+}
+__global__ void __launch_bounds__(256) resolve_key64_kernel(const unsigned long long* __restrict__ zkey,
+                                                            const PointRecord* __restrict__ pts, uint64_t index_base,
+                                                            uint64_t n_local, uint32_t* __restrict__ zbuf,
+                                                            uint8_t* __restrict__ image, uint64_t n_px, uint64_t cov) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const unsigned long long key = zkey[i];
+    zbuf[i] = uint32_t(key >> 32);
+    if (i >= cov) return;  // resolvePass coverage
+    uint32_t c = 0u;
+    const uint64_t idx = uint64_t(uint32_t(key)) - index_base;  // points of another shard resolve to 0 here
+    if (uint32_t(key >> 32) != kEmptyDepthBits && idx < n_local) c = pts[idx].bgra;
+    image[i * 3 + 0] = uint8_t(c); image[i * 3 + 1] = uint8_t(c >> 8); image[i * 3 + 2] = uint8_t(c >> 16);
+}
+cudaError_t launch_clear_key64(cudaStream_t s, int sm_count, unsigned long long* zkey, uint64_t cov) {
+    if (cov) clear_key64_kernel<<<sm_count * 4, 256, 0, s>>>(zkey, cov);
+    return cudaGetLastError();
+}
+cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey, const PointRecord* pts,
+                                 uint64_t index_base, uint64_t n_local, uint32_t* zbuf, uint8_t* image, uint64_t n_px,
+                                 uint64_t cov) {
+    if (n_px) resolve_key64_kernel<<<unsigned((n_px + 255) / 256), 256, 0, s>>>(zkey, pts, index_base, n_local, zbuf, image, n_px, cov);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool /*force_generic*/) {
+    for (int i = 4; i >= 1; --i) {
+        const int pairs = d.uw[i] * d.uh[i] * 2;  // fine pixels / 2
+        if (pairs == 0) continue;
+        const unsigned grid = (pairs + 255) / 256;
+        if (i > 1)
+            up_level_kernel<false><<<grid, 256, 0, s>>>(fb.level[i], d.uw[i], d.uh[i], fb.level[i - 1], fb.mask[i - 1], nullptr, nullptr, fb.minmax);
+        else
+            up_level_kernel<true><<<grid, 256, 0, s>>>(fb.level[1], d.uw[1], d.uh[1], fb.level[0], fb.mask[0], fb.image, fb.tensor, fb.minmax);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace rtr

@@ -1,0 +1,67 @@
+// Host-callable launchers of the sm_100a kernels (definitions in rtr_point_kernels.cu,
+// rtr_image_kernels.cu, rtr_synth.cu).  Every launcher only enqueues on `s` and returns the launch
+// status; nothing here synchronises.
+#pragma once
+#include "rtr_common.cuh"
+
+namespace rtr {
+
+constexpr int kPointBlock = 256;  // threads per CTA of the two point passes
+
+// Pyramid geometry exactly as applyDepthFilter derives it (project_cloud.cu:336-362): true level
+// dims are halved (floor) four times on the way down, the up-pass re-doubles the level-4 dims.
+struct PyramidDims {
+    int w[5], h[5];    // true dims of L_0..L_4 (w[0] = W, h[0] = H); buffers are w[i]*h[i] floats
+    int uw[5], uh[5];  // dims the up-pass indexes level i with: uw[4] = w[4], uw[i] = 2*uw[i+1]
+};
+inline PyramidDims make_pyramid_dims(int W, int H) {
+    PyramidDims d;
+    d.w[0] = W; d.h[0] = H;
+    for (int i = 1; i <= 4; ++i) { d.w[i] = d.w[i - 1] / 2; d.h[i] = d.h[i - 1] / 2; }
+    d.uw[4] = d.w[4]; d.uh[4] = d.h[4];
+    for (int i = 3; i >= 0; --i) { d.uw[i] = d.uw[i + 1] * 2; d.uh[i] = d.uh[i + 1] * 2; }
+    return d;
+}
+inline uint64_t clear_coverage(int W, int H) {  // fillBuffer/resolvePass grid: (W/16)*(H/16) blocks of 256
+    uint64_t c = uint64_t(W / 16) * uint64_t(H / 16) * 256u, p = uint64_t(W) * H;
+    return c < p ? c : p;
+}
+
+// ---- point passes (rtr_point_kernels.cu)
+cudaError_t launch_clear(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum, uint64_t n_px,
+                         uint32_t* minmax);
+cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
+                        uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
+cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
+                         const ProjParams& pp, const uint32_t* zbuf, uint32_t* accum);
+cudaError_t launch_project_dump(cudaStream_t s, const PointRecord* pts, uint64_t n, const ProjParams& pp,
+                                int32_t* pix_out, uint32_t* zbits_out);
+
+// ---- image-space passes (rtr_image_kernels.cu)
+struct FrameBuffers {
+    uint32_t* zbuf;      // P u32 depth bits; viewed as float = pyramid level 0; filtered in place
+    uint32_t* accum;     // 4P u32
+    uint8_t* image;      // 3P u8 BGR interleaved
+    uint16_t* tensor;    // 5P fp16, planes of stride uw[0]*uh[0]
+    float* level[5];     // level[0] aliases zbuf; level[1..4] persistent scratch
+    uint8_t* mask[4];    // optional taps: mask[i-1] produced by up-pass iteration i (nullptr = not kept)
+    uint32_t* minmax;    // {min, max} of the valid depth bits
+    unsigned long long* zkey;  // P u64, only in key64 mode
+};
+// accum -> image over [0, cov) (resolvePass), fused with the 4-level min pyramid (reduce x4) and the
+// depth min/max (find_*_minmax_kernel).  `pyramid` = false for plain computeRGBD.
+cudaError_t launch_resolve_pyramid(cudaStream_t s, const FrameBuffers& fb, int W, int H, const PyramidDims& d,
+                                   bool pyramid, bool resolve, bool force_generic);
+// 64-bit key mode: clear / split keys into depth bits + nearest-point colour.
+cudaError_t launch_clear_key64(cudaStream_t s, int sm_count, unsigned long long* zkey, uint64_t cov);
+cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey, const PointRecord* pts,
+                                 uint64_t index_base, uint64_t n_local, uint32_t* zbuf, uint8_t* image, uint64_t n_px,
+                                 uint64_t cov);
+// up-pass: laplacian + compare (+ resize | + removeMask) per level, 4 launches.
+cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool force_generic);
+
+// ---- synthetic cloud on the device (rtr_synth.cu; bench/test support, same generator as the oracle)
+cudaError_t launch_synth(cudaStream_t s, uint64_t seed, uint64_t n_total, uint64_t first, uint64_t count, int lx,
+                         int ly, int lz, int nbox, PointRecord* out);
+
+}  // namespace rtr

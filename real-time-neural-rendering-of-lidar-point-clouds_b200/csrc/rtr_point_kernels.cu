@@ -1,0 +1,264 @@
+// Point-level kernels of the hot path, hand-written for sm_100a.
+//
+//   clear_kernel   <- fillBuffer (render.cu:16-31) + cudaMemset (project_cloud.cu:316-317)
+//   zmin_kernel    <- minDepthPass   (render.cu:53-83)
+//   blend_kernel   <- accumulatePass (render.cu:85-130)
+//
+// Both point passes stream the packed 16-byte {x,y,z,bgra} record with one 128-bit no-allocate
+// load per point, UNROLL independent loads in flight per thread, project in registers with the
+// camera in the constant bank (kernel parameter), and touch the L2-resident frame buffers only for
+// points that survive culling.  HBM-bound by design: 16 B/point/pass.
+//
+// Z-min atomics.  min is idempotent and monotone, so three exact optimisations are legal:
+//  (1) early depth test: a plain (possibly stale) load of the z-buffer value; a point that is not
+//      strictly nearer than a value the pixel has already reached can never lower it;
+//  (2) warp aggregation (match.any on the pixel id, redux.min on the depth bits) — what the
+//      reference does for every in-frustum point, here only for the survivors of (1);
+//  (3) red.global.min (no return value).
+// Which combination is fastest depends on point order; `variant` selects it at run time
+// (rtr_set_option "zmin_variant"), default chosen from measurements.
+#include "rtr_kernels.h"
+
+namespace rtr {
+
+// ---------------------------------------------------------------- clear
+// zbuf[0, cov) = FLT_MAX bits ; accum[0, 4P) = 0 ; minmax = {UINT_MAX, 0}.
+__global__ void __launch_bounds__(256) clear_kernel(uint32_t* __restrict__ zbuf, uint64_t cov,
+                                                    uint4* __restrict__ accum, uint64_t n_px,
+                                                    uint32_t* __restrict__ minmax) {
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    if (tid == 0) {
+        minmax[0] = 0xFFFFFFFFu;
+        minmax[1] = 0u;
+    }
+    if (accum) {
+        for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const uint64_t cov4 = cov >> 2;
+    uint4* z4 = reinterpret_cast<uint4*>(zbuf);
+    for (uint64_t i = tid; i < cov4; i += stride)
+        z4[i] = make_uint4(kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits);
+    for (uint64_t i = (cov4 << 2) + tid; i < cov; i += stride) zbuf[i] = kEmptyDepthBits;
+}
+
+// ---------------------------------------------------------------- z-min
+// variant bit 0: early depth test   bit 1: warp aggregation   bit 2: early test through L1 (ld.ca)
+template <int UNROLL, int VARIANT, bool DISTORT, int KEY64>
+__global__ void __launch_bounds__(kPointBlock) zmin_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                           uint64_t index_base,
+                                                           const __grid_constant__ ProjParams pp,
+                                                           uint32_t* __restrict__ zbuf,
+                                                           unsigned long long* __restrict__ zkey) {
+    const uint64_t base = uint64_t(blockIdx.x) * (kPointBlock * UNROLL) + threadIdx.x;
+    // phase 1: UNROLL independent 128-bit loads in flight (tail lanes re-read the last record)
+    PointRecord p[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint64_t idx = base + uint64_t(u) * kPointBlock;
+        p[u] = ld_point_stream(pts + (idx < n ? idx : n - 1));
+    }
+    // phase 2: project, branch-free
+    uint32_t pix[UNROLL], dbits[UNROLL];
+    bool live[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        float depth;
+        live[u] = project<DISTORT>(pp, p[u].x, p[u].y, p[u].z, pix[u], depth) &
+                  (base + uint64_t(u) * kPointBlock < n);
+        dbits[u] = __float_as_uint(depth);
+    }
+    if constexpr (KEY64) {
+        // north_star's deterministic 64-bit key: (depth bits << 32) | global point index.
+        unsigned long long key[UNROLL], cur[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            key[u] = (static_cast<unsigned long long>(dbits[u]) << 32) |
+                     static_cast<unsigned long long>(uint32_t(index_base + base + uint64_t(u) * kPointBlock));
+            cur[u] = ~0ull;
+            if ((VARIANT & 1) && live[u]) cur[u] = (VARIANT & 4) ? __ldca(zkey + pix[u]) : __ldcg(zkey + pix[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (live[u] && key[u] < cur[u]) atomicMin(zkey + pix[u], key[u]);
+    } else {
+        // phase 3: early depth test, UNROLL gathers in flight
+        uint32_t cur[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            cur[u] = 0xFFFFFFFFu;
+            if ((VARIANT & 1) && live[u]) cur[u] = (VARIANT & 4) ? __ldca(zbuf + pix[u]) : __ldcg(zbuf + pix[u]);
+        }
+        // phase 4: RED.MIN for the survivors
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (live[u] && dbits[u] < cur[u]) {
+                if constexpr (VARIANT & 2) {
+                    const unsigned same = __match_any_sync(__activemask(), pix[u]);
+                    const uint32_t mn = __reduce_min_sync(same, dbits[u]);
+                    // one lane per (warp, pixel) group issues the RED
+                    const unsigned winners = __ballot_sync(same, dbits[u] == mn) & same;
+                    if ((threadIdx.x & 31) == (__ffs(winners) - 1)) atomicMin(zbuf + pix[u], mn);
+                } else {
+                    atomicMin(zbuf + pix[u], dbits[u]);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- blend (2 cm depth-window colour sums)
+// accum[pix] = {sum b, sum g, sum r, count} as 4 x u32 — the reference's layout.  The four u32
+// atomicAdds per (warp, pixel) group of the reference become two 64-bit RED.ADDs on the same
+// memory: (b | g<<32) and (r | count<<32).  Identical bits as long as no 32-bit channel sum wraps
+// (> 16.8 M points in one pixel; the reference wraps silently there, this carries — documented).
+// variant bit 1: warp aggregation (match.any + redux.add), as the reference does.
+template <int UNROLL, int VARIANT, bool DISTORT>
+__global__ void __launch_bounds__(kPointBlock) blend_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                            const __grid_constant__ ProjParams pp,
+                                                            const uint32_t* __restrict__ zbuf,
+                                                            unsigned long long* __restrict__ accum2) {
+    const uint64_t base = uint64_t(blockIdx.x) * (kPointBlock * UNROLL) + threadIdx.x;
+    PointRecord p[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint64_t idx = base + uint64_t(u) * kPointBlock;
+        p[u] = ld_point_stream(pts + (idx < n ? idx : n - 1));
+    }
+    uint32_t pix[UNROLL];
+    float depth[UNROLL];
+    bool live[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+        live[u] = project<DISTORT>(pp, p[u].x, p[u].y, p[u].z, pix[u], depth[u]) &
+                  (base + uint64_t(u) * kPointBlock < n);
+    uint32_t zmin[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        zmin[u] = 0u;
+        if (live[u]) zmin[u] = __ldg(zbuf + pix[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const float lim = __fadd_rn(__uint_as_float(zmin[u]), kDepthWindow);
+        if (live[u] && !(depth[u] > lim)) {  // render.cu:106 (NaN depth is accepted, as there)
+            uint32_t b = p[u].bgra & 0xFFu, g = (p[u].bgra >> 8) & 0xFFu, r = (p[u].bgra >> 16) & 0xFFu, c = 1u;
+            if constexpr (VARIANT & 2) {
+                const unsigned same = __match_any_sync(__activemask(), pix[u]);
+                b = __reduce_add_sync(same, b);
+                g = __reduce_add_sync(same, g);
+                r = __reduce_add_sync(same, r);
+                c = __popc(same);
+                if ((threadIdx.x & 31) != (__ffs(same) - 1)) continue;
+            }
+            unsigned long long* a = accum2 + uint64_t(pix[u]) * 2;
+            atomicAdd(a + 0, static_cast<unsigned long long>(b) | (static_cast<unsigned long long>(g) << 32));
+            atomicAdd(a + 1, static_cast<unsigned long long>(r) | (static_cast<unsigned long long>(c) << 32));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- per-point projection dump (tests)
+// Writes (pix or -1, depth bits) for every point: the "hybrid golden" tap of SURVEY.md §8 c.
+template <bool DISTORT>
+__global__ void __launch_bounds__(256) project_dump_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                           const __grid_constant__ ProjParams pp,
+                                                           int32_t* __restrict__ pix_out,
+                                                           uint32_t* __restrict__ zbits_out) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PointRecord p = ld_point_stream(pts + i);
+    uint32_t pix = 0;
+    float depth = 0.f;
+    const bool live = project<DISTORT>(pp, p.x, p.y, p.z, pix, depth);
+    pix_out[i] = live ? int32_t(pix) : -1;
+    zbits_out[i] = live ? __float_as_uint(depth) : 0u;
+}
+
+// ---------------------------------------------------------------- host launchers
+static inline unsigned grid_for(uint64_t n, int per_block) { return unsigned((n + per_block - 1) / per_block); }
+
+cudaError_t launch_clear(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum, uint64_t n_px,
+                         uint32_t* minmax) {
+    clear_kernel<<<sm_count * 8, 256, 0, s>>>(zbuf, cov, reinterpret_cast<uint4*>(accum), n_px, minmax);
+    return cudaGetLastError();
+}
+
+template <int UNROLL, int VARIANT>
+static cudaError_t launch_zmin_uv(cudaStream_t s, const PointRecord* pts, uint64_t n, uint64_t index_base,
+                                  const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey) {
+    const unsigned grid = grid_for(n, kPointBlock * UNROLL);
+    if (zkey) {
+        if (pp.distort) zmin_kernel<UNROLL, VARIANT, true, 1><<<grid, kPointBlock, 0, s>>>(pts, n, index_base, pp, zbuf, zkey);
+        else zmin_kernel<UNROLL, VARIANT, false, 1><<<grid, kPointBlock, 0, s>>>(pts, n, index_base, pp, zbuf, zkey);
+    } else {
+        if (pp.distort) zmin_kernel<UNROLL, VARIANT, true, 0><<<grid, kPointBlock, 0, s>>>(pts, n, index_base, pp, zbuf, zkey);
+        else zmin_kernel<UNROLL, VARIANT, false, 0><<<grid, kPointBlock, 0, s>>>(pts, n, index_base, pp, zbuf, zkey);
+    }
+    return cudaGetLastError();
+}
+
+template <int UNROLL>
+static cudaError_t launch_zmin_u(cudaStream_t s, int variant, const PointRecord* pts, uint64_t n, uint64_t index_base,
+                                 const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey) {
+    switch (variant & 7) {
+        case 0: return launch_zmin_uv<UNROLL, 0>(s, pts, n, index_base, pp, zbuf, zkey);
+        case 1: return launch_zmin_uv<UNROLL, 1>(s, pts, n, index_base, pp, zbuf, zkey);
+        case 2: return launch_zmin_uv<UNROLL, 2>(s, pts, n, index_base, pp, zbuf, zkey);
+        case 3: return launch_zmin_uv<UNROLL, 3>(s, pts, n, index_base, pp, zbuf, zkey);
+        case 5: return launch_zmin_uv<UNROLL, 5>(s, pts, n, index_base, pp, zbuf, zkey);
+        case 7: return launch_zmin_uv<UNROLL, 7>(s, pts, n, index_base, pp, zbuf, zkey);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
+                        uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey) {
+    if (n == 0) return cudaSuccess;
+    switch (unroll) {
+        case 1: return launch_zmin_u<1>(s, variant, pts, n, index_base, pp, zbuf, zkey);
+        case 2: return launch_zmin_u<2>(s, variant, pts, n, index_base, pp, zbuf, zkey);
+        case 4: return launch_zmin_u<4>(s, variant, pts, n, index_base, pp, zbuf, zkey);
+        case 8: return launch_zmin_u<8>(s, variant, pts, n, index_base, pp, zbuf, zkey);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int UNROLL>
+static cudaError_t launch_blend_u(cudaStream_t s, int variant, const PointRecord* pts, uint64_t n, const ProjParams& pp,
+                                  const uint32_t* zbuf, uint32_t* accum) {
+    const unsigned grid = grid_for(n, kPointBlock * UNROLL);
+    unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
+    const bool agg = (variant & 2) != 0;
+    if (pp.distort) {
+        if (agg) blend_kernel<UNROLL, 2, true><<<grid, kPointBlock, 0, s>>>(pts, n, pp, zbuf, a2);
+        else blend_kernel<UNROLL, 0, true><<<grid, kPointBlock, 0, s>>>(pts, n, pp, zbuf, a2);
+    } else {
+        if (agg) blend_kernel<UNROLL, 2, false><<<grid, kPointBlock, 0, s>>>(pts, n, pp, zbuf, a2);
+        else blend_kernel<UNROLL, 0, false><<<grid, kPointBlock, 0, s>>>(pts, n, pp, zbuf, a2);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
+                         const ProjParams& pp, const uint32_t* zbuf, uint32_t* accum) {
+    if (n == 0) return cudaSuccess;
+    switch (unroll) {
+        case 1: return launch_blend_u<1>(s, variant, pts, n, pp, zbuf, accum);
+        case 2: return launch_blend_u<2>(s, variant, pts, n, pp, zbuf, accum);
+        case 4: return launch_blend_u<4>(s, variant, pts, n, pp, zbuf, accum);
+        case 8: return launch_blend_u<8>(s, variant, pts, n, pp, zbuf, accum);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_project_dump(cudaStream_t s, const PointRecord* pts, uint64_t n, const ProjParams& pp,
+                                int32_t* pix_out, uint32_t* zbits_out) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = grid_for(n, 256);
+    if (pp.distort) project_dump_kernel<true><<<grid, 256, 0, s>>>(pts, n, pp, pix_out, zbits_out);
+    else project_dump_kernel<false><<<grid, 256, 0, s>>>(pts, n, pp, pix_out, zbits_out);
+    return cudaGetLastError();
+}
+
+}  // namespace rtr

@@ -1,0 +1,706 @@
+// Host side of the B200-native renderer + its C ABI (include/rtr_b200.h).
+//
+// Replaces ProjectCloud (project_cloud.cu:189-493) for the projection / z-buffer / blend / prefilter
+// path.  Differences in mechanism, not in results:
+//   - one non-blocking stream per renderer, no cudaDeviceSynchronize between stages
+//     (the reference issues 21 per filtered frame, project_cloud.cu:322-390);
+//   - persistent per-resolution buffers incl. pyramid scratch (the reference cudaMalloc/cudaFree's
+//     12 buffers per frame, project_cloud.cu:346-390), zero-initialised once at (re)allocation,
+//     which is the parity definition for non-multiple-of-16 resolutions;
+//   - camProj travels as a kernel parameter (the reference does a blocking 64-byte H2D per frame,
+//     project_cloud.cu:320);
+//   - two frame-buffer sets so a trajectory's D2H copies overlap the next frame's kernels.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rtr_b200.h"
+#include "rtr_kernels.h"
+
+using namespace rtr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- minimal NCCL binding, resolved at run time (libnccl.so.2 — torch's bundled copy when the
+// process already loaded it, else the system one).  Only what the point-sharded path needs.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclUint32_ = 3, ncclUint64_ = 5 };  // ncclDataType_t values (nccl.h)
+enum { ncclSum_ = 0, ncclMin_ = 3 };        // ncclRedOp_t values
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+struct FrameSet {
+    FrameBuffers fb{};
+    cudaEvent_t rendered = nullptr, copied = nullptr;
+};
+
+}  // namespace
+
+struct rtr_renderer {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // cloud
+    PointRecord* points = nullptr;
+    uint64_t n_points = 0;
+    bool owns_points = false;
+    uint64_t index_base = 0;  // global index of local point 0 (point sharding)
+    // camera
+    int W = 0, H = 0;
+    double K[9] = {0};
+    double dist[5] = {0};
+    double E[16] = {0};
+    bool have_K = false, have_E = false, raw_proj = false;
+    float cam_proj[16] = {0};
+    // frame buffers (two sets, see header)
+    FrameSet set[2];
+    int cur = 0;
+    int alloc_W = 0, alloc_H = 0;
+    PyramidDims dims{};
+    bool masks_allocated = false, key64_allocated = false;
+    // options
+    int zmin_variant = 1, zmin_unroll = 4, blend_variant = 0, blend_unroll = 4;
+    int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0;
+    cudaEvent_t ev[6] = {nullptr};
+    uint64_t launches = 0;
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    std::string err;
+};
+
+namespace {
+
+int fail(rtr_renderer* r, int code, const std::string& msg) {
+    if (r) r->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(rtr_renderer* r, cudaError_t e, const char* what) {
+    return fail(r, RTR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define RTR_CUDA(r, call)                                   \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return cuda_fail((r), e__, #call); \
+    } while (0)
+
+void free_frame_sets(rtr_renderer* r) {
+    for (auto& s : r->set) {
+        cudaFree(s.fb.zbuf); cudaFree(s.fb.accum); cudaFree(s.fb.image); cudaFree(s.fb.tensor); cudaFree(s.fb.minmax);
+        cudaFree(s.fb.zkey);
+        for (int i = 1; i <= 4; ++i) cudaFree(s.fb.level[i]);
+        for (int i = 0; i < 4; ++i) cudaFree(s.fb.mask[i]);
+        s.fb = FrameBuffers{};
+    }
+    r->alloc_W = r->alloc_H = 0;
+    r->masks_allocated = r->key64_allocated = false;
+}
+
+template <typename T> cudaError_t zalloc(T** p, size_t bytes, cudaStream_t s) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(*p, 0, bytes ? bytes : 16, s);
+}
+
+// (Re)allocate per-resolution buffers, zero-initialised — the reference reallocates six buffers
+// when W x H changes (project_cloud.cu:275-298).
+int ensure_buffers(rtr_renderer* r) {
+    const int W = r->W, H = r->H;
+    if (r->alloc_W != W || r->alloc_H != H) {
+        RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+        RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
+        free_frame_sets(r);
+        r->dims = make_pyramid_dims(W, H);
+        const size_t P = size_t(W) * H;
+        for (auto& s : r->set) {
+            RTR_CUDA(r, zalloc(&s.fb.zbuf, P * 4, r->stream));
+            RTR_CUDA(r, zalloc(&s.fb.accum, P * 16, r->stream));
+            RTR_CUDA(r, zalloc(&s.fb.image, P * 3 + 16, r->stream));
+            RTR_CUDA(r, zalloc(&s.fb.tensor, P * 5 * 2, r->stream));
+            RTR_CUDA(r, zalloc(&s.fb.minmax, 16, r->stream));
+            s.fb.level[0] = reinterpret_cast<float*>(s.fb.zbuf);
+            for (int i = 1; i <= 4; ++i) RTR_CUDA(r, zalloc(&s.fb.level[i], size_t(r->dims.w[i]) * r->dims.h[i] * 4, r->stream));
+        }
+        r->alloc_W = W; r->alloc_H = H;
+    }
+    if (r->keep_masks && !r->masks_allocated) {
+        for (auto& s : r->set)
+            for (int i = 0; i < 4; ++i) RTR_CUDA(r, zalloc(&s.fb.mask[i], size_t(r->dims.uw[i]) * r->dims.uh[i], r->stream));
+        r->masks_allocated = true;
+    }
+    if (r->key64 && !r->key64_allocated) {
+        for (auto& s : r->set) RTR_CUDA(r, zalloc(&s.fb.zkey, size_t(W) * H * 8, r->stream));
+        r->key64_allocated = true;
+    }
+    return RTR_OK;
+}
+
+// camProj = K4 * E in float, the way the reference's glm expression evaluates it
+// (project_cloud.cu:318, project_cloud.h:50-59, CameraCalibration.cpp:17-27): every factor is
+// cast to float first, products are summed left to right, no FMA.
+void build_cam_proj(const double* K9, const double* E16, float* out16) {
+    float K[4][4] = {{0.f}}, E[4][4];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) K[a][b] = static_cast<float>(K9[a * 3 + b]);
+    K[3][3] = 1.0f;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) E[a][b] = static_cast<float>(E16[a * 4 + b]);
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            volatile float t = K[a][0] * E[0][b];
+            volatile float p1 = K[a][1] * E[1][b];
+            t = t + p1;
+            volatile float p2 = K[a][2] * E[2][b];
+            t = t + p2;
+            volatile float p3 = K[a][3] * E[3][b];
+            t = t + p3;
+            out16[a * 4 + b] = t;
+        }
+}
+
+int make_params(rtr_renderer* r, ProjParams& pp) {
+    if (r->W < 16 || r->H < 16) return fail(r, RTR_ERR_STATE, "intrinsics not set (width/height must be >= 16)");
+    std::memset(&pp, 0, sizeof(pp));
+    pp.W = r->W; pp.H = r->H;
+    if (r->raw_proj) {
+        std::memcpy(pp.m, r->cam_proj, sizeof(float) * 12);
+        return RTR_OK;
+    }
+    if (!r->have_K || !r->have_E) return fail(r, RTR_ERR_STATE, "camera not set: call rtr_set_intrinsics and rtr_set_pose_w2c");
+    build_cam_proj(r->K, r->E, r->cam_proj);
+    std::memcpy(pp.m, r->cam_proj, sizeof(float) * 12);
+    bool any = false;
+    for (double d : r->dist) any = any || (d != 0.0);
+    if (any) {  // new feature (the reference never applies distortion): dist == 0 keeps the exact path
+        pp.distort = 1;
+        for (int i = 0; i < 12; ++i) pp.e[i] = static_cast<float>(r->E[i]);
+        pp.fx = float(r->K[0]); pp.skew = float(r->K[1]); pp.cx = float(r->K[2]);
+        pp.fy = float(r->K[4]); pp.cy = float(r->K[5]);
+        pp.k1 = float(r->dist[0]); pp.k2 = float(r->dist[1]); pp.p1 = float(r->dist[2]);
+        pp.p2 = float(r->dist[3]); pp.k3 = float(r->dist[4]);
+        // Cull beyond 1.5x the farthest image corner in normalised coordinates, or where the
+        // radial polynomial stops being monotone (fold-back of far off-axis points).
+        double rmax2 = 0;
+        const double xs[2] = {(0 - r->K[2]) / r->K[0], (r->W - 1 - r->K[2]) / r->K[0]};
+        const double ys[2] = {(0 - r->K[5]) / r->K[4], (r->H - 1 - r->K[5]) / r->K[4]};
+        for (double x : xs) for (double y : ys) rmax2 = std::fmax(rmax2, x * x + y * y);
+        double lim = rmax2 * 2.25 * 4.0;  // undistorted radius can exceed the distorted one; generous
+        const double k1 = r->dist[0], k2 = r->dist[1], k3 = r->dist[4];
+        for (int i = 1; i <= 4096; ++i) {  // first r2 where d/dr [ r (1 + k1 r2 + k2 r4 + k3 r6) ] <= 0
+            const double r2 = lim * i / 4096.0;
+            const double deriv = 1 + 3 * k1 * r2 + 5 * k2 * r2 * r2 + 7 * k3 * r2 * r2 * r2;
+            if (deriv <= 0) { lim = lim * (i - 1) / 4096.0; break; }
+        }
+        pp.r2_max = float(lim);
+    }
+    return RTR_OK;
+}
+
+int comm_allreduce(rtr_renderer* r, const void* src, void* dst, size_t count, int dtype, int op) {
+    const int rc = g_nccl.AllReduce(src, dst, count, dtype, op, r->comm, r->stream);
+    if (rc != 0) return fail(r, RTR_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return RTR_OK;
+}
+
+// Enqueue one frame on r->stream into frame set `si`.
+int enqueue_frame(rtr_renderer* r, int stage, int si) {
+    if (!r->points || r->n_points == 0) return fail(r, RTR_ERR_STATE, "no cloud uploaded");
+    ProjParams pp;
+    int rc = make_params(r, pp);
+    if (rc != RTR_OK) return rc;
+    rc = ensure_buffers(r);
+    if (rc != RTR_OK) return rc;
+    FrameSet& fs = r->set[si];
+    FrameBuffers fb = fs.fb;
+    if (!r->keep_masks) for (auto& m : fb.mask) m = nullptr;
+    const uint64_t P = uint64_t(r->W) * r->H, cov = clear_coverage(r->W, r->H);
+    const bool filtered = stage == RTR_STAGE_FILTERED;
+    cudaStream_t s = r->stream;
+    if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, fs.copied, 0));  // previous D2H of this set must be done
+    if (r->timing) cudaEventRecord(r->ev[0], s);
+    if (r->key64) {
+        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax));
+        RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
+        r->launches += 2;
+        if (r->timing) cudaEventRecord(r->ev[1], s);
+        RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
+        r->launches += 1;
+        if (r->comm) {
+            rc = comm_allreduce(r, fb.zkey, fb.zkey, P, ncclUint64_, ncclMin_);
+            if (rc != RTR_OK) return rc;
+        }
+        if (r->timing) { cudaEventRecord(r->ev[2], s); cudaEventRecord(r->ev[3], s); }
+        RTR_CUDA(r, launch_resolve_key64(s, fb.zkey, r->points, r->index_base, r->n_points, fb.zbuf, fb.image, P, cov));
+        r->launches += 1;
+        if (r->comm) {  // colour of a winning point lives on exactly one rank; others wrote 0 -> sum == the colour
+            // image bytes are summed as u32 words; no carry can occur because at most one rank is non-zero per byte
+            rc = comm_allreduce(r, fb.image, fb.image, (P * 3 + 3) / 4, ncclUint32_, ncclSum_);
+            if (rc != RTR_OK) return rc;
+        }
+        RTR_CUDA(r, launch_resolve_pyramid(s, fb, r->W, r->H, r->dims, filtered, false, r->force_generic != 0));
+        r->launches += filtered ? (((r->W % 16) == 0 && !r->force_generic) ? 1 : 5) : 0;
+    } else {
+        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax));
+        r->launches += 1;
+        if (r->timing) cudaEventRecord(r->ev[1], s);
+        RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
+        r->launches += 1;
+        if (r->comm) {
+            rc = comm_allreduce(r, fb.zbuf, fb.zbuf, P, ncclUint32_, ncclMin_);
+            if (rc != RTR_OK) return rc;
+        }
+        if (r->timing) cudaEventRecord(r->ev[2], s);
+        RTR_CUDA(r, launch_blend(s, r->blend_variant, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum));
+        r->launches += 1;
+        if (r->comm) {
+            rc = comm_allreduce(r, fb.accum, fb.accum, P * 4, ncclUint32_, ncclSum_);
+            if (rc != RTR_OK) return rc;
+        }
+        if (r->timing) cudaEventRecord(r->ev[3], s);
+        RTR_CUDA(r, launch_resolve_pyramid(s, fb, r->W, r->H, r->dims, filtered, true, r->force_generic != 0));
+        r->launches += ((r->W % 16) == 0 && !r->force_generic) ? 1 : (filtered ? 6 : 1);
+    }
+    if (r->timing) cudaEventRecord(r->ev[4], s);
+    if (filtered) {
+        RTR_CUDA(r, launch_up_pass(s, fb, r->dims, r->force_generic != 0));
+        r->launches += 4;
+    }
+    if (r->timing) cudaEventRecord(r->ev[5], s);
+    RTR_CUDA(r, cudaEventRecord(fs.rendered, s));
+    return RTR_OK;
+}
+
+// D2H of one frame set's outputs on the copy stream (after its render event).
+int enqueue_copy(rtr_renderer* r, int si, uint8_t* bgr, float* depth) {
+    FrameSet& fs = r->set[si];
+    const size_t P = size_t(r->W) * r->H;
+    RTR_CUDA(r, cudaStreamWaitEvent(r->copy_stream, fs.rendered, 0));
+    if (depth) RTR_CUDA(r, cudaMemcpyAsync(depth, fs.fb.zbuf, P * 4, cudaMemcpyDeviceToHost, r->copy_stream));
+    if (bgr) RTR_CUDA(r, cudaMemcpyAsync(bgr, fs.fb.image, P * 3, cudaMemcpyDeviceToHost, r->copy_stream));
+    RTR_CUDA(r, cudaEventRecord(fs.copied, r->copy_stream));
+    return RTR_OK;
+}
+
+int render_to_host(rtr_renderer* r, int stage, uint8_t* bgr, float* depth) {
+    if (!r) return RTR_ERR_ARG;
+    if (!bgr && !depth) return fail(r, RTR_ERR_ARG, "both output pointers are NULL");  // project_cloud.cu:270-273
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    int rc = enqueue_frame(r, stage, r->cur);
+    if (rc != RTR_OK) return rc;
+    rc = enqueue_copy(r, r->cur, bgr, depth);
+    if (rc != RTR_OK) return rc;
+    RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
+    return RTR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtr_version(void) { return "rtr_b200 0.1 (sm_100a)"; }
+
+int rtr_create(int device, rtr_renderer** out) {
+    if (!out) return fail(nullptr, RTR_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, RTR_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (rtr_b200 has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, RTR_ERR_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, RTR_ERR_UNSUPPORTED, "rtr_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    rtr_renderer* r = new rtr_renderer;
+    r->device = device;
+    r->sm_count = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete r;
+        return cuda_fail(nullptr, e, "stream creation");
+    }
+    for (auto& s : r->set) {
+        cudaEventCreateWithFlags(&s.rendered, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
+    }
+    for (auto& ev : r->ev) cudaEventCreate(&ev);
+    *out = r;
+    return RTR_OK;
+}
+
+void rtr_destroy(rtr_renderer* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    cudaStreamSynchronize(r->copy_stream);
+    if (r->comm) g_nccl.CommDestroy(r->comm);
+    free_frame_sets(r);
+    if (r->owns_points) cudaFree(r->points);
+    for (auto& s : r->set) { cudaEventDestroy(s.rendered); cudaEventDestroy(s.copied); }
+    for (auto& ev : r->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(r->stream);
+    cudaStreamDestroy(r->copy_stream);
+    delete r;
+}
+
+const char* rtr_last_error(const rtr_renderer* r) { return r ? r->err.c_str() : g_create_error.c_str(); }
+
+static int replace_cloud(rtr_renderer* r, uint64_t n) {
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    if (r->owns_points) cudaFree(r->points);
+    r->points = nullptr; r->n_points = 0; r->owns_points = false;
+    if (n == 0) return RTR_OK;
+    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->points), n * sizeof(PointRecord)));
+    r->owns_points = true;
+    r->n_points = n;
+    return RTR_OK;
+}
+
+int rtr_upload_cloud_xyz_bgr(rtr_renderer* r, const float* xyz, const uint8_t* bgr, uint64_t n) {
+    if (!r) return RTR_ERR_ARG;
+    if (n && (!xyz || !bgr)) return fail(r, RTR_ERR_ARG, "xyz/bgr is NULL");
+    if (n > 0xFFFFFFFFull) return fail(r, RTR_ERR_UNSUPPORTED, "more than 2^32 points per renderer");
+    int rc = replace_cloud(r, n);
+    if (rc != RTR_OK || n == 0) return rc;
+    // repack on the host through a pinned staging ring, 4 Mi points per chunk
+    const uint64_t chunk = 1ull << 22;
+    PointRecord* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    for (int i = 0; i < 2; ++i) {
+        RTR_CUDA(r, cudaMallocHost(reinterpret_cast<void**>(&stage[i]), std::min(chunk, n) * sizeof(PointRecord)));
+        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+    }
+    int b = 0;
+    for (uint64_t off = 0; off < n; off += chunk, b ^= 1) {
+        const uint64_t m = std::min(chunk, n - off);
+        cudaEventSynchronize(done[b]);
+        for (uint64_t i = 0; i < m; ++i) {
+            const float* p = xyz + (off + i) * 3;
+            const uint8_t* c = bgr + (off + i) * 3;
+            stage[b][i].x = p[0]; stage[b][i].y = p[1]; stage[b][i].z = p[2];
+            stage[b][i].bgra = uint32_t(c[0]) | (uint32_t(c[1]) << 8) | (uint32_t(c[2]) << 16) | 0xFF000000u;  // Octreegrid.h:176
+        }
+        RTR_CUDA(r, cudaMemcpyAsync(r->points + off, stage[b], m * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
+        cudaEventRecord(done[b], r->stream);
+    }
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
+    return RTR_OK;
+}
+
+int rtr_upload_cloud_packed16(rtr_renderer* r, const void* host_records, uint64_t n) {
+    if (!r) return RTR_ERR_ARG;
+    if (n && !host_records) return fail(r, RTR_ERR_ARG, "records is NULL");
+    if (n > 0xFFFFFFFFull) return fail(r, RTR_ERR_UNSUPPORTED, "more than 2^32 points per renderer");
+    int rc = replace_cloud(r, n);
+    if (rc != RTR_OK || n == 0) return rc;
+    RTR_CUDA(r, cudaMemcpyAsync(r->points, host_records, n * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RTR_OK;
+}
+
+int rtr_adopt_device_cloud_packed16(rtr_renderer* r, void* device_records, uint64_t n) {
+    if (!r) return RTR_ERR_ARG;
+    if (n && !device_records) return fail(r, RTR_ERR_ARG, "records is NULL");
+    if (reinterpret_cast<uintptr_t>(device_records) & 15) return fail(r, RTR_ERR_ARG, "records must be 16-byte aligned");
+    int rc = replace_cloud(r, 0);
+    if (rc != RTR_OK) return rc;
+    r->points = static_cast<PointRecord*>(device_records);
+    r->n_points = n;
+    r->owns_points = false;
+    return RTR_OK;
+}
+
+int rtr_synth_cloud(rtr_renderer* r, uint64_t seed, uint64_t n_total, uint64_t first, uint64_t count, int lx, int ly,
+                    int lz, int nbox) {
+    if (!r) return RTR_ERR_ARG;
+    if (lx < 8 || ly < 8 || lz < 4 || nbox < 0 || nbox > 20) return fail(r, RTR_ERR_ARG, "scene dims out of range");
+    if (count > 0xFFFFFFFFull) return fail(r, RTR_ERR_UNSUPPORTED, "more than 2^32 points per renderer");
+    int rc = replace_cloud(r, count);
+    if (rc != RTR_OK || count == 0) return rc;
+    RTR_CUDA(r, launch_synth(r->stream, seed, n_total, first, count, lx, ly, lz, nbox, r->points));
+    r->launches += 1;
+    r->index_base = first;
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RTR_OK;
+}
+
+uint64_t rtr_cloud_size(const rtr_renderer* r) { return r ? r->n_points : 0; }
+
+int rtr_download_cloud_packed16(rtr_renderer* r, uint64_t first, uint64_t count, void* host_records) {
+    if (!r || !host_records) return RTR_ERR_ARG;
+    if (first + count > r->n_points) return fail(r, RTR_ERR_ARG, "range exceeds cloud");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    RTR_CUDA(r, cudaMemcpyAsync(host_records, r->points + first, count * sizeof(PointRecord), cudaMemcpyDeviceToHost, r->stream));
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RTR_OK;
+}
+
+int rtr_set_intrinsics_matrix(rtr_renderer* r, int width, int height, const double* K9, const double* dist5) {
+    if (!r || !K9) return RTR_ERR_ARG;
+    if (width < 16 || height < 16 || width > 32768 || height > 32768) return fail(r, RTR_ERR_ARG, "width/height must be in [16, 32768]");
+    r->W = width; r->H = height;
+    std::memcpy(r->K, K9, sizeof(r->K));
+    for (int i = 0; i < 5; ++i) r->dist[i] = dist5 ? dist5[i] : 0.0;
+    r->have_K = true;
+    return RTR_OK;
+}
+
+int rtr_set_intrinsics(rtr_renderer* r, int width, int height, double fx, double fy, double cx, double cy, double skew,
+                       const double* dist5) {
+    const double K9[9] = {fx, skew, cx, 0, fy, cy, 0, 0, 1};
+    return rtr_set_intrinsics_matrix(r, width, height, K9, dist5);
+}
+
+int rtr_set_pose_w2c(rtr_renderer* r, const double* E16) {
+    if (!r || !E16) return RTR_ERR_ARG;
+    std::memcpy(r->E, E16, sizeof(r->E));
+    r->have_E = true;
+    r->raw_proj = false;
+    return RTR_OK;
+}
+
+int rtr_set_cam_proj_raw(rtr_renderer* r, const float* m16) {
+    if (!r || !m16) return RTR_ERR_ARG;
+    std::memcpy(r->cam_proj, m16, sizeof(r->cam_proj));
+    r->raw_proj = true;
+    return RTR_OK;
+}
+
+int rtr_get_cam_proj(const rtr_renderer* r, float* m16) {
+    if (!r || !m16) return RTR_ERR_ARG;
+    if (r->raw_proj) std::memcpy(m16, r->cam_proj, 64);
+    else if (r->have_K && r->have_E) build_cam_proj(r->K, r->E, m16);
+    else return RTR_ERR_STATE;
+    return RTR_OK;
+}
+
+int rtr_render_rgbd(rtr_renderer* r, uint8_t* bgr, float* depth) { return render_to_host(r, RTR_STAGE_RGBD, bgr, depth); }
+int rtr_render_filtered(rtr_renderer* r, uint8_t* bgr, float* depth) { return render_to_host(r, RTR_STAGE_FILTERED, bgr, depth); }
+
+int rtr_render_tensor(rtr_renderer* r, void** device_fp16) {
+    if (!r || !device_fp16) return RTR_ERR_ARG;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    int rc = enqueue_frame(r, RTR_STAGE_FILTERED, r->cur);
+    if (rc != RTR_OK) return rc;
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    *device_fp16 = r->set[r->cur].fb.tensor;
+    return RTR_OK;
+}
+
+int rtr_render_device(rtr_renderer* r, int stage) {
+    if (!r) return RTR_ERR_ARG;
+    if (stage != RTR_STAGE_RGBD && stage != RTR_STAGE_FILTERED) return fail(r, RTR_ERR_ARG, "bad stage");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    return enqueue_frame(r, stage, r->cur);
+}
+
+int rtr_sync(rtr_renderer* r) {
+    if (!r) return RTR_ERR_ARG;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
+    return RTR_OK;
+}
+
+int rtr_render_trajectory(rtr_renderer* r, int stage, const double* poses, int n_frames, uint8_t* bgr, float* depth) {
+    if (!r || !poses || n_frames < 0) return RTR_ERR_ARG;
+    if (stage != RTR_STAGE_RGBD && stage != RTR_STAGE_FILTERED) return fail(r, RTR_ERR_ARG, "bad stage");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    const size_t P = size_t(r->W) * r->H;
+    for (int f = 0; f < n_frames; ++f) {
+        int rc = rtr_set_pose_w2c(r, poses + size_t(f) * 16);
+        if (rc != RTR_OK) return rc;
+        const int si = r->cur;
+        rc = enqueue_frame(r, stage, si);
+        if (rc != RTR_OK) return rc;
+        if (bgr || depth) {
+            rc = enqueue_copy(r, si, bgr ? bgr + size_t(f) * P * 3 : nullptr, depth ? depth + size_t(f) * P : nullptr);
+            if (rc != RTR_OK) return rc;
+            r->cur ^= 1;  // next frame renders into the other set while this one drains over PCIe
+        }
+    }
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
+    return RTR_OK;
+}
+
+int rtr_get_device_buffers(rtr_renderer* r, rtr_device_buffers* out) {
+    if (!r || !out) return RTR_ERR_ARG;
+    if (r->alloc_W == 0) return fail(r, RTR_ERR_STATE, "no frame rendered yet");
+    const FrameBuffers& fb = r->set[r->cur].fb;
+    std::memset(out, 0, sizeof(*out));
+    out->points = r->points; out->zbuf = fb.zbuf; out->accum = fb.accum; out->image = fb.image; out->tensor = fb.tensor;
+    out->minmax = fb.minmax;
+    for (int i = 0; i < 5; ++i) {
+        out->level[i] = fb.level[i];
+        out->level_w[i] = r->dims.w[i]; out->level_h[i] = r->dims.h[i];
+        out->up_w[i] = r->dims.uw[i]; out->up_h[i] = r->dims.uh[i];
+    }
+    for (int i = 0; i < 4; ++i) out->mask[i] = r->keep_masks ? fb.mask[i] : nullptr;
+    out->width = r->alloc_W; out->height = r->alloc_H;
+    out->tensor_plane = uint64_t(r->dims.uw[0]) * r->dims.uh[0];
+    out->stream = r->stream;
+    return RTR_OK;
+}
+
+int rtr_read_buffer(rtr_renderer* r, int what, void* dst, size_t bytes) {
+    if (!r || !dst) return RTR_ERR_ARG;
+    if (r->alloc_W == 0) return fail(r, RTR_ERR_STATE, "no frame rendered yet");
+    const FrameBuffers& fb = r->set[r->cur].fb;
+    const size_t P = size_t(r->alloc_W) * r->alloc_H;
+    const void* src = nullptr;
+    size_t cap = 0;
+    if (what == 0) { src = fb.zbuf; cap = P * 4; }
+    else if (what == 1) { src = fb.accum; cap = P * 16; }
+    else if (what == 2) { src = fb.image; cap = P * 3; }
+    else if (what == 3) { src = fb.tensor; cap = P * 10; }
+    else if (what == 4) { src = fb.minmax; cap = 8; }
+    else if (what >= 5 && what <= 8) { const int i = what - 4; src = fb.level[i]; cap = size_t(r->dims.w[i]) * r->dims.h[i] * 4; }
+    else if (what >= 9 && what <= 12) { const int i = what - 9; src = r->keep_masks ? fb.mask[i] : nullptr; cap = size_t(r->dims.uw[i]) * r->dims.uh[i]; }
+    if (!src) return fail(r, RTR_ERR_ARG, "buffer not available");
+    if (bytes > cap) return fail(r, RTR_ERR_ARG, "read exceeds buffer");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return RTR_OK;
+}
+
+int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host) {
+    if (!r || !pix_host || !zbits_host) return RTR_ERR_ARG;
+    if (!r->points || r->n_points == 0) return fail(r, RTR_ERR_STATE, "no cloud uploaded");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    ProjParams pp;
+    int rc = make_params(r, pp);
+    if (rc != RTR_OK) return rc;
+    int32_t* d_pix = nullptr;
+    uint32_t* d_z = nullptr;
+    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&d_pix), r->n_points * 4));
+    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&d_z), r->n_points * 4));
+    cudaError_t e = launch_project_dump(r->stream, r->points, r->n_points, pp, d_pix, d_z);
+    r->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pix_host, d_pix, r->n_points * 4, cudaMemcpyDeviceToHost, r->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(zbits_host, d_z, r->n_points * 4, cudaMemcpyDeviceToHost, r->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    cudaFree(d_pix); cudaFree(d_z);
+    if (e != cudaSuccess) return cuda_fail(r, e, "project dump");
+    return RTR_OK;
+}
+
+static int* option_slot(rtr_renderer* r, const char* key) {
+    if (!std::strcmp(key, "zmin_variant")) return &r->zmin_variant;
+    if (!std::strcmp(key, "zmin_unroll")) return &r->zmin_unroll;
+    if (!std::strcmp(key, "blend_variant")) return &r->blend_variant;
+    if (!std::strcmp(key, "blend_unroll")) return &r->blend_unroll;
+    if (!std::strcmp(key, "force_generic")) return &r->force_generic;
+    if (!std::strcmp(key, "keep_masks")) return &r->keep_masks;
+    if (!std::strcmp(key, "timing")) return &r->timing;
+    if (!std::strcmp(key, "key64")) return &r->key64;
+    return nullptr;
+}
+
+int rtr_set_option(rtr_renderer* r, const char* key, int64_t value) {
+    if (!r || !key) return RTR_ERR_ARG;
+    if (!std::strcmp(key, "index_base")) { r->index_base = uint64_t(value); return RTR_OK; }
+    int* slot = option_slot(r, key);
+    if (!slot) return fail(r, RTR_ERR_ARG, std::string("unknown option: ") + key);
+    if ((!std::strcmp(key, "zmin_unroll") || !std::strcmp(key, "blend_unroll")) && value != 1 && value != 2 && value != 4 && value != 8)
+        return fail(r, RTR_ERR_ARG, "unroll must be 1, 2, 4 or 8");
+    if (!std::strcmp(key, "zmin_variant") && !(value == 0 || value == 1 || value == 2 || value == 3 || value == 5 || value == 7))
+        return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7");
+    *slot = int(value);
+    return RTR_OK;
+}
+
+int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
+    if (!r || !key) return RTR_ERR_ARG;
+    if (!std::strcmp(key, "index_base")) return int64_t(r->index_base);
+    if (!std::strcmp(key, "sm_count")) return r->sm_count;
+    const int* slot = option_slot(const_cast<rtr_renderer*>(r), key);
+    return slot ? *slot : RTR_ERR_ARG;
+}
+
+int rtr_get_stage_ms(rtr_renderer* r, float* ms6) {
+    if (!r || !ms6) return RTR_ERR_ARG;
+    if (!r->timing) return fail(r, RTR_ERR_STATE, "option timing is off");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    RTR_CUDA(r, cudaEventSynchronize(r->ev[5]));
+    for (int i = 0; i < 5; ++i) RTR_CUDA(r, cudaEventElapsedTime(&ms6[i], r->ev[i], r->ev[i + 1]));
+    RTR_CUDA(r, cudaEventElapsedTime(&ms6[5], r->ev[0], r->ev[5]));
+    return RTR_OK;
+}
+
+uint64_t rtr_launch_count(const rtr_renderer* r) { return r ? r->launches : 0; }
+
+int rtr_comm_unique_id(void* id128) {
+    if (!id128) return RTR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    std::string err;
+    if (!g_nccl.load(err)) return fail(nullptr, RTR_ERR_COMM, err);
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return fail(nullptr, RTR_ERR_COMM, "ncclGetUniqueId failed");
+    std::memcpy(id128, &id, 128);
+    return RTR_OK;
+}
+
+int rtr_comm_init(rtr_renderer* r, const void* id128, int rank, int n_ranks) {
+    if (!r || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return RTR_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> lk(g_nccl_mu);
+        std::string err;
+        if (!g_nccl.load(err)) return fail(r, RTR_ERR_COMM, err);
+    }
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    const int rc = g_nccl.CommInitRank(&r->comm, n_ranks, id, rank);
+    if (rc != 0) { r->comm = nullptr; return fail(r, RTR_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); }
+    r->rank = rank; r->n_ranks = n_ranks;
+    return RTR_OK;
+}
+
+int rtr_comm_destroy(rtr_renderer* r) {
+    if (!r) return RTR_ERR_ARG;
+    if (r->comm) {
+        cudaStreamSynchronize(r->stream);
+        g_nccl.CommDestroy(r->comm);
+        r->comm = nullptr;
+    }
+    r->rank = 0; r->n_ranks = 1;
+    return RTR_OK;
+}
+
+}  // extern "C"
