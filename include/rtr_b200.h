@@ -129,6 +129,9 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key);
 /* With option timing=1: CUDA-event ms of the last frame's stages
  * {clear, zmin, blend, resolve+pyramid, up-pass, total}. */
 int rtr_get_stage_ms(rtr_renderer* r, float* ms6);
+/* With option timing=2 every frame records its own six events (pooled); this returns the per-stage
+ * SUMS in ms over all frames rendered since the last reset, and how many frames that was. */
+int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, int reset);
 /* Number of kernel launches issued by this renderer since creation. */
 uint64_t rtr_launch_count(const rtr_renderer* r);
 

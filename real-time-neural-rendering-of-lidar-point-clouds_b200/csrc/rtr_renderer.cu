@@ -93,6 +93,11 @@ struct rtr_renderer {
     int zmin_variant = 1, zmin_unroll = 4, blend_variant = 0, blend_unroll = 4;
     int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0;
     cudaEvent_t ev[6] = {nullptr};
+    // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
+    std::vector<cudaEvent_t> ev_pool;
+    int ev_frames = 0;
+    double ev_sum[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t ev_count = 0;
     uint64_t launches = 0;
     // comm
     ncclComm_t comm = nullptr;
@@ -233,6 +238,27 @@ int comm_allreduce(rtr_renderer* r, const void* src, void* dst, size_t count, in
     return RTR_OK;
 }
 
+constexpr int kEvPoolFrames = 256;
+
+// Fold the pooled per-frame events into ev_sum (blocks until the last recorded frame finished).
+int drain_event_pool(rtr_renderer* r) {
+    if (r->ev_frames == 0) return RTR_OK;
+    RTR_CUDA(r, cudaEventSynchronize(r->ev_pool[size_t(r->ev_frames - 1) * 6 + 5]));
+    for (int f = 0; f < r->ev_frames; ++f) {
+        cudaEvent_t* e = &r->ev_pool[size_t(f) * 6];
+        float ms = 0.f;
+        for (int i = 0; i < 5; ++i) {
+            RTR_CUDA(r, cudaEventElapsedTime(&ms, e[i], e[i + 1]));
+            r->ev_sum[i] += ms;
+        }
+        RTR_CUDA(r, cudaEventElapsedTime(&ms, e[0], e[5]));
+        r->ev_sum[5] += ms;
+    }
+    r->ev_count += uint64_t(r->ev_frames);
+    r->ev_frames = 0;
+    return RTR_OK;
+}
+
 // Enqueue one frame on r->stream into frame set `si`.
 int enqueue_frame(rtr_renderer* r, int stage, int si) {
     if (!r->points || r->n_points == 0) return fail(r, RTR_ERR_STATE, "no cloud uploaded");
@@ -248,19 +274,28 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     const bool filtered = stage == RTR_STAGE_FILTERED;
     cudaStream_t s = r->stream;
     if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, fs.copied, 0));  // previous D2H of this set must be done
-    if (r->timing) cudaEventRecord(r->ev[0], s);
+    cudaEvent_t* ev = r->ev;
+    if (r->timing == 2) {
+        if (r->ev_pool.empty()) {
+            r->ev_pool.resize(size_t(kEvPoolFrames) * 6);
+            for (auto& e : r->ev_pool) RTR_CUDA(r, cudaEventCreate(&e));
+        }
+        if (r->ev_frames == kEvPoolFrames && (rc = drain_event_pool(r)) != RTR_OK) return rc;
+        ev = &r->ev_pool[size_t(r->ev_frames) * 6];
+    }
+    if (r->timing) cudaEventRecord(ev[0], s);
     if (r->key64) {
         RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax));
         RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
         r->launches += 2;
-        if (r->timing) cudaEventRecord(r->ev[1], s);
+        if (r->timing) cudaEventRecord(ev[1], s);
         RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
         r->launches += 1;
         if (r->comm) {
             rc = comm_allreduce(r, fb.zkey, fb.zkey, P, ncclUint64_, ncclMin_);
             if (rc != RTR_OK) return rc;
         }
-        if (r->timing) { cudaEventRecord(r->ev[2], s); cudaEventRecord(r->ev[3], s); }
+        if (r->timing) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
         RTR_CUDA(r, launch_resolve_key64(s, fb.zkey, r->points, r->index_base, r->n_points, fb.zbuf, fb.image, P, cov));
         r->launches += 1;
         if (r->comm) {  // colour of a winning point lives on exactly one rank; others wrote 0 -> sum == the colour
@@ -273,30 +308,31 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     } else {
         RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax));
         r->launches += 1;
-        if (r->timing) cudaEventRecord(r->ev[1], s);
+        if (r->timing) cudaEventRecord(ev[1], s);
         RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
         r->launches += 1;
         if (r->comm) {
             rc = comm_allreduce(r, fb.zbuf, fb.zbuf, P, ncclUint32_, ncclMin_);
             if (rc != RTR_OK) return rc;
         }
-        if (r->timing) cudaEventRecord(r->ev[2], s);
+        if (r->timing) cudaEventRecord(ev[2], s);
         RTR_CUDA(r, launch_blend(s, r->blend_variant, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum));
         r->launches += 1;
         if (r->comm) {
             rc = comm_allreduce(r, fb.accum, fb.accum, P * 4, ncclUint32_, ncclSum_);
             if (rc != RTR_OK) return rc;
         }
-        if (r->timing) cudaEventRecord(r->ev[3], s);
+        if (r->timing) cudaEventRecord(ev[3], s);
         RTR_CUDA(r, launch_resolve_pyramid(s, fb, r->W, r->H, r->dims, filtered, true, r->force_generic != 0));
         r->launches += ((r->W % 16) == 0 && !r->force_generic) ? 1 : (filtered ? 6 : 1);
     }
-    if (r->timing) cudaEventRecord(r->ev[4], s);
+    if (r->timing) cudaEventRecord(ev[4], s);
     if (filtered) {
         RTR_CUDA(r, launch_up_pass(s, fb, r->dims, r->force_generic != 0));
         r->launches += 4;
     }
-    if (r->timing) cudaEventRecord(r->ev[5], s);
+    if (r->timing) cudaEventRecord(ev[5], s);
+    if (r->timing == 2) r->ev_frames += 1;
     RTR_CUDA(r, cudaEventRecord(fs.rendered, s));
     return RTR_OK;
 }
@@ -370,6 +406,7 @@ void rtr_destroy(rtr_renderer* r) {
     if (r->owns_points) cudaFree(r->points);
     for (auto& s : r->set) { cudaEventDestroy(s.rendered); cudaEventDestroy(s.copied); }
     for (auto& ev : r->ev) cudaEventDestroy(ev);
+    for (auto& ev : r->ev_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(r->stream);
     cudaStreamDestroy(r->copy_stream);
     delete r;
@@ -655,11 +692,25 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
 
 int rtr_get_stage_ms(rtr_renderer* r, float* ms6) {
     if (!r || !ms6) return RTR_ERR_ARG;
-    if (!r->timing) return fail(r, RTR_ERR_STATE, "option timing is off");
+    if (r->timing != 1) return fail(r, RTR_ERR_STATE, "option timing is not 1");
     RTR_CUDA(r, cudaSetDevice(r->device));
     RTR_CUDA(r, cudaEventSynchronize(r->ev[5]));
     for (int i = 0; i < 5; ++i) RTR_CUDA(r, cudaEventElapsedTime(&ms6[i], r->ev[i], r->ev[i + 1]));
     RTR_CUDA(r, cudaEventElapsedTime(&ms6[5], r->ev[0], r->ev[5]));
+    return RTR_OK;
+}
+
+int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, int reset) {
+    if (!r || !ms6_sum || !n_frames) return RTR_ERR_ARG;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    int rc = drain_event_pool(r);
+    if (rc != RTR_OK) return rc;
+    for (int i = 0; i < 6; ++i) ms6_sum[i] = r->ev_sum[i];
+    *n_frames = r->ev_count;
+    if (reset) {
+        for (double& v : r->ev_sum) v = 0.0;
+        r->ev_count = 0;
+    }
     return RTR_OK;
 }
 

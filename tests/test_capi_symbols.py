@@ -1,0 +1,52 @@
+"""The C-ABI library loads and exports every symbol include/rtr_b200.h declares; without a GPU it
+fails loudly instead of falling back to anything."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT, has_gpu
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rtr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for s in ("rtr_create", "rtr_upload_cloud_xyz_bgr", "rtr_set_intrinsics", "rtr_set_pose_w2c", "rtr_render_rgbd",
+              "rtr_render_filtered", "rtr_render_tensor", "rtr_destroy", "rtr_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"librtr_b200.so does not export {s}"
+    assert set(declared_symbols()) == set(pkg.API), "python binding and header disagree"
+
+
+def test_no_cpu_fallback(pkg):
+    if has_gpu():
+        return
+    lib = pkg.load_library()
+    h = ctypes.c_void_p()
+    rc = lib.rtr_create(0, ctypes.byref(h))
+    assert rc == pkg.RTR_ERR_CUDA and not h.value
+    assert b"no CPU fallback" in lib.rtr_last_error(None)
+    try:
+        pkg.ProjectCloud()
+        raise AssertionError("ProjectCloud() must raise without a GPU")
+    except pkg.RtrError as e:
+        assert e.code == pkg.RTR_ERR_CUDA
+
+
+def test_product_does_not_reference_the_oracle():
+    pkgdir = os.path.join(ROOT, "real-time-neural-rendering-of-lidar-point-clouds_b200")
+    for base, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, f)).read()
+                assert "import oracle" not in src and "oracle/" not in src.replace("oracle/rtr_oracle.c:rtro_synth_packed", "") \
+                    or f == "rtr_synth_common.h", f"{f} references the oracle"

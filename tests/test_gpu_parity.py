@@ -1,0 +1,387 @@
+"""Parity of the sm_100a CUDA path (through the C ABI) with
+  (1) the CPU oracle fed the GPU's own per-point projection (hybrid golden, SURVEY.md §8 c) — every
+      stage tap, bit for bit;
+  (2) the committed golden vectors = outputs of the unmodified reference on a B200 (sha256);
+  (3) the live reference (oracle/_ref), when its library travelled to this box — 0 differing
+      pixels allowed (bar from north_star: bit-exact framebuffer, depth, mask/tensor).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import scenes
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+_clouds = {}
+
+
+def cloud_of(cpu_oracle, case):
+    key = (case.seed, case.n, case.hall, case.n_boxes)
+    if key not in _clouds:
+        _clouds[key] = cpu_oracle.synth_packed(case.seed, case.n, 0, case.n, case.hall, case.n_boxes)
+    return _clouds[key]
+
+
+def calib_of(pkg, case):
+    c = pkg.CameraCalibration()
+    c.setIntrinsicsMatrix(case.K)
+    c.setWidth(case.W)
+    c.setHeight(case.H)
+    return c
+
+
+def render_mine(pkg, case, rec, keep_masks=False, options=None, with_taps=True):
+    """Per pose: computeRGBD then computeFilteredRGBD on one renderer (like one reference object).
+    Returns (frames, taps, extras)."""
+    pc = pkg.ProjectCloud.from_packed(rec)
+    for k, v in (options or {}).items():
+        pc.set_option(k, v)
+    if keep_masks:
+        pc.set_option("keep_masks", 1)
+    W, H, P = case.W, case.H, case.W * case.H
+    calib = calib_of(pkg, case)
+    frames, taps, extras = [], [], []
+    for E in case.poses:
+        o = {}
+        color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        assert pc.computeRGBD(calib, E, color, depth) == 1
+        o["raw_depth_host"], o["raw_color_host"] = depth.view(np.uint32).copy(), color.copy()
+        o["raw_zbuf"], o["raw_accum"], o["raw_image"] = pc.read("zbuf", np.uint32, P), pc.read("accum", np.uint32, P * 4), pc.read("image", np.uint8, P * 3)
+        color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        assert pc.computeFilteredRGBD(calib, E, color, depth) == 1
+        o["flt_depth_host"], o["flt_color_host"] = depth.view(np.uint32).copy(), color.copy()
+        o["flt_tensor"], o["flt_minmax"] = pc.read("tensor", np.uint16, P * 5), pc.read("minmax", np.uint32, 2)
+        frames.append(o)
+        ex = {"cam_proj": pc.get_cam_proj().reshape(16)}
+        if keep_masks:
+            b = pc.device_buffers()
+            ex["levels"] = {i: pc.read(f"level{i}", np.float32, b.level_w[i] * b.level_h[i]) for i in range(1, 5)}
+            ex["masks"] = {i: pc.read(f"mask{i}", np.uint8, b.up_w[i] * b.up_h[i]) for i in range(4)}
+            ex["up"] = [(b.up_w[i], b.up_h[i]) for i in range(5)]
+        extras.append(ex)
+        if with_taps:
+            taps.append(pc.project_points())
+    pc.close()
+    return frames, taps, extras
+
+
+def assert_frames_equal(a, b, what):
+    for fi, (fa, fb) in enumerate(zip(a, b)):
+        for k in scenes.OUTPUT_KEYS:
+            if not np.array_equal(fa[k], fb[k]):
+                n = int((np.asarray(fa[k]) != np.asarray(fb[k])).sum())
+                raise AssertionError(f"{what}: frame {fi} '{k}' differs in {n} of {fa[k].size} elements")
+
+
+@pytest.mark.parametrize("name", list(scenes.CASES))
+def test_cuda_vs_cpu_oracle_all_stages(gpu, cpu_oracle, name):
+    case = scenes.CASES[name]
+    rec = cloud_of(cpu_oracle, case)
+    mine, taps, extras = render_mine(gpu, case, rec, keep_masks=True)
+    assert (taps[0][0] >= 0).sum() > 1000
+    # host matrix: K4*E as the reference's glm expression evaluates it
+    for E, ex in zip(case.poses, extras):
+        assert np.array_equal(ex["cam_proj"], cpu_oracle.cam_proj(case.K, E))
+    gold = scenes.oracle_frames(cpu_oracle, case, rec, taps)
+    assert_frames_equal(mine, gold, f"{name} CUDA vs CPU oracle")
+    # pyramid levels and masks of the last frame (stage taps 4-5)
+    f = gold[-1]
+    flt = cpu_oracle.depth_filter(f["raw_zbuf"], f["raw_image"], case.W, case.H, taps=True)
+    ex = extras[-1]
+    for i in range(1, 5):
+        n = ex["up"][i][0] * ex["up"][i][1] if case.W % 16 == 0 else flt["levels"][i].size
+        assert np.array_equal(ex["levels"][i][:n].view(np.uint32), flt["levels"][i][:n].view(np.uint32)), f"level {i}"
+    for i in range(4):
+        assert np.array_equal(ex["masks"][i], flt["masks"][i]), f"mask {i}"
+
+
+def load_golden(name):
+    p = os.path.join(GOLDEN_DIR, name + ".npz")
+    return np.load(p) if os.path.exists(p) else None
+
+
+@pytest.mark.parametrize("name", list(scenes.CASES))
+def test_cuda_vs_golden_reference_outputs(gpu, cpu_oracle, name):
+    g = load_golden(name)
+    if g is None:
+        pytest.skip("golden not generated yet (tests/golden/make_golden.py)")
+    case = scenes.CASES[name]
+    mine, _, extras = render_mine(gpu, case, cloud_of(cpu_oracle, case), with_taps=False)
+    for fi, f in enumerate(mine):
+        assert np.array_equal(extras[fi]["cam_proj"], g[f"f{fi}_cam_proj"]), "camProj differs from the reference's glm product"
+        for k in scenes.OUTPUT_KEYS:
+            assert scenes.sha(f[k]) == bytes(g[f"f{fi}_{k}_sha"]).decode(), f"{name} frame {fi} {k}: differs from the reference"
+
+
+def have_ref():
+    import oracle
+    return os.path.exists(oracle.REF_LIB)
+
+
+@pytest.mark.parametrize("name", list(scenes.CASES))
+def test_cuda_vs_live_reference(gpu, cpu_oracle, name):
+    if not have_ref():
+        pytest.skip("oracle/_ref/libref_rtrenderer.so not on this box")
+    import oracle
+    case = scenes.CASES[name]
+    rec = cloud_of(cpu_oracle, case)
+    xyz, bgr = scenes.split_records(rec)
+    ref = oracle.RefOracle(xyz, bgr)
+    W, H, P = case.W, case.H, case.W * case.H
+    ref_frames = []
+    for E in case.poses:
+        o = {}
+        rc, color, depth = ref.computeRGBD(W, H, case.K, E)
+        assert rc == 1
+        o["raw_depth_host"], o["raw_color_host"] = depth.view(np.uint32), color
+        o["raw_zbuf"], o["raw_accum"], o["raw_image"] = ref.read("zbuf", P), ref.read("accum", P * 4), ref.read("image", P * 3)
+        rc, color, depth = ref.computeFilteredRGBD(W, H, case.K, E)
+        assert rc == 1
+        o["flt_depth_host"], o["flt_color_host"] = depth.view(np.uint32), color
+        o["flt_tensor"] = ref.read("tensor", P * 5)
+        o["flt_minmax"] = np.array([ref.read("min", 1)[0], ref.read("max", 1)[0]], np.uint32)
+        ref_frames.append(o)
+    ref.close()
+    mine, _, _ = render_mine(gpu, case, rec, with_taps=False)
+    assert_frames_equal(mine, ref_frames, f"{name} CUDA vs live reference")
+
+
+# ------------------------------------------------------------------ invariances / variants
+VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u)
+            for v, u, b in [(0, 1, 0), (1, 2, 2), (2, 4, 0), (3, 8, 2), (5, 4, 0), (7, 4, 2)]]
+
+
+@pytest.mark.parametrize("opts", VARIANTS)
+def test_kernel_variants_give_identical_frames(gpu, cpu_oracle, opts):
+    case = scenes.CASES["c1_640x480"]
+    rec = cloud_of(cpu_oracle, case)
+    base, _, _ = render_mine(gpu, case, rec, with_taps=False)
+    other, _, _ = render_mine(gpu, case, rec, options=opts, with_taps=False)
+    assert_frames_equal(other, base, f"variant {opts}")
+
+
+def test_generic_path_equals_fused_path(gpu, cpu_oracle):
+    for name in ("small_176x104", "c3_1920x1080"):
+        case = scenes.CASES[name]
+        rec = cloud_of(cpu_oracle, case)
+        base, _, _ = render_mine(gpu, case, rec, with_taps=False)
+        other, _, _ = render_mine(gpu, case, rec, options={"force_generic": 1}, with_taps=False)
+        assert_frames_equal(other, base, f"{name} generic vs fused")
+
+
+def test_point_order_does_not_matter(gpu, cpu_oracle):
+    case = scenes.CASES["c1_640x480"]
+    rec = cloud_of(cpu_oracle, case)
+    base, _, _ = render_mine(gpu, case, rec, with_taps=False)
+    perm = np.random.default_rng(7).permutation(len(rec))
+    other, _, _ = render_mine(gpu, case, np.ascontiguousarray(rec[perm]), with_taps=False)
+    assert_frames_equal(other, base, "shuffled cloud")
+
+
+def test_upload_xyz_bgr_equals_packed(gpu, cpu_oracle):
+    case = scenes.CASES["small_160x96"]
+    rec = cloud_of(cpu_oracle, case)
+    xyz, bgr = scenes.split_records(rec)
+    pc = gpu.ProjectCloud(xyz, bgr)
+    assert pc.cloud_size == len(rec)
+    assert np.array_equal(pc.download_cloud().view(np.uint32), rec.view(np.uint32))
+    pc.close()
+
+
+def test_device_synth_equals_oracle_synth(gpu, cpu_oracle):
+    n = 300_000
+    pc = gpu.ProjectCloud.synthetic(seed=99, n_total=n, hall=scenes.HALL_LARGE, n_boxes=12)
+    rec = cpu_oracle.synth_packed(99, n, 0, n, scenes.HALL_LARGE, 12)
+    assert np.array_equal(pc.download_cloud().view(np.uint32), rec.view(np.uint32))
+    pc.close()
+    pc = gpu.ProjectCloud.synthetic(seed=99, n_total=n, first=1000, count=5000, hall=scenes.HALL_LARGE, n_boxes=12)
+    assert np.array_equal(pc.download_cloud().view(np.uint32), rec[1000:6000].view(np.uint32))
+    pc.close()
+
+
+def test_key64_depth_is_reference_depth_and_colour_is_nearest_point(gpu, cpu_oracle):
+    case = scenes.CASES["c1_640x480"]
+    rec = cloud_of(cpu_oracle, case)
+    W, H, P = case.W, case.H, case.W * case.H
+    base, taps, _ = render_mine(gpu, case, rec)
+    pc = gpu.ProjectCloud.from_packed(rec)
+    pc.set_option("key64", 1)
+    color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+    assert pc.computeRGBD(calib_of(gpu, case), case.poses[0], color, depth) == 1
+    pc.close()
+    assert np.array_equal(depth.view(np.uint32), base[0]["raw_depth_host"])
+    # nearest point with the lowest index wins (deterministic 64-bit key)
+    pix, zb = taps[0]
+    live = np.nonzero(pix >= 0)[0]
+    key = (zb[live].astype(np.uint64) << np.uint64(32)) | live.astype(np.uint64)
+    best = np.full(P, np.iinfo(np.uint64).max, np.uint64)
+    np.minimum.at(best, pix[live], key)
+    hit = best != np.iinfo(np.uint64).max
+    idx = (best[hit] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    exp = np.zeros((P, 3), np.uint8)
+    c = scenes.bgra_of(rec)[idx]
+    exp[hit] = np.stack([c & 0xFF, (c >> 8) & 0xFF, (c >> 16) & 0xFF], axis=1).astype(np.uint8)
+    assert np.array_equal(color.reshape(P, 3), exp)
+
+
+def test_trajectory_equals_frame_by_frame(gpu, cpu_oracle):
+    case = scenes.CASES["c3_1920x1080"]
+    rec = cloud_of(cpu_oracle, case)
+    P = case.W * case.H
+    poses = np.stack([case.poses[i % 2] for i in range(5)])
+    pc = gpu.ProjectCloud.from_packed(rec)
+    calib = calib_of(gpu, case)
+    pc.set_camera(calib)
+    color = np.zeros((5, P * 3), np.uint8)
+    depth = np.zeros((5, P), np.float32)
+    pc.render_trajectory(gpu.STAGE_FILTERED, poses, color, depth)
+    pc.close()
+    # each frame set is persistent; with only filtered frames the stale 1080p tail is all-zero
+    one = gpu.ProjectCloud.from_packed(rec)
+    for i in range(5):
+        c1, d1 = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        one.computeFilteredRGBD(calib, poses[i], c1, d1)
+        assert np.array_equal(c1, color[i]) and np.array_equal(d1.view(np.uint32), depth[i].view(np.uint32)), f"frame {i}"
+    one.close()
+
+
+# ------------------------------------------------------------------ edge cases
+def _render_records(gpu, rec, W, H, m16, filtered=True):
+    pc = gpu.ProjectCloud.from_packed(rec)
+    c = gpu.CameraCalibration()
+    c.setWidth(W)
+    c.setHeight(H)
+    pc.set_camera(c)
+    pc.set_cam_proj_raw(m16)
+    color, depth = np.zeros(W * H * 3, np.uint8), np.zeros(W * H, np.float32)
+    fn = pc._lib.rtr_render_filtered if filtered else pc._lib.rtr_render_rgbd
+    pc._check(fn(pc._h, color.ctypes.data, depth.ctypes.data))
+    out = dict(color=color, depth=depth.view(np.uint32), tensor=pc.read("tensor", np.uint16, W * H * 5),
+               accum=pc.read("accum", np.uint32, W * H * 4), minmax=pc.read("minmax", np.uint32, 2))
+    tap = pc.project_points()
+    pc.close()
+    return out, tap
+
+
+def _oracle_records(cpu_oracle, rec, W, H, tap, filtered=True):
+    return cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(rec), W, H, filtered=filtered)
+
+
+def test_adversarial_points(gpu, cpu_oracle):
+    """NaN / inf / denormal / behind-camera / exactly-on-boundary / huge coordinates, many points per
+    pixel, colour sums near the byte limits."""
+    W, H = 64, 48
+    m = np.array([50, 0, 31.5, 0, 0, 50, 23.5, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
+    rng = np.random.default_rng(3)
+    n = 40_000
+    xyz = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    xyz[:, 2] = rng.uniform(0.5, 3.0, n).astype(np.float32)
+    special = np.array([[np.nan, 0, 1], [0, np.nan, 1], [0, 0, np.nan], [np.inf, 0, 1], [0, 0, np.inf], [-np.inf, 1, 1],
+                        [0, 0, 0], [0, 0, -0.0], [0, 0, -1], [1e-41, 1e-41, 1e-41], [1e-39, 0, 1e-39], [3e38, 3e38, 1],
+                        [3e38, 0, 3e38], [0, 0, 1e-45], [-0.63, -0.47, 1.0], [0.65, 0.49, 1.0], [-0.64, 0.0, 1.0],
+                        [0.01, 0.01, 1.0], [0.01, 0.01, 1.0199], [0.01, 0.01, 1.02], [0.01, 0.01, 1.0201]], np.float32)
+    xyz[:len(special)] = special
+    xyz[1000:3000, :2] = 0.0          # 2000 points in one pixel, depths spread around the 2 cm window
+    xyz[1000:3000, 2] = (1.0 + rng.uniform(0, 0.04, 2000)).astype(np.float32)
+    bgr = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    bgr[1000:2000] = 255
+    rec = gpu.pack_records(xyz, bgr)
+    for filtered in (False, True):
+        out, tap = _render_records(gpu, rec, W, H, m, filtered)
+        gold = _oracle_records(cpu_oracle, rec, W, H, tap, filtered)
+        assert np.array_equal(out["depth"], gold["zbuf"])
+        assert np.array_equal(out["accum"], gold["accum"])
+        assert np.array_equal(out["color"], gold["image"])
+        if filtered:
+            assert np.array_equal(out["tensor"], gold["tensor"])
+            assert np.array_equal(out["minmax"], gold["minmax"])
+
+
+def test_nothing_in_frustum_and_single_point(gpu, cpu_oracle):
+    W, H = 32, 16
+    m = np.array([20, 0, 15.5, 0, 0, 20, 7.5, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
+    behind = gpu.pack_records(np.array([[0, 0, -1.0], [0.1, 0.1, -2.0]], np.float32), np.full((2, 3), 200, np.uint8))
+    out, tap = _render_records(gpu, behind, W, H, m)
+    assert (tap[0] == -1).all()
+    assert (out["depth"] == np.float32(-1.0).view(np.uint32)).all() and not out["color"].any()
+    assert out["minmax"].tolist() == [0xFFFFFFFF, 0]
+    gold = _oracle_records(cpu_oracle, behind, W, H, tap)
+    assert np.array_equal(out["tensor"], gold["tensor"]) and np.array_equal(out["depth"], gold["zbuf"])
+    one = gpu.pack_records(np.array([[0.0, 0.0, 2.0]], np.float32), np.array([[10, 20, 30]], np.uint8))
+    out, tap = _render_records(gpu, one, W, H, m, filtered=False)
+    pix = 8 * W + 16  # rint(7.5) = 8, rint(15.5) = 16 (ties to even)
+    assert tap[0][0] == pix
+    assert out["depth"][pix] == np.float32(2.0).view(np.uint32) and out["color"].reshape(-1, 3)[pix].tolist() == [10, 20, 30]
+    assert (np.delete(out["depth"], pix) == 0x7F7FFFFF).all()
+
+
+def test_error_behaviour(gpu):
+    pc = gpu.ProjectCloud()
+    calib = gpu.CameraCalibration()
+    assert pc.computeRGBD(calib, np.eye(4), None, None) == -1          # project_cloud.cu:270-273
+    with pytest.raises(gpu.RtrError) as e:                             # no cloud uploaded
+        pc.computeRGBD(calib, np.eye(4), np.zeros(640 * 480 * 3, np.uint8), None)
+    assert e.value.code == gpu.RTR_ERR_STATE
+    with pytest.raises(gpu.RtrError):
+        pc.set_option("no_such_option", 1)
+    pc.close()
+
+
+def test_resolution_change_reallocates(gpu, cpu_oracle):
+    a, b = scenes.CASES["small_160x96"], scenes.CASES["small_176x104"]
+    rec = cloud_of(cpu_oracle, a)
+    pc = gpu.ProjectCloud.from_packed(rec)
+    outs = []
+    for case in (a, b, a):
+        P = case.W * case.H
+        color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        pc.computeFilteredRGBD(calib_of(gpu, case), case.poses[0], color, depth)
+        outs.append((color, depth.view(np.uint32)))
+    pc.close()
+    assert np.array_equal(outs[0][0], outs[2][0]) and np.array_equal(outs[0][1], outs[2][1])
+    fresh = gpu.ProjectCloud.from_packed(rec)
+    P = b.W * b.H
+    color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+    fresh.computeFilteredRGBD(calib_of(gpu, b), b.poses[0], color, depth)
+    fresh.close()
+    assert np.array_equal(outs[1][0], color) and np.array_equal(outs[1][1], depth.view(np.uint32))
+
+
+def test_distortion_matches_opencv_model(gpu, cpu_oracle):
+    """New feature (the reference never applies distortion): parity unpinned, checked against
+    cv2.projectPoints; tolerance: the rounded pixel may differ by at most 1 in u or v, and for
+    >= 99.9 % of the points it is identical."""
+    cv2 = pytest.importorskip("cv2")
+    case = scenes.CASES["c2_1280x720"]
+    rec = cloud_of(cpu_oracle, case)[:500_000]
+    dist = [-0.05, 0.01, 0.0005, -0.0005, 0.0]
+    pc = gpu.ProjectCloud.from_packed(rec, apply_distortion=True)
+    calib = calib_of(gpu, case)
+    calib.setDistortionParameters(dist)
+    E = case.poses[0]
+    pc.set_camera(calib, E)
+    pix, zb = pc.project_points()
+    pc.close()
+    xyz = rec[:, :3].astype(np.float64)
+    cam = xyz @ E[:3, :3].T + E[:3, 3]
+    front = cam[:, 2] > 0.05
+    uv, _ = cv2.projectPoints(cam[front].reshape(-1, 1, 3), np.zeros(3), np.zeros(3), case.K, np.array(dist))
+    uv = uv.reshape(-1, 2)
+    u, v = np.rint(uv[:, 0]).astype(np.int64), np.rint(uv[:, 1]).astype(np.int64)
+    inside = (u >= 0) & (u < case.W) & (v >= 0) & (v < case.H)
+    got = pix[front]
+    both = inside & (got >= 0)
+    assert both.sum() > 50_000
+    gu, gv = got[both] % case.W, got[both] // case.W
+    du, dv = np.abs(gu - u[both]), np.abs(gv - v[both])
+    assert du.max() <= 1 and dv.max() <= 1
+    assert ((du == 0) & (dv == 0)).mean() >= 0.999
+    # in/out disagreement only at the image border
+    assert (inside != (got >= 0)).mean() < 2e-3
+    # depth is the camera-space z
+    z = zb[front][both].view(np.float32)
+    assert np.allclose(z, cam[front][both, 2], rtol=1e-5)
