@@ -94,7 +94,11 @@ def test_cuda_vs_cpu_oracle_all_stages(gpu, cpu_oracle, name):
     ex = extras[-1]
     for i in range(1, 5):
         n = ex["up"][i][0] * ex["up"][i][1] if case.W % 16 == 0 else flt["levels"][i].size
-        assert np.array_equal(ex["levels"][i][:n].view(np.uint32), flt["levels"][i][:n].view(np.uint32)), f"level {i}"
+        a, b = ex["levels"][i][:n], flt["levels"][i][:n]
+        # hole-filled levels can hold NaN (bilinear of FLT_MAX overflows to inf - inf); its sign/payload is
+        # not defined by IEEE (x86 gives 0xFFC00000, the GPU 0x7FFFFFFF) and no comparison ever sees it
+        same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), f"level {i}"
     for i in range(4):
         assert np.array_equal(ex["masks"][i], flt["masks"][i]), f"mask {i}"
 
