@@ -48,7 +48,7 @@ WORKLOADS = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
@@ -106,7 +106,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         if self.nv:
@@ -136,7 +136,7 @@ def trajectory(pkg, hall, n_poses):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_port_baseline(args, wl, sample_points, min_seconds=10.0, max_frames=6):
+def cpu_port_baseline(args, wl, sample_points, min_seconds=12.0, max_frames=400):
     """OpenMP CPU port of the same frame (oracle/rtr_oracle.c) on a bounded sample: the same scene
     and camera at `sample_points` points.  Returns the cpu_baseline object."""
     import oracle

@@ -135,6 +135,13 @@ int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, i
 /* Number of kernel launches issued by this renderer since creation. */
 uint64_t rtr_launch_count(const rtr_renderer* r);
 
+/* Measurement support: RED.MIN throughput into a W*H L2-resident buffer (u32, or u64 with key64).
+ * mode 0: n_ops uniformly random addresses generated in registers; mode 1: the pixel ids the
+ * current cloud + camera project to (n_ops = cloud size; *live_ops = in-frustum points, the number
+ * of REDs really issued).  Returns the mean CUDA-event time of one launch. */
+int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int iters, float* ms_per_launch,
+                      uint64_t* live_ops);
+
 /* ---- point-sharded multi-GPU (one process per GPU; plumbing by the caller, e.g. torch.distributed).
  * rtr_comm_unique_id fills a 128-byte NCCL id on rank 0; broadcast it, then every rank calls
  * rtr_comm_init.  With a communicator attached, rendering merges the per-GPU z-buffers with

@@ -63,6 +63,7 @@ API = {
     "rtr_get_stage_ms": (_i, [_vp, _fp]),
     "rtr_get_stage_ms_sum": (_i, [_vp, _dp, C.POINTER(_u64), _i]),
     "rtr_launch_count": (_u64, [_vp]),
+    "rtr_bench_red_min": (_i, [_vp, _i, _u64, _i, _i, _fp, C.POINTER(_u64)]),
     "rtr_comm_unique_id": (_i, [_vp]),
     "rtr_comm_init": (_i, [_vp, _vp, _i, _i]),
     "rtr_comm_destroy": (_i, [_vp]),
@@ -293,6 +294,12 @@ class ProjectCloud:
         n = _u64(0)
         self._check(self._lib.rtr_get_stage_ms_sum(self._h, ms.ctypes.data_as(_dp), C.byref(n), int(reset)))
         return ms, int(n.value)
+
+    def bench_red_min(self, mode: int, n_ops: int = 0, key64: bool = False, iters: int = 5):
+        """(ms per launch, REDs issued per launch) of the L2 atomic micro-benchmark."""
+        ms, live = C.c_float(0), _u64(0)
+        self._check(self._lib.rtr_bench_red_min(self._h, mode, n_ops, int(key64), iters, C.byref(ms), C.byref(live)))
+        return float(ms.value), int(live.value)
 
     @property
     def cloud_size(self) -> int:

@@ -64,4 +64,8 @@ cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const Pyramid
 cudaError_t launch_synth(cudaStream_t s, uint64_t seed, uint64_t n_total, uint64_t first, uint64_t count, int lx,
                          int ly, int lz, int nbox, PointRecord* out);
 
+// ---- L2 atomic micro-benchmark (rtr_microbench.cu; measurement support)
+cudaError_t launch_red_bench(cudaStream_t s, int sm_count, int mode, bool key64, const int32_t* pix, uint64_t n_ops,
+                             uint32_t n_px, uint32_t* z32, unsigned long long* z64);
+
 }  // namespace rtr

@@ -657,6 +657,60 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
     return RTR_OK;
 }
 
+int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int iters, float* ms_per_launch,
+                      uint64_t* live_ops) {
+    if (!r || !ms_per_launch || iters < 1 || (mode != 0 && mode != 1)) return RTR_ERR_ARG;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    ProjParams pp;
+    int rc = make_params(r, pp);
+    if (rc != RTR_OK) return rc;
+    const uint64_t P = uint64_t(r->W) * r->H;
+    if (mode == 1) {
+        if (!r->points || r->n_points == 0) return fail(r, RTR_ERR_STATE, "no cloud uploaded");
+        n_ops = r->n_points;
+    }
+    void* zb = nullptr;
+    int32_t* d_pix = nullptr;
+    uint32_t* d_z = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaMalloc(&zb, P * (key64 ? 8 : 4));
+    if (e == cudaSuccess) e = cudaMemsetAsync(zb, 0xFF, P * (key64 ? 8 : 4), r->stream);
+    if (e == cudaSuccess && mode == 1) {
+        e = cudaMalloc(reinterpret_cast<void**>(&d_pix), n_ops * 4);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_z), n_ops * 4);
+        if (e == cudaSuccess) e = launch_project_dump(r->stream, r->points, n_ops, pp, d_pix, d_z);
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    for (int it = 0; it < iters + 1 && e == cudaSuccess; ++it) {  // first launch = warm-up
+        if (it == 1) e = cudaEventRecord(e0, r->stream);
+        if (e == cudaSuccess)
+            e = launch_red_bench(r->stream, r->sm_count, mode, key64 != 0, d_pix, n_ops, uint32_t(P),
+                                 static_cast<uint32_t*>(zb), static_cast<unsigned long long*>(zb));
+        r->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(e1, r->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_launch = ms / float(iters);
+    if (live_ops) {
+        *live_ops = n_ops;
+        if (mode == 1 && e == cudaSuccess) {  // count the in-frustum points on the host (measurement support only)
+            std::vector<int32_t> h(n_ops);
+            e = cudaMemcpy(h.data(), d_pix, n_ops * 4, cudaMemcpyDeviceToHost);
+            uint64_t c = 0;
+            for (int32_t v : h) c += (v >= 0);
+            *live_ops = c;
+        }
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(zb); cudaFree(d_pix); cudaFree(d_z);
+    if (e != cudaSuccess) return cuda_fail(r, e, "rtr_bench_red_min");
+    return RTR_OK;
+}
+
 static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "zmin_variant")) return &r->zmin_variant;
     if (!std::strcmp(key, "zmin_unroll")) return &r->zmin_unroll;
