@@ -203,7 +203,8 @@ def run_reference(args, wl):
     bgr = np.stack([c & 0xFF, (c >> 8) & 0xFF, (c >> 16) & 0xFF], axis=1).astype(np.uint8)
     xyz = np.ascontiguousarray(rec[:, :3])
     del rec, c
-    ref = oracle.RefOracle(xyz, bgr)
+    stock = os.path.exists(oracle.REF_LIB_STOCK)   # timing build: no zero-initialising cudaMalloc prelude
+    ref = oracle.RefOracle(xyz, bgr, stock=stock)
     del xyz, bgr
     K = np.array([[f, 0, cx], [0, f, cy], [0, 0, 1]], np.float64)
     poses = trajectory(pkg, hall, n_poses)
@@ -236,7 +237,7 @@ def run_reference(args, wl):
                                         "compiled unmodified for sm_100, one host thread driving one B200), not a CPU implementation"},
                 e2e={"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 reference_kernels_ms={"clear": float(kms[0]), "minDepthPass": float(kms[1]), "accumulatePass": float(kms[2]),
-                                      "resolvePass": float(kms[3]), "block_size": ref.block_size,
+                                      "resolvePass": float(kms[3]), "block_size": ref.block_size, "build": "stock" if stock else "zero-init parity build",
                                       "minDepthPass_GBps_at_16B_per_point": 16.0 * n / (float(kms[1]) * 1e-3) / 1e9})
     line["config"]["note"] = "unmodified reference CUDA code through ProjectCloud::compute*RGBD with host outputs (sync + pageable D2H per frame, as shipped)"
     ref.close()

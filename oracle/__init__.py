@@ -17,7 +17,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CPU_LIB = os.path.join(HERE, "liboracle_cpu.so")
-REF_LIB = os.path.join(HERE, "_ref", "libref_rtrenderer.so")
+REF_LIB = os.path.join(HERE, "_ref", "libref_rtrenderer.so")              # parity build (zero-initialising cudaMalloc)
+REF_LIB_STOCK = os.path.join(HERE, "_ref", "libref_rtrenderer_stock.so")  # timing build (reference exactly as shipped)
 REFERENCE_ROOT = "/root/reference"
 
 _vp, _i, _u64 = C.c_void_p, C.c_int, C.c_uint64
@@ -32,7 +33,7 @@ def build_cpu(force: bool = False) -> str:
 
 def build_ref() -> str | None:
     """Compile the reference where it lies; only possible where /root/reference exists."""
-    if os.path.exists(REF_LIB):
+    if os.path.exists(REF_LIB) and os.path.exists(REF_LIB_STOCK):
         return REF_LIB
     if not os.path.isdir(REFERENCE_ROOT):
         return None
@@ -164,10 +165,11 @@ class CpuOracle:
 class RefOracle:
     """The reference's ProjectCloud, compiled unmodified (GPU required)."""
 
-    def __init__(self, xyz: np.ndarray, bgr: np.ndarray):
-        if not os.path.exists(REF_LIB):
-            raise RuntimeError("oracle/_ref/libref_rtrenderer.so missing: run `make -C oracle ref` where /root/reference exists")
-        self.lib = C.CDLL(REF_LIB)
+    def __init__(self, xyz: np.ndarray, bgr: np.ndarray, stock: bool = False):
+        path = REF_LIB_STOCK if stock else REF_LIB
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(path)
         L = self.lib
         L.ref_create.restype = _vp
         L.ref_create.argtypes = [_vp, _vp, C.c_size_t]

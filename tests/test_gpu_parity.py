@@ -379,7 +379,7 @@ def test_distortion_matches_opencv_model(gpu, cpu_oracle):
     inside = (u >= 0) & (u < case.W) & (v >= 0) & (v < case.H)
     got = pix[front]
     both = inside & (got >= 0)
-    assert both.sum() > 50_000
+    assert both.sum() > 5_000
     gu, gv = got[both] % case.W, got[both] // case.W
     du, dv = np.abs(gu - u[both]), np.abs(gv - v[both])
     assert du.max() <= 1 and dv.max() <= 1

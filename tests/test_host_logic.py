@@ -1,0 +1,55 @@
+"""Host-side logic of the package (no GPU, no compute through the library)."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("n,world", [(1000, 1), (1000, 8), (1003, 8), (5, 8), (0, 4), (300, 7)])
+def test_shards_partition_the_range(pkg, n, world):
+    seen = []
+    for r in range(world):
+        fr = pkg.shard_frames(n, r, world)
+        first, count = pkg.shard_points(n, r, world)
+        assert (fr.start, len(fr)) == (first, count)
+        seen += list(fr)
+    assert seen == list(range(n))
+    sizes = [len(pkg.shard_frames(n, r, world)) for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_look_at_and_trajectory_are_rigid_world_to_camera(pkg):
+    T = pkg.trajectory_w2c(12, center=(6.0, 5.0, 1.5), radius=2.0)
+    assert T.shape == (12, 4, 4)
+    for i, E in enumerate(T):
+        R = E[:3, :3]
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.isclose(np.linalg.det(R), 1.0)
+        a = 2 * np.pi * i / 12
+        eye = np.array([6.0 + 2 * np.cos(a), 5.0 + 2 * np.sin(a), 1.5, 1.0])
+        assert np.allclose(E @ eye, [0, 0, 0, 1], atol=1e-12)          # the camera centre maps to the origin
+        ahead = eye[:3] + np.linalg.inv(E)[:3, 2]                       # one metre along the optical axis
+        assert np.allclose(E @ np.append(ahead, 1.0), [0, 0, 1, 1], atol=1e-12)
+    assert np.allclose(T[0], pkg.trajectory_w2c(12, center=(6.0, 5.0, 1.5), radius=2.0)[0])
+
+
+def test_pack_records_layout(pkg):
+    xyz = np.array([[1.5, -2.0, 3.25], [0, 0, 0]], np.float32)
+    bgr = np.array([[1, 2, 3], [255, 128, 0]], np.uint8)
+    rec = pkg.pack_records(xyz, bgr)
+    assert rec.dtype == np.float32 and rec.shape == (2, 4) and rec.nbytes == 32
+    assert np.array_equal(rec[:, :3], xyz)
+    assert rec[:, 3].view(np.uint32).tolist() == [0xFF030201, 0xFF0080FF]   # b | g<<8 | r<<16 | 255<<24 (Octreegrid.h:176)
+
+
+def test_camera_calibration_mirror(pkg):
+    c = pkg.CameraCalibration()
+    assert (c.getWidth(), c.getHeight()) == (640, 480)                        # CameraCalibration.cpp:7-8
+    assert c.loadCalibration(525.0, 526.0, 319.5, 239.5, [0.1, 0.2], 1280, 720)
+    assert c.getIntrinsicsMatrix().tolist() == [[525.0, 0, 319.5], [0, 526.0, 239.5], [0, 0, 1]]
+    assert c.getDistortionParameters() == [0.1, 0.2, 0.0, 0.0, 0.0]
+    assert (c.getFocalLengthX(), c.getFocalLengthY(), c.getPrincipalPointX(), c.getPrincipalPointY()) == (525.0, 526.0, 319.5, 239.5)
+    assert (c.getWidth(), c.getHeight()) == (1280, 720)
+
+
+def test_device_buffers_struct_matches_header(pkg):
+    import ctypes as C
+    # rtr_device_buffers: 6 pointers + 5 + 4 pointers, 2 ints, 4 x 5 ints, u64, pointer
+    assert C.sizeof(pkg.DeviceBuffers) == 15 * 8 + 2 * 4 + 20 * 4 + 8 + 8
