@@ -346,26 +346,66 @@ def run_b200(args, wl):
     value = points_per_frame * frames_total / (ms * 1e-3) / 1e9
 
     # ---- leg 2: same loop with per-stage CUDA events (roofline of the dominant kernel)
-    pc.set_option("timing", 2)
-    pc.stage_ms_sum(reset=True)
-    ms_t, _ = timed_device_loop()
-    sums, nfr = pc.stage_ms_sum(reset=True)
-    pc.set_option("timing", 0)
-    stage_ms = (sums / max(nfr, 1)).tolist()   # includes the warm-up frames of this loop (same work)
     peak, peak_src = peaks()
-    zmin_ms, blend_ms = stage_ms[1], stage_ms[2]
-    achieved = 16.0 * count / (zmin_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "zmin_kernel (project + cull + z-min, 16 B/point read)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBps": achieved / 8000.0,
-                "peak_source": peak_src, "traffic": None, "launch_ms": zmin_ms,
-                "blend_kernel": {"launch_ms": blend_ms, "achieved": 16.0 * count / (blend_ms * 1e-3) / 1e9,
-                                 "frac": 16.0 * count / (blend_ms * 1e-3) / 1e9 / peak},
-                "stage_ms": dict(zip(["clear", "zmin", "blend", "resolve_pyramid_minmax", "up_pass_tensor", "frame"], stage_ms)),
-                "frame_ms_with_stage_events": ms_t / K_steps}
+    names = ["clear_classify", "zmin", "blend", "resolve_pyramid_minmax", "up_pass_tensor", "frame"]
+
+    def staged_loop():
+        pc.set_option("timing", 2)
+        pc.stage_ms_sum(reset=True)
+        pc.cull_stats(reset=True)
+        ms_t, _ = timed_device_loop()
+        sums, nfr = pc.stage_ms_sum(reset=True)
+        cf, cvis, nch = pc.cull_stats(reset=True)
+        pc.set_option("timing", 0)
+        return (sums / max(nfr, 1)).tolist(), ms_t / K_steps, (cvis / cf if cf else None), nch   # warm-up frames included (same work)
+
+    culling = bool(pc.get_option("chunk_cull"))
+    stage_ms, frame_ms_ev, vis_chunks, n_chunks = staged_loop()
+    streamed = count if not (culling and vis_chunks is not None) else min(count, vis_chunks * 1024.0)
+
+    def kernel_line(ms, pts):
+        a = 16.0 * pts / (ms * 1e-3) / 1e9
+        return {"launch_ms": ms, "achieved": a, "frac": a / peak, "frac_of_nominal_8TBps": a / 8000.0}
+    dom = "zmin" if stage_ms[1] >= stage_ms[2] else "blend"
+    dom_ms = max(stage_ms[1], stage_ms[2])
+    kl = kernel_line(dom_ms, streamed)
+    roofline = {"bound": "hbm",
+                "kernel": (f"{dom}_list_kernel (walks the frame's visible 1024-point chunks: 16 B/point read for the "
+                           f"{streamed / count * 100:.1f}% of the cloud inside or near the frustum)") if culling
+                else f"{dom}_kernel (every point streamed, 16 B/point read)",
+                "achieved": kl["achieved"], "peak": peak, "unit": "GB/s", "frac": kl["frac"],
+                "frac_of_nominal_8TBps": kl["frac_of_nominal_8TBps"], "peak_source": peak_src, "traffic": None,
+                "launch_ms": dom_ms, "algorithmic_bytes_per_launch": 16.0 * streamed,
+                "points_streamed_per_launch": streamed, "points_in_cloud": count,
+                "zmin": kernel_line(stage_ms[1], streamed), "blend": kernel_line(stage_ms[2], streamed),
+                "stage_ms": dict(zip(names, stage_ms)), "frame_ms_with_stage_events": frame_ms_ev}
+    if culling:
+        # the same trajectory with chunk culling off: every record of the cloud is streamed by both passes
+        # (the configuration north_star's "16 B/point against the HBM roofline" is quoted on)
+        roofline["visible_chunks_per_frame"], roofline["chunks_in_cloud"] = vis_chunks, n_chunks
+        pc.set_option("chunk_cull", 0)
+        sm_all, fm_all, _, _ = staged_loop()
+        ms_all, _ = timed_device_loop()
+        pc.set_option("chunk_cull", 1)
+        roofline["stream_all"] = {"note": "chunk_cull=0: zmin_kernel / blend_kernel stream all points, 16 B/point/pass",
+                                  "zmin": kernel_line(sm_all[1], count), "blend": kernel_line(sm_all[2], count),
+                                  "stage_ms": dict(zip(names, sm_all)), "ms_per_step": max_over_ranks(ms_all) / K_steps,
+                                  "value_gpoints_per_s": points_per_frame * frames_total / (max_over_ranks(ms_all) * 1e-3) / 1e9}
+    if world == 1:
+        # second bound named by north_star: L2 atomic (RED) throughput into a frame-sized buffer
+        set_pose(Wm)
+        ms_rand, ops_rand = pc.bench_red_min(0, 200_000_000, False)
+        _, live = pc.bench_red_min(1, 0, False, iters=1)
+        red_peak = ops_rand / ms_rand / 1e6
+        roofline["l2_atomics"] = {"measured_red_min_u32_random_Gops": red_peak, "in_frustum_points_this_pose": live,
+                                  "zmin_upper_bound_red_Gops": live / stage_ms[1] / 1e6,
+                                  "zmin_frac_of_measured_red_peak": live / stage_ms[1] / 1e6 / red_peak,
+                                  "blend_upper_bound_red64_Gops": 2 * live / stage_ms[2] / 1e6,
+                                  "note": "upper bounds: one RED per in-frustum point (z-min, before the early depth test) / two 64-bit REDs per in-frustum point (blend)"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(f"zmin_{args.workload}")
+            roofline["traffic"] = json.load(open(tr)).get(f"{dom}_{args.workload}")
         except Exception:
             pass
 
@@ -415,7 +455,7 @@ def run_b200(args, wl):
             "config": {"workload": f"{args.workload}: {points_per_frame} points, {W}x{H}, stage {args.stage}, {n_poses}-pose trajectory",
                        "sharding": ("frame-sharded, cloud replicated" if args.mode == "frames" else "point-sharded, NCCL min/sum all-reduce"),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
-                       "options": {k: pc.get_option(k) for k in ("zmin_variant", "zmin_unroll", "blend_variant", "blend_unroll", "key64")}},
+                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "zmin_variant", "zmin_unroll", "blend_variant", "blend_unroll", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

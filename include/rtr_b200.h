@@ -123,7 +123,7 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
 
 /* ---- options / introspection.  Known keys: "zmin_variant" (bit0 early test, bit1 warp
  * aggregation, bit2 L1-cached test), "zmin_unroll", "blend_variant", "blend_unroll",
- * "force_generic", "keep_masks", "timing", "key64". */
+ * "force_generic", "keep_masks", "timing", "key64", "chunk_cull". */
 int rtr_set_option(rtr_renderer* r, const char* key, int64_t value);
 int64_t rtr_get_option(const rtr_renderer* r, const char* key);
 /* With option timing=1: CUDA-event ms of the last frame's stages
@@ -132,6 +132,10 @@ int rtr_get_stage_ms(rtr_renderer* r, float* ms6);
 /* With option timing=2 every frame records its own six events (pooled); this returns the per-stage
  * SUMS in ms over all frames rendered since the last reset, and how many frames that was. */
 int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, int reset);
+/* Chunk-level frustum culling statistics since the last reset: frames rendered with culling, the sum
+ * over those frames of the chunks (1024 consecutive points) that were streamed, and the cloud's
+ * chunk count.  Option "chunk_cull" (default 1) switches the culling; results are identical. */
+int rtr_get_cull_stats(rtr_renderer* r, uint64_t* frames, uint64_t* visible_chunks_total, uint64_t* n_chunks, int reset);
 /* Number of kernel launches issued by this renderer since creation. */
 uint64_t rtr_launch_count(const rtr_renderer* r);
 

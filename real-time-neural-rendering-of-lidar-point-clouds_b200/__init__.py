@@ -62,6 +62,7 @@ API = {
     "rtr_get_option": (_i64, [_vp, C.c_char_p]),
     "rtr_get_stage_ms": (_i, [_vp, _fp]),
     "rtr_get_stage_ms_sum": (_i, [_vp, _dp, C.POINTER(_u64), _i]),
+    "rtr_get_cull_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _i]),
     "rtr_launch_count": (_u64, [_vp]),
     "rtr_bench_red_min": (_i, [_vp, _i, _u64, _i, _i, _fp, C.POINTER(_u64)]),
     "rtr_comm_unique_id": (_i, [_vp]),
@@ -294,6 +295,12 @@ class ProjectCloud:
         n = _u64(0)
         self._check(self._lib.rtr_get_stage_ms_sum(self._h, ms.ctypes.data_as(_dp), C.byref(n), int(reset)))
         return ms, int(n.value)
+
+    def cull_stats(self, reset: bool = True):
+        """(frames, visible chunks summed over those frames, chunks in the cloud)."""
+        f, v, n = _u64(0), _u64(0), _u64(0)
+        self._check(self._lib.rtr_get_cull_stats(self._h, C.byref(f), C.byref(v), C.byref(n), int(reset)))
+        return int(f.value), int(v.value), int(n.value)
 
     def bench_red_min(self, mode: int, n_ops: int = 0, key64: bool = False, iters: int = 5):
         """(ms per launch, REDs issued per launch) of the L2 atomic micro-benchmark."""

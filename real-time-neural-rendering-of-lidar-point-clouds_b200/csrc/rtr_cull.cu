@@ -1,0 +1,158 @@
+// Chunk-level frustum culling for the two point passes (sm_100a).
+//
+// The reference tests every point against the image rectangle inside minDepthPass/accumulatePass
+// (render.cu:63-68, 96-101) and therefore streams the whole cloud twice per frame, although a
+// camera inside a scan sees a fraction of it.  The reference loader delivers points grouped by
+// 0.25 m cell (cloudreader.cpp:47-60, Octreegrid.h:162-170), so kChunkPoints consecutive records
+// form a compact box.  At upload we store each chunk's axis-aligned bounds; per frame one thread
+// per chunk decides whether ANY point of the box can survive the reference's per-point test and
+// appends the survivors to a compact list that the point passes walk.
+//
+// The test must never drop a chunk holding a point the reference would keep.  For a point p of
+// the box, with R0,R1,R2 the camProj rows, the reference computes in float
+//     rx_f = R0.p (+-ex)   ry_f = R1.p (+-ey)   rz_f = R2.p (+-ez)
+// where e* <= gamma * (sum_j |R_ij| |p_j| + |R_i3|), gamma = 2^-20 (the true bound of the
+// mul/fma/fma/add chain is < 2^-22), keeps the point iff rz_f > 0 and
+// u = rint(rx_f * rcp(rz_f)) in [0, W) (same for v), and rcp/mul add < 2^-21 relative error.
+// A chunk is dropped only if one of these holds for the whole box (interval arithmetic in double):
+//     behind : max R2.p + ez < 0                                  -> rz_f < 0 for every point
+//     left   : max (R0 + 1.5 R2).p + (ex + 1.5 ez) < 0            -> rx_f/rz_f < -1.5  -> u <= -1
+//     right  : min (R0 - (W+0.5) R2).p - (ex + (W+0.5) ez) > 0    -> rx_f/rz_f > W+0.5 -> u >= W
+//     top / bottom likewise with R1, H.
+// (one extra pixel of margin on each side).  NaN anywhere makes every comparison false, i.e. keeps
+// the chunk; chunks holding a non-finite or huge (> 2^40) coordinate are always kept (the reference
+// maps NaN depth to pixel 0 and __fdividef returns 0 for |z| > 2^126).  DESIGN.md "chunk culling".
+#include "rtr_kernels.h"
+
+namespace rtr {
+
+// ---------------------------------------------------------------- bounds of every chunk (at upload)
+__global__ void __launch_bounds__(256) chunk_bounds_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                           ChunkBounds* __restrict__ bounds) {
+    __shared__ float s_lo[3][8], s_hi[3][8];
+    __shared__ uint32_t s_bad[8];
+    const uint64_t first = uint64_t(blockIdx.x) * kChunkPoints;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    uint32_t bad = 0;
+    for (int k = 0; k < kChunkPoints / 256; ++k) {
+        const uint64_t i = first + uint64_t(k) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const PointRecord p = pts[i];
+        const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (!(fabsf(c[a]) <= 1.0995116e12f)) bad = 1;  // NaN, inf or > 2^40
+            lo[a] = fminf(lo[a], c[a]);
+            hi[a] = fmaxf(hi[a], c[a]);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
+        }
+    }
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_lo[a][warp] = lo[a]; s_hi[a][warp] = hi[a]; }
+        s_bad[warp] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ChunkBounds b;
+        b.always_visible = 0;
+        b.pad = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float l = s_lo[a][0], h = s_hi[a][0];
+            for (int w = 1; w < 8; ++w) { l = fminf(l, s_lo[a][w]); h = fmaxf(h, s_hi[a][w]); }
+            b.lo[a] = l;
+            b.hi[a] = h;
+        }
+        for (int w = 0; w < 8; ++w) b.always_visible |= s_bad[w];
+        bounds[blockIdx.x] = b;
+    }
+}
+
+// ---------------------------------------------------------------- per-frame classification
+struct Interval { double lo, hi; };
+// range of f.p over the box, f = (f0,f1,f2,f3)
+__device__ __forceinline__ Interval box_range(const double f[4], const double lo[3], const double hi[3]) {
+    Interval r{f[3], f[3]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double u = f[a] * lo[a], v = f[a] * hi[a];
+        r.lo += fmin(u, v);
+        r.hi += fmax(u, v);
+    }
+    return r;
+}
+// gamma * (sum |f_a| max|p_a| + |f3|): bound of the float evaluation error of row f over the box
+__device__ __forceinline__ double row_err(const double f[4], const double mabs[3]) {
+    return 9.5367431640625e-7 * (fabs(f[0]) * mabs[0] + fabs(f[1]) * mabs[1] + fabs(f[2]) * mabs[2] + fabs(f[3]));
+}
+
+__global__ void __launch_bounds__(256) classify_chunks_kernel(const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
+                                                              const __grid_constant__ CullParams cp,
+                                                              uint32_t* __restrict__ vis_list,
+                                                              CullState* __restrict__ cull) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool visible = false;
+    if (c < n_chunks) {
+        const ChunkBounds b = bounds[c];
+        visible = true;
+        if (!b.always_visible) {
+            const double lo[3] = {b.lo[0], b.lo[1], b.lo[2]}, hi[3] = {b.hi[0], b.hi[1], b.hi[2]};
+            const double mabs[3] = {fmax(fabs(lo[0]), fabs(hi[0])), fmax(fabs(lo[1]), fabs(hi[1])), fmax(fabs(lo[2]), fabs(hi[2]))};
+            const double ex = row_err(cp.r0, mabs), ey = row_err(cp.r1, mabs), ez = row_err(cp.r2, mabs);
+            const bool sane = (ex < 1e30) & (ey < 1e30) & (ez < 1e30);  // false for NaN / inf / absurd matrices
+            if (sane) {
+                const double cl = 1.5, cr = cp.W + 0.5, cb = cp.H + 0.5;
+                double f[4];
+                bool cut = box_range(cp.r2, lo, hi).hi + ez < 0.0;  // behind
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] + cl * cp.r2[k];
+                cut = cut || (box_range(f, lo, hi).hi + (ex + cl * ez) < 0.0);  // left
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] - cr * cp.r2[k];
+                cut = cut || (box_range(f, lo, hi).lo - (ex + cr * ez) > 0.0);  // right
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] + cl * cp.r2[k];
+                cut = cut || (box_range(f, lo, hi).hi + (ey + cl * ez) < 0.0);  // top
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] - cb * cp.r2[k];
+                cut = cut || (box_range(f, lo, hi).lo - (ey + cb * ez) > 0.0);  // bottom
+                visible = !cut;
+            }
+        }
+    }
+    // warp-aggregated append
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, visible);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&cull->n_visible, uint32_t(__popc(m)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (visible) vis_list[base + __popc(m & ((1u << lane) - 1u))] = c;
+    }
+    if (c == 0) cull->armed = 1u;
+}
+
+cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds) {
+    if (n == 0) return cudaSuccess;
+    chunk_bounds_kernel<<<unsigned((n + kChunkPoints - 1) / kChunkPoints), 256, 0, s>>>(pts, n, bounds);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_classify_chunks(cudaStream_t s, const ChunkBounds* bounds, uint32_t n_chunks, const CullParams& cp,
+                                   uint32_t* vis_list, CullState* cull) {
+    if (n_chunks == 0) return cudaSuccess;
+    classify_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, s>>>(bounds, n_chunks, cp, vis_list, cull);
+    return cudaGetLastError();
+}
+
+}  // namespace rtr

@@ -6,7 +6,28 @@
 
 namespace rtr {
 
-constexpr int kPointBlock = 256;  // threads per CTA of the two point passes
+constexpr int kPointBlock = 256;    // threads per CTA of the two point passes
+constexpr int kChunkPoints = 1024;  // points per culling chunk (= one CTA tile at unroll 4)
+
+// Axis-aligned bounds of one chunk of kChunkPoints consecutive records (rtr_cull.cu).
+struct ChunkBounds {
+    float lo[3], hi[3];
+    uint32_t always_visible;  // a coordinate is NaN/inf or huge: never cull (NaN points are live in the reference)
+    uint32_t pad;
+};
+// Per-renderer culling state in device memory.
+struct CullState {
+    uint32_t n_visible;            // chunks in vis_list for the frame being rendered
+    uint32_t armed;                // set by classify, cleared when the count is folded into the totals
+    uint32_t frames;               // frames folded into total_visible
+    uint32_t pad;
+    unsigned long long total_visible;
+};
+// The frame's camera for the chunk test, in double (exact images of the float camProj rows).
+struct CullParams {
+    double r0[4], r1[4], r2[4];
+    double W, H;
+};
 
 // Pyramid geometry exactly as applyDepthFilter derives it (project_cloud.cu:336-362): true level
 // dims are halved (floor) four times on the way down, the up-pass re-doubles the level-4 dims.
@@ -29,7 +50,19 @@ inline uint64_t clear_coverage(int W, int H) {  // fillBuffer/resolvePass grid: 
 
 // ---- point passes (rtr_point_kernels.cu)
 cudaError_t launch_clear(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum, uint64_t n_px,
-                         uint32_t* minmax);
+                         uint32_t* minmax, CullState* cull);
+// Point passes over the frame's visible chunks only (persistent grid over the compacted list).
+cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
+                             uint64_t index_base, const ProjParams& pp, const CullState* cull, const uint32_t* vis_list,
+                             uint32_t* zbuf, unsigned long long* zkey);
+cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
+                              const ProjParams& pp, const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf,
+                              uint32_t* accum);
+
+// ---- chunk-level frustum culling (rtr_cull.cu)
+cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds);
+cudaError_t launch_classify_chunks(cudaStream_t s, const ChunkBounds* bounds, uint32_t n_chunks, const CullParams& cp,
+                                   uint32_t* vis_list, CullState* cull);
 cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                         uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,

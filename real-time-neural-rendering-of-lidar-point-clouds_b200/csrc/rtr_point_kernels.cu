@@ -25,12 +25,18 @@ namespace rtr {
 // zbuf[0, cov) = FLT_MAX bits ; accum[0, 4P) = 0 ; minmax = {UINT_MAX, 0}.
 __global__ void __launch_bounds__(256) clear_kernel(uint32_t* __restrict__ zbuf, uint64_t cov,
                                                     uint4* __restrict__ accum, uint64_t n_px,
-                                                    uint32_t* __restrict__ minmax) {
+                                                    uint32_t* __restrict__ minmax, CullState* __restrict__ cull) {
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
     if (tid == 0) {
         minmax[0] = 0xFFFFFFFFu;
         minmax[1] = 0u;
+        if (cull) {  // fold the previous frame's visible-chunk count into the running total, reset for this frame
+            cull->total_visible += cull->n_visible;
+            cull->frames += (cull->armed ? 1u : 0u);
+            cull->n_visible = 0u;
+            cull->armed = 0u;
+        }
     }
     if (accum) {
         for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -45,12 +51,9 @@ __global__ void __launch_bounds__(256) clear_kernel(uint32_t* __restrict__ zbuf,
 // ---------------------------------------------------------------- z-min
 // variant bit 0: early depth test   bit 1: warp aggregation   bit 2: early test through L1 (ld.ca)
 template <int UNROLL, int VARIANT, bool DISTORT, int KEY64>
-__global__ void __launch_bounds__(kPointBlock) zmin_kernel(const PointRecord* __restrict__ pts, uint64_t n,
-                                                           uint64_t index_base,
-                                                           const __grid_constant__ ProjParams pp,
-                                                           uint32_t* __restrict__ zbuf,
-                                                           unsigned long long* __restrict__ zkey) {
-    const uint64_t base = uint64_t(blockIdx.x) * (kPointBlock * UNROLL) + threadIdx.x;
+__device__ __forceinline__ void zmin_tile(const PointRecord* __restrict__ pts, uint64_t n, uint64_t index_base,
+                                          const uint64_t base, const ProjParams& pp, uint32_t* __restrict__ zbuf,
+                                          unsigned long long* __restrict__ zkey) {
     // phase 1: UNROLL independent 128-bit loads in flight (tail lanes re-read the last record)
     PointRecord p[UNROLL];
 #pragma unroll
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(kPointBlock) zmin_kernel(const PointRecord* __
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-            if (live[u] && key[u] < cur[u]) atomicMin(zkey + pix[u], key[u]);
+            if (live[u] && key[u] < cur[u] && !(VARIANT & 8)) atomicMin(zkey + pix[u], key[u]);
     } else {
         // phase 3: early depth test, UNROLL gathers in flight
         uint32_t cur[UNROLL];
@@ -99,12 +102,41 @@ __global__ void __launch_bounds__(kPointBlock) zmin_kernel(const PointRecord* __
                     // one lane per (warp, pixel) group issues the RED
                     const unsigned winners = __ballot_sync(same, dbits[u] == mn) & same;
                     if ((threadIdx.x & 31) == (__ffs(winners) - 1)) atomicMin(zbuf + pix[u], mn);
+                } else if constexpr (VARIANT & 8) {  // measurement only: no RED issued (results are wrong)
+                    if (dbits[u] == 0x12345678u && pix[u] == 0xFFFFFFFFu) zbuf[0] = 0u;
                 } else {
                     atomicMin(zbuf + pix[u], dbits[u]);
                 }
             }
         }
     }
+}
+
+template <int UNROLL, int VARIANT, bool DISTORT, int KEY64>
+__global__ void __launch_bounds__(kPointBlock) zmin_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                           uint64_t index_base,
+                                                           const __grid_constant__ ProjParams pp,
+                                                           uint32_t* __restrict__ zbuf,
+                                                           unsigned long long* __restrict__ zkey) {
+    zmin_tile<UNROLL, VARIANT, DISTORT, KEY64>(pts, n, index_base,
+                                               uint64_t(blockIdx.x) * (kPointBlock * UNROLL) + threadIdx.x, pp, zbuf, zkey);
+}
+
+// Same tile body over the frame's VISIBLE chunks only (chunk-level frustum culling, see
+// rtr_cull.cu): a persistent grid walks the compacted chunk list, so nothing is launched, loaded or
+// scheduled for the chunks whose bounding box lies outside the frustum.
+template <int VARIANT, int KEY64>
+__global__ void __launch_bounds__(kPointBlock) zmin_list_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                                uint64_t index_base,
+                                                                const __grid_constant__ ProjParams pp,
+                                                                const CullState* __restrict__ cull,
+                                                                const uint32_t* __restrict__ vis_list,
+                                                                uint32_t* __restrict__ zbuf,
+                                                                unsigned long long* __restrict__ zkey) {
+    const uint32_t n_vis = cull->n_visible;
+    for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
+        zmin_tile<kChunkPoints / kPointBlock, VARIANT, false, KEY64>(
+            pts, n, index_base, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x, pp, zbuf, zkey);
 }
 
 // ---------------------------------------------------------------- blend (2 cm depth-window colour sums)
@@ -114,11 +146,9 @@ __global__ void __launch_bounds__(kPointBlock) zmin_kernel(const PointRecord* __
 // (> 16.8 M points in one pixel; the reference wraps silently there, this carries — documented).
 // variant bit 1: warp aggregation (match.any + redux.add), as the reference does.
 template <int UNROLL, int VARIANT, bool DISTORT>
-__global__ void __launch_bounds__(kPointBlock) blend_kernel(const PointRecord* __restrict__ pts, uint64_t n,
-                                                            const __grid_constant__ ProjParams pp,
-                                                            const uint32_t* __restrict__ zbuf,
-                                                            unsigned long long* __restrict__ accum2) {
-    const uint64_t base = uint64_t(blockIdx.x) * (kPointBlock * UNROLL) + threadIdx.x;
+__device__ __forceinline__ void blend_tile(const PointRecord* __restrict__ pts, uint64_t n, const uint64_t base,
+                                           const ProjParams& pp, const uint32_t* __restrict__ zbuf,
+                                           unsigned long long* __restrict__ accum2) {
     PointRecord p[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -158,6 +188,27 @@ __global__ void __launch_bounds__(kPointBlock) blend_kernel(const PointRecord* _
     }
 }
 
+template <int UNROLL, int VARIANT, bool DISTORT>
+__global__ void __launch_bounds__(kPointBlock) blend_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                            const __grid_constant__ ProjParams pp,
+                                                            const uint32_t* __restrict__ zbuf,
+                                                            unsigned long long* __restrict__ accum2) {
+    blend_tile<UNROLL, VARIANT, DISTORT>(pts, n, uint64_t(blockIdx.x) * (kPointBlock * UNROLL) + threadIdx.x, pp, zbuf, accum2);
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kPointBlock) blend_list_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                                 const __grid_constant__ ProjParams pp,
+                                                                 const CullState* __restrict__ cull,
+                                                                 const uint32_t* __restrict__ vis_list,
+                                                                 const uint32_t* __restrict__ zbuf,
+                                                                 unsigned long long* __restrict__ accum2) {
+    const uint32_t n_vis = cull->n_visible;
+    for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
+        blend_tile<kChunkPoints / kPointBlock, VARIANT, false>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x,
+                                                              pp, zbuf, accum2);
+}
+
 // ---------------------------------------------------------------- per-point projection dump (tests)
 // Writes (pix or -1, depth bits) for every point: the "hybrid golden" tap of SURVEY.md §8 c.
 template <bool DISTORT>
@@ -179,8 +230,46 @@ __global__ void __launch_bounds__(256) project_dump_kernel(const PointRecord* __
 static inline unsigned grid_for(uint64_t n, int per_block) { return unsigned((n + per_block - 1) / per_block); }
 
 cudaError_t launch_clear(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum, uint64_t n_px,
-                         uint32_t* minmax) {
-    clear_kernel<<<sm_count * 8, 256, 0, s>>>(zbuf, cov, reinterpret_cast<uint4*>(accum), n_px, minmax);
+                         uint32_t* minmax, CullState* cull) {
+    clear_kernel<<<sm_count * 8, 256, 0, s>>>(zbuf, cov, reinterpret_cast<uint4*>(accum), n_px, minmax, cull);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
+                             uint64_t index_base, const ProjParams& pp, const CullState* cull, const uint32_t* vis_list,
+                             uint32_t* zbuf, unsigned long long* zkey) {
+    if (n == 0) return cudaSuccess;
+    unsigned grid = unsigned(sm_count) * 8u;
+    if (variant & 16) grid = unsigned((n + kChunkPoints - 1) / kChunkPoints);  // experiment: one CTA per chunk slot
+    if (variant & 32) grid = unsigned(sm_count) * 4u;
+#define RTR_ZL(V)                                                                                                  \
+    do {                                                                                                           \
+        if (zkey) zmin_list_kernel<V, 1><<<grid, kPointBlock, 0, s>>>(pts, n, index_base, pp, cull, vis_list, zbuf, zkey); \
+        else zmin_list_kernel<V, 0><<<grid, kPointBlock, 0, s>>>(pts, n, index_base, pp, cull, vis_list, zbuf, zkey);      \
+    } while (0)
+    switch (variant & 15) {
+        case 0: RTR_ZL(0); break;
+        case 1: RTR_ZL(1); break;
+        case 2: RTR_ZL(2); break;
+        case 3: RTR_ZL(3); break;
+        case 5: RTR_ZL(5); break;
+        case 7: RTR_ZL(7); break;
+        case 8: RTR_ZL(8); break;
+        case 9: RTR_ZL(9); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef RTR_ZL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
+                              const ProjParams& pp, const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf,
+                              uint32_t* accum) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = unsigned(sm_count) * 8u;
+    unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
+    if (variant & 2) blend_list_kernel<2><<<grid, kPointBlock, 0, s>>>(pts, n, pp, cull, vis_list, zbuf, a2);
+    else blend_list_kernel<0><<<grid, kPointBlock, 0, s>>>(pts, n, pp, cull, vis_list, zbuf, a2);
     return cudaGetLastError();
 }
 
@@ -201,7 +290,8 @@ static cudaError_t launch_zmin_uv(cudaStream_t s, const PointRecord* pts, uint64
 template <int UNROLL>
 static cudaError_t launch_zmin_u(cudaStream_t s, int variant, const PointRecord* pts, uint64_t n, uint64_t index_base,
                                  const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey) {
-    switch (variant & 7) {
+    switch (variant & 15) {
+        case 8: return launch_zmin_uv<UNROLL, 8>(s, pts, n, index_base, pp, zbuf, zkey);
         case 0: return launch_zmin_uv<UNROLL, 0>(s, pts, n, index_base, pp, zbuf, zkey);
         case 1: return launch_zmin_uv<UNROLL, 1>(s, pts, n, index_base, pp, zbuf, zkey);
         case 2: return launch_zmin_uv<UNROLL, 2>(s, pts, n, index_base, pp, zbuf, zkey);

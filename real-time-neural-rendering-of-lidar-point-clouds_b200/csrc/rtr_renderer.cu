@@ -76,6 +76,11 @@ struct rtr_renderer {
     uint64_t n_points = 0;
     bool owns_points = false;
     uint64_t index_base = 0;  // global index of local point 0 (point sharding)
+    // chunk-level frustum culling (rtr_cull.cu)
+    ChunkBounds* bounds = nullptr;
+    uint32_t* vis_list = nullptr;
+    CullState* cull_state = nullptr;
+    uint32_t n_chunks = 0;
     // camera
     int W = 0, H = 0;
     double K[9] = {0};
@@ -90,8 +95,8 @@ struct rtr_renderer {
     PyramidDims dims{};
     bool masks_allocated = false, key64_allocated = false;
     // options
-    int zmin_variant = 1, zmin_unroll = 4, blend_variant = 0, blend_unroll = 4;
-    int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0;
+    int zmin_variant = 5, zmin_unroll = 4, blend_variant = 0, blend_unroll = 4;
+    int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1;
     cudaEvent_t ev[6] = {nullptr};
     // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
     std::vector<cudaEvent_t> ev_pool;
@@ -283,13 +288,25 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         if (r->ev_frames == kEvPoolFrames && (rc = drain_event_pool(r)) != RTR_OK) return rc;
         ev = &r->ev_pool[size_t(r->ev_frames) * 6];
     }
+    // chunk-level frustum culling: exact (conservative) for the pinhole path; the distorted path streams everything
+    const bool cull = r->chunk_cull && !pp.distort && r->bounds;
+    CullParams cp;
+    if (cull) {
+        for (int k = 0; k < 4; ++k) { cp.r0[k] = pp.m[k]; cp.r1[k] = pp.m[4 + k]; cp.r2[k] = pp.m[8 + k]; }
+        cp.W = r->W; cp.H = r->H;
+    }
     if (r->timing) cudaEventRecord(ev[0], s);
     if (r->key64) {
-        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax));
+        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, cull ? r->cull_state : nullptr));
         RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
         r->launches += 2;
+        if (cull) {
+            RTR_CUDA(r, launch_classify_chunks(s, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state));
+            r->launches += 1;
+        }
         if (r->timing) cudaEventRecord(ev[1], s);
-        RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
+        if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, fb.zkey));
+        else RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
         r->launches += 1;
         if (r->comm) {
             rc = comm_allreduce(r, fb.zkey, fb.zkey, P, ncclUint64_, ncclMin_);
@@ -306,17 +323,23 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         RTR_CUDA(r, launch_resolve_pyramid(s, fb, r->W, r->H, r->dims, filtered, false, r->force_generic != 0));
         r->launches += filtered ? (((r->W % 16) == 0 && !r->force_generic) ? 1 : 5) : 0;
     } else {
-        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax));
+        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, cull ? r->cull_state : nullptr));
         r->launches += 1;
+        if (cull) {
+            RTR_CUDA(r, launch_classify_chunks(s, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state));
+            r->launches += 1;
+        }
         if (r->timing) cudaEventRecord(ev[1], s);
-        RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
+        if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, nullptr));
+        else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
         r->launches += 1;
         if (r->comm) {
             rc = comm_allreduce(r, fb.zbuf, fb.zbuf, P, ncclUint32_, ncclMin_);
             if (rc != RTR_OK) return rc;
         }
         if (r->timing) cudaEventRecord(ev[2], s);
-        RTR_CUDA(r, launch_blend(s, r->blend_variant, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum));
+        if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, r->blend_variant, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum));
+        else RTR_CUDA(r, launch_blend(s, r->blend_variant, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum));
         r->launches += 1;
         if (r->comm) {
             rc = comm_allreduce(r, fb.accum, fb.accum, P * 4, ncclUint32_, ncclSum_);
@@ -404,6 +427,7 @@ void rtr_destroy(rtr_renderer* r) {
     if (r->comm) g_nccl.CommDestroy(r->comm);
     free_frame_sets(r);
     if (r->owns_points) cudaFree(r->points);
+    cudaFree(r->bounds); cudaFree(r->vis_list); cudaFree(r->cull_state);
     for (auto& s : r->set) { cudaEventDestroy(s.rendered); cudaEventDestroy(s.copied); }
     for (auto& ev : r->ev) cudaEventDestroy(ev);
     for (auto& ev : r->ev_pool) cudaEventDestroy(ev);
@@ -418,11 +442,27 @@ static int replace_cloud(rtr_renderer* r, uint64_t n) {
     RTR_CUDA(r, cudaSetDevice(r->device));
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     if (r->owns_points) cudaFree(r->points);
+    cudaFree(r->bounds); cudaFree(r->vis_list); cudaFree(r->cull_state);
+    r->bounds = nullptr; r->vis_list = nullptr; r->cull_state = nullptr; r->n_chunks = 0;
     r->points = nullptr; r->n_points = 0; r->owns_points = false;
     if (n == 0) return RTR_OK;
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->points), n * sizeof(PointRecord)));
     r->owns_points = true;
     r->n_points = n;
+    return RTR_OK;
+}
+
+// Chunk bounds + visible-list storage for the cloud now in r->points (every upload path ends here).
+static int build_chunk_bounds(rtr_renderer* r) {
+    if (r->n_points == 0) return RTR_OK;
+    r->n_chunks = uint32_t((r->n_points + kChunkPoints - 1) / kChunkPoints);
+    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->bounds), size_t(r->n_chunks) * sizeof(ChunkBounds)));
+    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->vis_list), size_t(r->n_chunks) * sizeof(uint32_t)));
+    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->cull_state), sizeof(CullState)));
+    RTR_CUDA(r, cudaMemsetAsync(r->cull_state, 0, sizeof(CullState), r->stream));
+    RTR_CUDA(r, launch_chunk_bounds(r->stream, r->points, r->n_points, r->bounds));
+    r->launches += 1;
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     return RTR_OK;
 }
 
@@ -455,7 +495,7 @@ int rtr_upload_cloud_xyz_bgr(rtr_renderer* r, const float* xyz, const uint8_t* b
     }
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     for (int i = 0; i < 2; ++i) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
-    return RTR_OK;
+    return build_chunk_bounds(r);
 }
 
 int rtr_upload_cloud_packed16(rtr_renderer* r, const void* host_records, uint64_t n) {
@@ -466,7 +506,7 @@ int rtr_upload_cloud_packed16(rtr_renderer* r, const void* host_records, uint64_
     if (rc != RTR_OK || n == 0) return rc;
     RTR_CUDA(r, cudaMemcpyAsync(r->points, host_records, n * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
-    return RTR_OK;
+    return build_chunk_bounds(r);
 }
 
 int rtr_adopt_device_cloud_packed16(rtr_renderer* r, void* device_records, uint64_t n) {
@@ -478,7 +518,7 @@ int rtr_adopt_device_cloud_packed16(rtr_renderer* r, void* device_records, uint6
     r->points = static_cast<PointRecord*>(device_records);
     r->n_points = n;
     r->owns_points = false;
-    return RTR_OK;
+    return build_chunk_bounds(r);
 }
 
 int rtr_synth_cloud(rtr_renderer* r, uint64_t seed, uint64_t n_total, uint64_t first, uint64_t count, int lx, int ly,
@@ -492,7 +532,7 @@ int rtr_synth_cloud(rtr_renderer* r, uint64_t seed, uint64_t n_total, uint64_t f
     r->launches += 1;
     r->index_base = first;
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
-    return RTR_OK;
+    return build_chunk_bounds(r);
 }
 
 uint64_t rtr_cloud_size(const rtr_renderer* r) { return r ? r->n_points : 0; }
@@ -720,6 +760,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "keep_masks")) return &r->keep_masks;
     if (!std::strcmp(key, "timing")) return &r->timing;
     if (!std::strcmp(key, "key64")) return &r->key64;
+    if (!std::strcmp(key, "chunk_cull")) return &r->chunk_cull;
     return nullptr;
 }
 
@@ -730,8 +771,8 @@ int rtr_set_option(rtr_renderer* r, const char* key, int64_t value) {
     if (!slot) return fail(r, RTR_ERR_ARG, std::string("unknown option: ") + key);
     if ((!std::strcmp(key, "zmin_unroll") || !std::strcmp(key, "blend_unroll")) && value != 1 && value != 2 && value != 4 && value != 8)
         return fail(r, RTR_ERR_ARG, "unroll must be 1, 2, 4 or 8");
-    if (!std::strcmp(key, "zmin_variant") && !(value == 0 || value == 1 || value == 2 || value == 3 || value == 5 || value == 7))
-        return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7");
+    if (!std::strcmp(key, "zmin_variant") && !((value & 7) == 0 || (value & 7) == 1 || (value & 7) == 2 || (value & 7) == 3 || (value & 7) == 5 || (value & 7) == 7))
+        return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7 (+8/16/32 measurement bits)");
     *slot = int(value);
     return RTR_OK;
 }
@@ -765,6 +806,21 @@ int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, i
         for (double& v : r->ev_sum) v = 0.0;
         r->ev_count = 0;
     }
+    return RTR_OK;
+}
+
+int rtr_get_cull_stats(rtr_renderer* r, uint64_t* frames, uint64_t* visible_chunks_total, uint64_t* n_chunks, int reset) {
+    if (!r || !frames || !visible_chunks_total || !n_chunks) return RTR_ERR_ARG;
+    *frames = *visible_chunks_total = 0;
+    *n_chunks = r->n_chunks;
+    if (!r->cull_state) return RTR_OK;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    CullState st;
+    RTR_CUDA(r, cudaMemcpy(&st, r->cull_state, sizeof(st), cudaMemcpyDeviceToHost));
+    *frames = uint64_t(st.frames) + (st.armed ? 1u : 0u);   // the frame in flight is folded at the next clear
+    *visible_chunks_total = st.total_visible + (st.armed ? st.n_visible : 0u);
+    if (reset) RTR_CUDA(r, cudaMemset(r->cull_state, 0, sizeof(CullState)));
     return RTR_OK;
 }
 

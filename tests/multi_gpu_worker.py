@@ -1,0 +1,99 @@
+"""torchrun worker for tests/test_gpu_multi.py: one rank per GPU, NCCL.
+  point-sharded : every rank uploads its contiguous shard, the library merges z-buffers (ncclMin) and
+                  colour sums (ncclSum); every rank's frame must equal the single-GPU frame of the
+                  whole cloud (rendered here by rank 0 on its own GPU), bit for bit — blend mode and
+                  the 64-bit key mode.
+  frame-sharded : ranks render disjoint frame ranges of one trajectory from a replicated cloud; the
+                  gathered per-frame digests must equal those of rank 0 rendering every frame."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as entry  # noqa: E402
+import scenes  # noqa: E402
+
+
+def frame(pc, pkg, calib, E, P, filtered=True):
+    color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+    fn = pc.computeFilteredRGBD if filtered else pc.computeRGBD
+    assert fn(calib, E, color, depth) == 1
+    return color, depth.view(np.uint32), pc.read("tensor", np.uint16, P * 5)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = entry.load_package()
+    case = scenes.CASES["c3_1920x1080"]
+    n, W, H, P = 1_000_003, case.W, case.H, case.W * case.H   # odd size: uneven shards
+    calib = pkg.CameraCalibration()
+    calib.setIntrinsicsMatrix(case.K)
+    calib.setWidth(W)
+    calib.setHeight(H)
+    # ---- point-sharded
+    first, count = pkg.shard_points(n, rank, world)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(pkg.ProjectCloud.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    shard = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, first=first, count=count, hall=case.hall, n_boxes=case.n_boxes, device=local)
+    shard.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+    full = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local) if rank == 0 else None
+    ok = True
+    for key64 in (0, 1):
+        shard.set_option("key64", key64)
+        for E in case.poses:
+            got = frame(shard, pkg, calib, E, P)
+            dig = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in got)).digest()
+            t = torch.frombuffer(bytearray(dig), dtype=torch.uint8).cuda()
+            if rank == 0:
+                full.set_option("key64", key64)
+                want = frame(full, pkg, calib, E, P)
+                wd = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in want)).digest()
+                t = torch.frombuffer(bytearray(wd), dtype=torch.uint8).cuda()
+            dist.broadcast(t, 0)
+            same = bytes(t.cpu().numpy().tobytes()) == dig
+            if not same:
+                print(f"[rank {rank}] point-sharded key64={key64}: frame differs from the single-GPU frame", flush=True)
+            ok &= same
+    shard.close()
+    # ---- frame-sharded
+    poses = pkg.trajectory_w2c(11, center=(6.0, 5.0, 1.5), radius=2.0)
+    rep = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local)
+    mine = pkg.shard_frames(len(poses), rank, world)
+    digs = torch.zeros((len(poses), 32), dtype=torch.uint8, device="cuda")
+    for f in mine:
+        got = frame(rep, pkg, calib, poses[f], P)
+        digs[f] = torch.frombuffer(bytearray(hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in got)).digest()), dtype=torch.uint8).cuda()
+    dist.all_reduce(digs.view(torch.uint8).to(torch.int32).contiguous(), op=dist.ReduceOp.SUM) if False else None
+    gathered = digs.to(torch.int32)
+    dist.all_reduce(gathered, op=dist.ReduceOp.SUM)   # disjoint rows: the sum is the union
+    if rank == 0:
+        for f in range(len(poses)):
+            want = frame(full, pkg, calib, poses[f], P) if False else frame(rep, pkg, calib, poses[f], P)
+            wd = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in want)).digest()
+            if bytes(gathered[f].to(torch.uint8).cpu().numpy().tobytes()) != wd:
+                print(f"frame-sharded: frame {f} differs", flush=True)
+                ok = False
+    rep.close()
+    if full is not None:
+        full.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_OK" if int(flag.item()) == 1 else "MULTI_GPU_FAIL", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

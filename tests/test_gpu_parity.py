@@ -155,8 +155,9 @@ def test_cuda_vs_live_reference(gpu, cpu_oracle, name):
 
 
 # ------------------------------------------------------------------ invariances / variants
-VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u)
-            for v, u, b in [(0, 1, 0), (1, 2, 2), (2, 4, 0), (3, 8, 2), (5, 4, 0), (7, 4, 2)]]
+VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u, chunk_cull=c)
+            for v, u, b, c in [(0, 1, 0, 0), (1, 2, 2, 0), (2, 4, 0, 0), (3, 8, 2, 0), (5, 4, 0, 0), (7, 4, 2, 0),
+                               (0, 4, 2, 1), (1, 4, 0, 1), (3, 4, 0, 1), (7, 4, 2, 1)]]
 
 
 @pytest.mark.parametrize("opts", VARIANTS)
@@ -389,3 +390,89 @@ def test_distortion_matches_opencv_model(gpu, cpu_oracle):
     # depth is the camera-space z
     z = zb[front][both].view(np.float32)
     assert np.allclose(z, cam[front][both, 2], rtol=1e-5)
+
+
+# ------------------------------------------------------------------ chunk-level frustum culling
+def test_chunk_culling_never_changes_a_frame(gpu, cpu_oracle):
+    """Culling on (default) vs off over many random cameras, including cameras outside the cloud, grazing
+    views, huge focal lengths and chunks that hold NaN / inf / huge points: every buffer identical."""
+    case = scenes.CASES["c1_640x480"]
+    rec = cloud_of(cpu_oracle, case)[:400_000].copy()
+    rng = np.random.default_rng(11)
+    rec[5000:5003, 0] = [np.nan, np.inf, -np.inf]     # chunk 4
+    rec[123456, 2] = np.nan
+    rec[200000, 1] = 3e38
+    rec[200001, :3] = [1e20, -1e20, 1e20]
+    rec[300000, :3] = [2e12, 0, 0]
+    W, H, P = 320, 208, 320 * 208                       # H % 16 == 0, small for speed
+    on = gpu.ProjectCloud.from_packed(rec)
+    off = gpu.ProjectCloud.from_packed(rec)
+    off.set_option("chunk_cull", 0)
+    assert on.get_option("chunk_cull") == 1
+    culled_any = False
+    for it in range(60):
+        f = float(rng.choice([80.0, 230.0, 1000.0, 20000.0]))
+        calib = gpu.CameraCalibration()
+        calib.loadCalibration(f, f * rng.uniform(0.8, 1.2), rng.uniform(0, W), rng.uniform(0, H), [0.0] * 5, W, H)
+        eye = rng.uniform([-3, -3, -1], [11, 9, 4])
+        fwd = rng.standard_normal(3)
+        E = gpu.look_at_w2c(eye, fwd, up=(0.0, 0.3, 1.0))
+        outs = []
+        for pc in (on, off):
+            pc.set_camera(calib, E)
+            pc.render_device(gpu.STAGE_FILTERED)
+            outs.append((pc.read("zbuf", np.uint32, P), pc.read("accum", np.uint32, P * 4), pc.read("image", np.uint8, P * 3),
+                         pc.read("tensor", np.uint16, P * 5)))
+        for a, b, what in zip(outs[0], outs[1], ("zbuf", "accum", "image", "tensor")):
+            assert np.array_equal(a, b), f"camera {it}: {what} changed by chunk culling"
+        fr, vis, nch = on.cull_stats(reset=True)
+        assert fr == 1 and 0 < vis <= nch           # the always-visible chunks are never dropped
+        culled_any |= vis < nch
+    assert culled_any
+    # raw matrices with NaN / inf / absurd entries must simply disable the culling
+    for bad in (np.nan, np.inf, 1e38):
+        m = np.array([300, 0, 160, 0, 0, 300, 104, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
+        m[3] = bad
+        res = []
+        for pc in (on, off):
+            pc.set_cam_proj_raw(m)
+            pc.render_device(gpu.STAGE_RGBD)
+            res.append((pc.read("zbuf", np.uint32, P), pc.read("accum", np.uint32, P * 4)))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    on.close()
+    off.close()
+
+
+def test_chunk_culling_pixel_boundary_points(gpu):
+    """Points placed exactly on and one ulp around the four image borders and the z = 0 plane, one chunk
+    each, with a camera whose rows make u and v land on k + 0.5 ties: cull on == cull off."""
+    W, H = 64, 48
+    P = W * H
+    m = np.array([32, 0, 31.5, 0, 0, 32, 23.5, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
+    chunks = []
+    for ux in (-0.5, -0.5000001, -0.4999999, 63.5, 63.49999, 63.50001, 31.0):
+        for vy in (-0.5, -0.5000001, 47.5, 47.50001, 23.0):
+            z = np.float32(2.0)
+            x = np.float32((ux - 31.5) * 2.0 / 32.0)
+            y = np.float32((vy - 23.5) * 2.0 / 32.0)
+            pts = np.tile(np.array([x, y, z], np.float32), (1024, 1))
+            pts[:, 0] = np.nextafter(pts[:, 0], np.float32(np.inf) * np.where(np.arange(1024) % 2, 1, -1)).astype(np.float32)
+            chunks.append(pts)
+    for z in (0.0, -0.0, 1e-45, -1e-45, 1e-38, 1e-30):
+        chunks.append(np.tile(np.array([0.0, 0.0, z], np.float32), (1024, 1)))
+    xyz = np.concatenate(chunks)
+    rec = gpu.pack_records(xyz, np.full((len(xyz), 3), 77, np.uint8))
+    res = []
+    for cull in (1, 0):
+        pc = gpu.ProjectCloud.from_packed(rec)
+        pc.set_option("chunk_cull", cull)
+        c = gpu.CameraCalibration()
+        c.setWidth(W)
+        c.setHeight(H)
+        pc.set_camera(c)
+        pc.set_cam_proj_raw(m)
+        pc.render_device(gpu.STAGE_RGBD)
+        res.append((pc.read("zbuf", np.uint32, P), pc.read("accum", np.uint32, P * 4)))
+        pc.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert (res[0][0] != 0x7F7FFFFF).sum() > 4

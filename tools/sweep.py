@@ -34,8 +34,29 @@ def main():
     pc.set_camera(bench.make_calib(pkg, W, H, f, cx, cy))
     poses = bench.trajectory(pkg, hall, n_poses)
     poses = np.ascontiguousarray(poses[:: max(1, len(poses) // 8)][:8].reshape(-1, 16))
-    out = {"workload": wl_name, "points": n, "zmin": {}, "blend": {}, "key64": {}, "atomics": {}}
+    out = {"workload": wl_name, "points": n, "zmin": {}, "blend": {}, "key64": {}, "atomics": {}, "culled": {}}
     stage_times(pc, pkg, poses)  # warm-up
+    # ---- chunk culling on (default): list kernels, unroll fixed at 4
+    pc.cull_stats(reset=True)
+    out["culled"]["frame_stages_default"] = stage_times(pc, pkg, poses)
+    fr, vis, nch = pc.cull_stats(reset=True)
+    out["culled"]["visible_chunk_fraction"] = vis / fr / nch
+    for v in (0, 1, 2, 3, 5, 7):
+        pc.set_option("zmin_variant", v)
+        out["culled"][f"zmin_v{v}"] = stage_times(pc, pkg, poses)[1]
+    pc.set_option("zmin_variant", 1)
+    for v in (0, 2):
+        pc.set_option("blend_variant", v)
+        out["culled"][f"blend_v{v}"] = stage_times(pc, pkg, poses)[2]
+    pc.set_option("blend_variant", 0)
+    pc.set_option("key64", 1)
+    for v in (0, 1, 5):
+        pc.set_option("zmin_variant", v)
+        out["culled"][f"key64_zmin_v{v}"] = stage_times(pc, pkg, poses)[1]
+    pc.set_option("key64", 0)
+    pc.set_option("zmin_variant", 1)
+    pc.set_option("chunk_cull", 0)
+    # ---- chunk culling off: every point streamed
     for v in (0, 1, 2, 3, 5, 7):
         for u in (1, 2, 4, 8):
             pc.set_option("zmin_variant", v)
