@@ -295,8 +295,8 @@ def run_b200(args, wl):
     calib = make_calib(pkg, W, H, f, cx, cy)
     pc.set_camera(calib)
     poses = trajectory(pkg, hall, n_poses)
-    if args.mode == "frames":   # rank r renders its own K-frame stretch of the trajectory
-        my = [poses[(rank * (K_steps + Wm) + i) % len(poses)] for i in range(K_steps + Wm)]
+    if args.mode == "frames":   # frame f of the (looping) trajectory goes to rank f mod N (SURVEY.md §8 e)
+        my = [poses[(i * world + rank) % len(poses)] for i in range(K_steps + Wm)]
     else:
         my = [poses[i % len(poses)] for i in range(K_steps + Wm)]
     my = np.ascontiguousarray(np.stack(my).reshape(-1, 16))

@@ -50,3 +50,27 @@ def test_product_does_not_reference_the_oracle():
                 src = open(os.path.join(base, f)).read()
                 assert "import oracle" not in src and "oracle/" not in src.replace("oracle/rtr_oracle.c:rtro_synth_packed", "") \
                     or f == "rtr_synth_common.h", f"{f} references the oracle"
+
+
+def test_headers_compile_as_c99_and_cpp17_and_link(pkg, tmp_path):
+    """include/rtr_b200.h is plain C; the header-only C++ adapter (reference method names) compiles
+    and links against the in-tree library; without a GPU the constructor throws (no fallback)."""
+    import subprocess
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "rtr_b200.h"\nint main(void) { return rtr_version() == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{inc}", str(c), "-o", str(tmp_path / "t_c"),
+                    f"-L{libdir}", "-lrtr_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    assert subprocess.run([str(tmp_path / "t_c")]).returncode == 0
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "rtr_b200/project_cloud.hpp"\n#include <cstdio>\n'
+                   'int main() { try { rtr_b200::ProjectCloud pc(0); rtr_b200::Intrinsics k; double E[16] = {1,0,0,0,0,1,0,0,0,0,1,0,0,0,0,1};\n'
+                   '  return pc.computeRGBD(k, E, nullptr, nullptr) == -1 ? 0 : 3; }\n'
+                   '  catch (const std::exception& e) { std::puts(e.what()); return 2; } }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", f"-I{inc}", str(cpp), "-o", str(tmp_path / "t_cpp"),
+                    f"-L{libdir}", "-lrtr_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([str(tmp_path / "t_cpp")], capture_output=True, text=True)
+    assert res.returncode == (0 if has_gpu() else 2)
+    if not has_gpu():
+        assert "no CPU fallback" in res.stdout
