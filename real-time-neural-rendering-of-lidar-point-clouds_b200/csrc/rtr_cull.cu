@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256) classify_chunks_kernel(const ChunkBounds*
                                                               const __grid_constant__ CullParams cp,
                                                               uint32_t* __restrict__ vis_list,
                                                               CullState* __restrict__ cull) {
+    pdl_prologue();
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     bool visible = false;
     if (c < n_chunks) {
@@ -151,7 +152,7 @@ cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t
 cudaError_t launch_classify_chunks(cudaStream_t s, const ChunkBounds* bounds, uint32_t n_chunks, const CullParams& cp,
                                    uint32_t* vis_list, CullState* cull) {
     if (n_chunks == 0) return cudaSuccess;
-    classify_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, s>>>(bounds, n_chunks, cp, vis_list, cull);
+    launch_pdl(classify_chunks_kernel, dim3((n_chunks + 255) / 256), dim3(256), s, bounds, n_chunks, cp, vis_list, cull);
     return cudaGetLastError();
 }
 

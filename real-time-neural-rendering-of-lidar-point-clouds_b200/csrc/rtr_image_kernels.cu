@@ -37,13 +37,23 @@ __device__ __forceinline__ void resolve_px(const uint4 a, uint8_t& b, uint8_t& g
 // 4 x 1 of L4.  Thread (tx, ty) owns the 2x2 quad of level-0 pixels under L1 pixel (tx, ty).
 // Tiles cover rows [0, 16*floor(H/16)): exactly resolvePass's / the min-max's coverage when
 // W % 16 == 0, and every pyramid row the up-pass can read (uh[i] = 16*floor(H/16) >> i).
-template <bool PYRAMID, bool RESOLVE>
+// float accumulator -> the integer sums it holds; flags counts beyond the exact range
+__device__ __forceinline__ uint4 accum_as_u32(const uint4 raw, bool f32acc, uint32_t* __restrict__ overflow) {
+    if (!f32acc) return raw;
+    const float c = __uint_as_float(raw.w);
+    if (c > kF32ExactCount) *overflow = 1u;
+    return make_uint4(__float2uint_rz(__uint_as_float(raw.x)), __float2uint_rz(__uint_as_float(raw.y)),
+                      __float2uint_rz(__uint_as_float(raw.z)), __float2uint_rz(c));
+}
+
+template <bool PYRAMID, bool RESOLVE, bool F32ACC>
 __global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __restrict__ zbuf,
                                                               const uint4* __restrict__ accum,
                                                               uint8_t* __restrict__ image, float* __restrict__ l1,
                                                               float* __restrict__ l2, float* __restrict__ l3,
                                                               float* __restrict__ l4, uint32_t* __restrict__ minmax,
                                                               int W) {
+    pdl_prologue();
     __shared__ float s1[8][33];
     __shared__ float s2[4][17];
     __shared__ float s3[2][9];
@@ -59,7 +69,8 @@ __global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __
         const uint2 z0 = *reinterpret_cast<const uint2*>(zbuf + p0);
         const uint2 z1 = *reinterpret_cast<const uint2*>(zbuf + p1);
         if constexpr (RESOLVE) {
-            const uint4 a00 = accum[p0], a01 = accum[p0 + 1], a10 = accum[p1], a11 = accum[p1 + 1];
+            const uint4 a00 = accum_as_u32(accum[p0], F32ACC, minmax + 2), a01 = accum_as_u32(accum[p0 + 1], F32ACC, minmax + 2),
+                        a10 = accum_as_u32(accum[p1], F32ACC, minmax + 2), a11 = accum_as_u32(accum[p1 + 1], F32ACC, minmax + 2);
             uint8_t c[12];
             resolve_px(a00, c[0], c[1], c[2]);
             resolve_px(a01, c[3], c[4], c[5]);
@@ -121,16 +132,20 @@ __global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __
 
 // ---------------------------------------------------------------- generic (any W, H) restatements
 __global__ void __launch_bounds__(256) resolve_generic_kernel(const uint4* __restrict__ accum,
-                                                              uint8_t* __restrict__ image, uint64_t cov) {
+                                                              uint8_t* __restrict__ image, uint64_t cov, bool f32acc,
+                                                              uint32_t* __restrict__ overflow, bool gated) {
+    pdl_prologue();
+    if (gated && *overflow == 0u) return;
     const uint64_t id = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (id >= cov) return;
     uint8_t b, g, r;
-    resolve_px(accum[id], b, g, r);
+    resolve_px(accum_as_u32(accum[id], f32acc, overflow), b, g, r);
     image[id * 3 + 0] = b; image[id * 3 + 1] = g; image[id * 3 + 2] = r;
 }
 
 __global__ void __launch_bounds__(256) minmax_generic_kernel(const uint32_t* __restrict__ zbuf, uint64_t count,
                                                              uint32_t* __restrict__ minmax) {
+    pdl_prologue();
     __shared__ uint32_t smin[8], smax[8];
     uint32_t tmin = 0xFFFFFFFFu, tmax = 0u;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += uint64_t(gridDim.x) * blockDim.x) {
@@ -149,6 +164,7 @@ __global__ void __launch_bounds__(256) minmax_generic_kernel(const uint32_t* __r
 
 __global__ void __launch_bounds__(256) reduce_generic_kernel(const float* __restrict__ hi, float* __restrict__ lo,
                                                              int w, int h) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= w * h) return;
     const int x = idx % w, y = idx / w, wh = w * 2;
@@ -193,6 +209,7 @@ __global__ void __launch_bounds__(256) up_level_kernel(const float* __restrict__
                                                        float* __restrict__ hi, uint8_t* __restrict__ mask_tap,
                                                        uint8_t* __restrict__ image, uint16_t* __restrict__ tensor,
                                                        const uint32_t* __restrict__ minmax) {
+    pdl_prologue();
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     const int hh = lh * 2, hw = lw * 2;
     if (pair >= lw * hh) return;
@@ -281,29 +298,36 @@ __global__ void __launch_bounds__(256) up_level_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------- launchers
+cudaError_t launch_resolve_gated(cudaStream_t s, const FrameBuffers& fb, int W, int H) {
+    const uint64_t cov = clear_coverage(W, H);
+    if (cov == 0) return cudaSuccess;
+    launch_pdl(resolve_generic_kernel, dim3(unsigned((cov + 255) / 256)), dim3(256), s, reinterpret_cast<const uint4*>(fb.accum), fb.image, cov,
+                                                                       false, fb.minmax + 2, true);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve_pyramid(cudaStream_t s, const FrameBuffers& fb, int W, int H, const PyramidDims& d,
-                                   bool pyramid, bool resolve, bool force_generic) {
+                                   bool pyramid, bool resolve, bool force_generic, bool f32acc) {
     const uint64_t cov = clear_coverage(W, H);
     if (cov == 0 || (!pyramid && !resolve)) return cudaSuccess;
     const uint4* acc = reinterpret_cast<const uint4*>(fb.accum);
     if ((W % 16) == 0 && !force_generic) {
         dim3 grid((W + 63) / 64, H / 16);
-        if (pyramid && resolve)
-            resolve_pyramid_kernel<true, true><<<grid, 256, 0, s>>>(fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W);
-        else if (pyramid)
-            resolve_pyramid_kernel<true, false><<<grid, 256, 0, s>>>(fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W);
-        else
-            resolve_pyramid_kernel<false, true><<<grid, 256, 0, s>>>(fb.zbuf, acc, fb.image, nullptr, nullptr, nullptr, nullptr, fb.minmax, W);
+#define RTR_RP(P_, R_, F_) launch_pdl((resolve_pyramid_kernel<P_, R_, F_>), dim3(grid), dim3(256), s, fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W)
+        if (pyramid && resolve) { if (f32acc) RTR_RP(true, true, true); else RTR_RP(true, true, false); }
+        else if (pyramid) RTR_RP(true, false, false);
+        else { if (f32acc) RTR_RP(false, true, true); else RTR_RP(false, true, false); }
+#undef RTR_RP
         return cudaGetLastError();
     }
-    if (resolve) resolve_generic_kernel<<<unsigned((cov + 255) / 256), 256, 0, s>>>(acc, fb.image, cov);
+    if (resolve) launch_pdl(resolve_generic_kernel, dim3(unsigned((cov + 255) / 256)), dim3(256), s, acc, fb.image, cov, f32acc, fb.minmax + 2, false);
     if (pyramid) {
         const uint64_t count = uint64_t(d.uw[0]) * d.uh[0];
         const uint64_t mm_blocks = (count + 255) / 256;
-        if (count) minmax_generic_kernel<<<unsigned(mm_blocks < 148 * 8 ? mm_blocks : 148 * 8), 256, 0, s>>>(fb.zbuf, count, fb.minmax);
+        if (count) launch_pdl(minmax_generic_kernel, dim3(unsigned(mm_blocks < 148 * 8 ? mm_blocks : 148 * 8)), dim3(256), s, fb.zbuf, count, fb.minmax);
         for (int i = 1; i <= 4; ++i) {
             const int n = d.w[i] * d.h[i];
-            if (n) reduce_generic_kernel<<<(n + 255) / 256, 256, 0, s>>>(fb.level[i - 1], fb.level[i], d.w[i], d.h[i]);
+            if (n) launch_pdl(reduce_generic_kernel, dim3((n + 255) / 256), dim3(256), s, fb.level[i - 1], fb.level[i], d.w[i], d.h[i]);
         }
     }
     return cudaGetLastError();
@@ -313,6 +337,7 @@ cudaError_t launch_resolve_pyramid(cudaStream_t s, const FrameBuffers& fb, int W
 // zkey[p] = (depth bits << 32) | point index.  Splits the key back into the reference-identical
 // depth buffer and a NEAREST-point colour (not the reference's 2 cm average: opt-in, non-parity).
 __global__ void __launch_bounds__(256) clear_key64_kernel(unsigned long long* __restrict__ zkey, uint64_t cov) {
+    pdl_prologue();
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cov; i += uint64_t(gridDim.x) * blockDim.x)
         zkey[i] = (static_cast<unsigned long long>(kEmptyDepthBits) << 32) | 0xFFFFFFFFull;
 }
@@ -320,6 +345,7 @@ __global__ void __launch_bounds__(256) resolve_key64_kernel(const unsigned long 
                                                             const PointRecord* __restrict__ pts, uint64_t index_base,
                                                             uint64_t n_local, uint32_t* __restrict__ zbuf,
                                                             uint8_t* __restrict__ image, uint64_t n_px, uint64_t cov) {
+    pdl_prologue();
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_px) return;
     const unsigned long long key = zkey[i];
@@ -331,13 +357,13 @@ __global__ void __launch_bounds__(256) resolve_key64_kernel(const unsigned long 
     image[i * 3 + 0] = uint8_t(c); image[i * 3 + 1] = uint8_t(c >> 8); image[i * 3 + 2] = uint8_t(c >> 16);
 }
 cudaError_t launch_clear_key64(cudaStream_t s, int sm_count, unsigned long long* zkey, uint64_t cov) {
-    if (cov) clear_key64_kernel<<<sm_count * 4, 256, 0, s>>>(zkey, cov);
+    if (cov) launch_pdl(clear_key64_kernel, dim3(sm_count * 4), dim3(256), s, zkey, cov);
     return cudaGetLastError();
 }
 cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey, const PointRecord* pts,
                                  uint64_t index_base, uint64_t n_local, uint32_t* zbuf, uint8_t* image, uint64_t n_px,
                                  uint64_t cov) {
-    if (n_px) resolve_key64_kernel<<<unsigned((n_px + 255) / 256), 256, 0, s>>>(zkey, pts, index_base, n_local, zbuf, image, n_px, cov);
+    if (n_px) launch_pdl(resolve_key64_kernel, dim3(unsigned((n_px + 255) / 256)), dim3(256), s, zkey, pts, index_base, n_local, zbuf, image, n_px, cov);
     return cudaGetLastError();
 }
 
@@ -347,9 +373,9 @@ cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const Pyramid
         if (pairs == 0) continue;
         const unsigned grid = (pairs + 255) / 256;
         if (i > 1)
-            up_level_kernel<false><<<grid, 256, 0, s>>>(fb.level[i], d.uw[i], d.uh[i], fb.level[i - 1], fb.mask[i - 1], nullptr, nullptr, fb.minmax);
+            launch_pdl((up_level_kernel<false>), dim3(grid), dim3(256), s, fb.level[i], d.uw[i], d.uh[i], fb.level[i - 1], fb.mask[i - 1], nullptr, nullptr, fb.minmax);
         else
-            up_level_kernel<true><<<grid, 256, 0, s>>>(fb.level[1], d.uw[1], d.uh[1], fb.level[0], fb.mask[0], fb.image, fb.tensor, fb.minmax);
+            launch_pdl((up_level_kernel<true>), dim3(grid), dim3(256), s, fb.level[1], d.uw[1], d.uh[1], fb.level[0], fb.mask[0], fb.image, fb.tensor, fb.minmax);
     }
     return cudaGetLastError();
 }

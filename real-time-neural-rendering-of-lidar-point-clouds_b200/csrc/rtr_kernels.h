@@ -8,6 +8,9 @@ namespace rtr {
 
 constexpr int kPointBlock = 256;    // threads per CTA of the two point passes
 constexpr int kChunkPoints = 1024;  // points per culling chunk (= one CTA tile at unroll 4)
+// Float accumulators ({b,g,r,count} as 4 x f32) hold exact integers while count <= 65793
+// (255 * 65793 = 2^24 - 1).  A pixel beyond that raises the frame's overflow flag in resolve.
+constexpr float kF32ExactCount = 65793.0f;
 
 // Axis-aligned bounds of one chunk of kChunkPoints consecutive records (rtr_cull.cu).
 struct ChunkBounds {
@@ -48,6 +51,24 @@ inline uint64_t clear_coverage(int W, int H) {  // fillBuffer/resolvePass grid: 
     return c < p ? c : p;
 }
 
+// Launch with the PDL attribute (see pdl_prologue in rtr_common.cuh).  RTR_PDL=0 in the environment
+// falls back to plain stream serialisation (A/B measurements).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- point passes (rtr_point_kernels.cu)
 cudaError_t launch_clear(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum, uint64_t n_px,
                          uint32_t* minmax, CullState* cull);
@@ -57,7 +78,7 @@ cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const Po
                              uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
                               const ProjParams& pp, const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf,
-                              uint32_t* accum);
+                              uint32_t* accum, const uint32_t* gate);
 
 // ---- chunk-level frustum culling (rtr_cull.cu)
 cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds);
@@ -66,7 +87,8 @@ cudaError_t launch_classify_chunks(cudaStream_t s, const ChunkBounds* bounds, ui
 cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                         uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
-                         const ProjParams& pp, const uint32_t* zbuf, uint32_t* accum);
+                         const ProjParams& pp, const uint32_t* zbuf, uint32_t* accum, const uint32_t* gate);
+cudaError_t launch_clear_accum_gated(cudaStream_t s, int sm_count, uint32_t* accum, uint64_t n_px, const uint32_t* gate);
 cudaError_t launch_project_dump(cudaStream_t s, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                 int32_t* pix_out, uint32_t* zbits_out);
 
@@ -78,13 +100,16 @@ struct FrameBuffers {
     uint16_t* tensor;    // 5P fp16, planes of stride uw[0]*uh[0]
     float* level[5];     // level[0] aliases zbuf; level[1..4] persistent scratch
     uint8_t* mask[4];    // optional taps: mask[i-1] produced by up-pass iteration i (nullptr = not kept)
-    uint32_t* minmax;    // {min, max} of the valid depth bits
+    uint32_t* minmax;    // {min, max} of the valid depth bits, [2] = float-accumulator overflow flag
     unsigned long long* zkey;  // P u64, only in key64 mode
 };
 // accum -> image over [0, cov) (resolvePass), fused with the 4-level min pyramid (reduce x4) and the
 // depth min/max (find_*_minmax_kernel).  `pyramid` = false for plain computeRGBD.
+// f32acc: accum holds floats (blend variant bit 2); raises minmax[2] when a pixel's count exceeds
+// kF32ExactCount.  gated: run (resolve only) iff minmax[2] != 0 — the exact re-resolve.
 cudaError_t launch_resolve_pyramid(cudaStream_t s, const FrameBuffers& fb, int W, int H, const PyramidDims& d,
-                                   bool pyramid, bool resolve, bool force_generic);
+                                   bool pyramid, bool resolve, bool force_generic, bool f32acc = false);
+cudaError_t launch_resolve_gated(cudaStream_t s, const FrameBuffers& fb, int W, int H);
 // 64-bit key mode: clear / split keys into depth bits + nearest-point colour.
 cudaError_t launch_clear_key64(cudaStream_t s, int sm_count, unsigned long long* zkey, uint64_t cov);
 cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey, const PointRecord* pts,

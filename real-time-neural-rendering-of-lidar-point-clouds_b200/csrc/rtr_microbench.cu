@@ -33,10 +33,32 @@ __global__ void __launch_bounds__(256) red_pix_kernel(const int32_t* __restrict_
     }
 }
 
+// modes 2/3: the blend pass's update of one 16-byte {b,g,r,count} accumulator at a random pixel, as
+// two RED.ADD.64 (what blend_kernel issues) or as one RED.ADD.F32x4.
+template <bool VEC4F>
+__global__ void __launch_bounds__(256) red_accum_kernel(uint64_t n_ops, uint32_t n_px, unsigned long long* __restrict__ acc) {
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_ops; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t h = rtr_splitmix64(i);
+        const uint32_t px = uint32_t((uint64_t(uint32_t(h)) * n_px) >> 32);
+        const uint32_t b = uint32_t(h >> 32) & 0xFF, g = uint32_t(h >> 40) & 0xFF, r = uint32_t(h >> 48) & 0xFF;
+        if constexpr (VEC4F) {
+            asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(acc + 2 * uint64_t(px)), "f"(float(b)), "f"(float(g)),
+                         "f"(float(r)), "f"(1.0f)
+                         : "memory");
+        } else {
+            atomicAdd(acc + 2 * uint64_t(px), static_cast<unsigned long long>(b) | (static_cast<unsigned long long>(g) << 32));
+            atomicAdd(acc + 2 * uint64_t(px) + 1, static_cast<unsigned long long>(r) | (1ull << 32));
+        }
+    }
+}
+
 cudaError_t launch_red_bench(cudaStream_t s, int sm_count, int mode, bool key64, const int32_t* pix, uint64_t n_ops,
                              uint32_t n_px, uint32_t* z32, unsigned long long* z64) {
     const unsigned grid = unsigned(sm_count) * 8u;
-    if (mode == 0) {
+    if (mode == 2 || mode == 3) {
+        if (mode == 3) red_accum_kernel<true><<<grid, 256, 0, s>>>(n_ops, n_px, z64);
+        else red_accum_kernel<false><<<grid, 256, 0, s>>>(n_ops, n_px, z64);
+    } else if (mode == 0) {
         if (key64) red_random_kernel<true><<<grid, 256, 0, s>>>(n_ops, n_px, z32, z64);
         else red_random_kernel<false><<<grid, 256, 0, s>>>(n_ops, n_px, z32, z64);
     } else {

@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,6 +26,16 @@
 #include "rtr_kernels.h"
 
 using namespace rtr;
+
+namespace rtr {
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("RTR_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+}  // namespace rtr
 
 namespace {
 
@@ -62,6 +73,7 @@ std::mutex g_nccl_mu;
 
 struct FrameSet {
     FrameBuffers fb{};
+    bool f32acc = false;  // the last frame rendered into this set accumulated colour sums as floats
     cudaEvent_t rendered = nullptr, copied = nullptr;
 };
 
@@ -95,7 +107,7 @@ struct rtr_renderer {
     PyramidDims dims{};
     bool masks_allocated = false, key64_allocated = false;
     // options
-    int zmin_variant = 5, zmin_unroll = 4, blend_variant = 0, blend_unroll = 4;
+    int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
     int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1;
     cudaEvent_t ev[6] = {nullptr};
     // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
@@ -297,6 +309,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     }
     if (r->timing) cudaEventRecord(ev[0], s);
     if (r->key64) {
+        fs.f32acc = false;
         RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, cull ? r->cull_state : nullptr));
         RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
         r->launches += 2;
@@ -338,16 +351,30 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
             if (rc != RTR_OK) return rc;
         }
         if (r->timing) cudaEventRecord(ev[2], s);
-        if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, r->blend_variant, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum));
-        else RTR_CUDA(r, launch_blend(s, r->blend_variant, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum));
+        // float accumulators (one 16-byte RED per point) unless the sums must be all-reduced as integers
+        const int bv = r->comm ? (r->blend_variant & ~4) : r->blend_variant;
+        const bool f32acc = (bv & 4) != 0;
+        fs.f32acc = f32acc;
+        if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, nullptr));
+        else RTR_CUDA(r, launch_blend(s, bv, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, nullptr));
         r->launches += 1;
         if (r->comm) {
             rc = comm_allreduce(r, fb.accum, fb.accum, P * 4, ncclUint32_, ncclSum_);
             if (rc != RTR_OK) return rc;
         }
         if (r->timing) cudaEventRecord(ev[3], s);
-        RTR_CUDA(r, launch_resolve_pyramid(s, fb, r->W, r->H, r->dims, filtered, true, r->force_generic != 0));
+        RTR_CUDA(r, launch_resolve_pyramid(s, fb, r->W, r->H, r->dims, filtered, true, r->force_generic != 0, f32acc));
         r->launches += ((r->W % 16) == 0 && !r->force_generic) ? 1 : (filtered ? 6 : 1);
+        if (f32acc) {
+            // A pixel that collected more than 65793 points leaves the exact range of the float sums; resolve
+            // raised minmax[2] for it.  These three launches return at once unless that happened, in which
+            // case they redo the colour sums of the frame with the integer REDs and resolve again.
+            RTR_CUDA(r, launch_clear_accum_gated(s, r->sm_count, fb.accum, P, fb.minmax + 2));
+            if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv & ~4, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, fb.minmax + 2));
+            else RTR_CUDA(r, launch_blend(s, bv & ~4, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, fb.minmax + 2));
+            RTR_CUDA(r, launch_resolve_gated(s, fb, r->W, r->H));
+            r->launches += 3;
+        }
     }
     if (r->timing) cudaEventRecord(ev[4], s);
     if (filtered) {
@@ -665,7 +692,7 @@ int rtr_read_buffer(rtr_renderer* r, int what, void* dst, size_t bytes) {
     else if (what == 1) { src = fb.accum; cap = P * 16; }
     else if (what == 2) { src = fb.image; cap = P * 3; }
     else if (what == 3) { src = fb.tensor; cap = P * 10; }
-    else if (what == 4) { src = fb.minmax; cap = 8; }
+    else if (what == 4) { src = fb.minmax; cap = 12; }
     else if (what >= 5 && what <= 8) { const int i = what - 4; src = fb.level[i]; cap = size_t(r->dims.w[i]) * r->dims.h[i] * 4; }
     else if (what >= 9 && what <= 12) { const int i = what - 9; src = r->keep_masks ? fb.mask[i] : nullptr; cap = size_t(r->dims.uw[i]) * r->dims.uh[i]; }
     if (!src) return fail(r, RTR_ERR_ARG, "buffer not available");
@@ -673,6 +700,18 @@ int rtr_read_buffer(rtr_renderer* r, int what, void* dst, size_t bytes) {
     RTR_CUDA(r, cudaSetDevice(r->device));
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     RTR_CUDA(r, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    if (what == 1 && r->set[r->cur].f32acc) {  // always hand out the reference's layout: {b,g,r,count} as u32
+        uint32_t flag = 0;
+        RTR_CUDA(r, cudaMemcpy(&flag, fb.minmax + 2, 4, cudaMemcpyDeviceToHost));
+        if (!flag) {  // (after an overflow the exact re-run left integers in the buffer)
+            uint32_t* u = static_cast<uint32_t*>(dst);
+            for (size_t i = 0; i < bytes / 4; ++i) {
+                float f;
+                std::memcpy(&f, u + i, 4);
+                u[i] = static_cast<uint32_t>(f);
+            }
+        }
+    }
     return RTR_OK;
 }
 
@@ -699,7 +738,7 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
 
 int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int iters, float* ms_per_launch,
                       uint64_t* live_ops) {
-    if (!r || !ms_per_launch || iters < 1 || (mode != 0 && mode != 1)) return RTR_ERR_ARG;
+    if (!r || !ms_per_launch || iters < 1 || mode < 0 || mode > 3) return RTR_ERR_ARG;
     RTR_CUDA(r, cudaSetDevice(r->device));
     ProjParams pp;
     int rc = make_params(r, pp);
@@ -713,8 +752,9 @@ int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int 
     int32_t* d_pix = nullptr;
     uint32_t* d_z = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaError_t e = cudaMalloc(&zb, P * (key64 ? 8 : 4));
-    if (e == cudaSuccess) e = cudaMemsetAsync(zb, 0xFF, P * (key64 ? 8 : 4), r->stream);
+    const size_t zb_bytes = P * (mode >= 2 ? 16 : (key64 ? 8 : 4));
+    cudaError_t e = cudaMalloc(&zb, zb_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(zb, mode >= 2 ? 0 : 0xFF, zb_bytes, r->stream);
     if (e == cudaSuccess && mode == 1) {
         e = cudaMalloc(reinterpret_cast<void**>(&d_pix), n_ops * 4);
         if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_z), n_ops * 4);
@@ -773,6 +813,8 @@ int rtr_set_option(rtr_renderer* r, const char* key, int64_t value) {
         return fail(r, RTR_ERR_ARG, "unroll must be 1, 2, 4 or 8");
     if (!std::strcmp(key, "zmin_variant") && !((value & 7) == 0 || (value & 7) == 1 || (value & 7) == 2 || (value & 7) == 3 || (value & 7) == 5 || (value & 7) == 7))
         return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7 (+8/16/32 measurement bits)");
+    if (!std::strcmp(key, "blend_variant") && (value < 0 || value > 7 || (value & 1)))
+        return fail(r, RTR_ERR_ARG, "blend_variant must be 0, 2, 4 or 6");
     *slot = int(value);
     return RTR_OK;
 }

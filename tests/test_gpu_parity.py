@@ -157,7 +157,7 @@ def test_cuda_vs_live_reference(gpu, cpu_oracle, name):
 # ------------------------------------------------------------------ invariances / variants
 VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u, chunk_cull=c)
             for v, u, b, c in [(0, 1, 0, 0), (1, 2, 2, 0), (2, 4, 0, 0), (3, 8, 2, 0), (5, 4, 0, 0), (7, 4, 2, 0),
-                               (0, 4, 2, 1), (1, 4, 0, 1), (3, 4, 0, 1), (7, 4, 2, 1)]]
+                               (0, 4, 2, 1), (1, 4, 0, 1), (3, 4, 0, 1), (7, 4, 2, 1), (5, 4, 4, 1), (5, 4, 6, 0), (5, 2, 4, 0)]]
 
 
 @pytest.mark.parametrize("opts", VARIANTS)
@@ -476,3 +476,42 @@ def test_chunk_culling_pixel_boundary_points(gpu):
         pc.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert (res[0][0] != 0x7F7FFFFF).sum() > 4
+
+
+def test_float_accumulator_overflow_falls_back_to_exact_sums(gpu, cpu_oracle):
+    """The default blend keeps {b,g,r,count} as floats (one 16-byte RED per point), exact up to 65793 points per
+    pixel.  70 000 white points in one pixel must trigger the in-stream exact re-run; 65 793 must not need it; both
+    equal the oracle (the reference's u32 sums)."""
+    W, H = 64, 48
+    m = np.array([50, 0, 31.5, 0, 0, 50, 23.5, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
+    rng = np.random.default_rng(5)
+    for heavy in (70_000, 65_793, 65_794):
+        n = heavy + 3000
+        xyz = rng.uniform(-1.0, 1.0, (n, 3)).astype(np.float32)
+        xyz[:, 2] = rng.uniform(1.5, 3.0, n).astype(np.float32)
+        xyz[:heavy] = np.array([0.013, 0.009, 1.0], np.float32)
+        bgr = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+        bgr[:heavy] = 255
+        rec = gpu.pack_records(xyz, bgr)
+        for filtered in (False, True):
+            for opts in ({}, {"chunk_cull": 0}, {"blend_variant": 0}):
+                pc = gpu.ProjectCloud.from_packed(rec)
+                for k, v in opts.items():
+                    pc.set_option(k, v)
+                c = gpu.CameraCalibration()
+                c.setWidth(W)
+                c.setHeight(H)
+                pc.set_camera(c)
+                pc.set_cam_proj_raw(m)
+                color, depth = np.zeros(W * H * 3, np.uint8), np.zeros(W * H, np.float32)
+                fn = pc._lib.rtr_render_filtered if filtered else pc._lib.rtr_render_rgbd
+                pc._check(fn(pc._h, color.ctypes.data, depth.ctypes.data))
+                accum = pc.read("accum", np.uint32, W * H * 4)
+                flag = pc.read("minmax", np.uint32, 3)[2]
+                tap = pc.project_points()
+                pc.close()
+                gold = cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(rec), W, H, filtered=filtered)
+                assert accum.reshape(-1, 4)[:, 3].max() == heavy
+                assert np.array_equal(accum, gold["accum"]) and np.array_equal(color, gold["image"])
+                assert np.array_equal(depth.view(np.uint32), gold["zbuf"])
+                assert flag == (1 if (heavy > 65_793 and opts.get("blend_variant", 4) == 4) else 0)
