@@ -233,6 +233,41 @@ class RefOracle:
             pass
 
 
+class RefHost:
+    """CPU-only entry points of the compiled reference (no GPU needed): its .oct writer/reader
+    (Octreegrid.h:53-114) and CameraCalibration::loadCalibration(file) (CameraCalibration.cpp:101-209)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_LIB):
+            raise RuntimeError(f"{REF_LIB} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(REF_LIB)
+        self.lib.ref_oct_write.argtypes = [C.c_char_p, _vp, _vp, _vp, C.c_size_t, _i, _i, _i]
+        self.lib.ref_oct_read.argtypes = [C.c_char_p, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp]
+        self.lib.ref_load_calibration.argtypes = [C.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp]
+
+    def oct_write(self, path, xyz, bgr, keys, dims):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        keys = np.ascontiguousarray(keys, np.int32)
+        assert self.lib.ref_oct_write(os.fsencode(path), _p(xyz), _p(bgr), _p(keys), len(keys), *[int(d) for d in dims]) == 1
+
+    def oct_read(self, path, cap):
+        xyz4 = np.zeros((cap, 4), np.float32)
+        bgra = np.zeros((cap, 4), np.uint8)
+        n = C.c_size_t(0)
+        dims = np.zeros(3, np.int32)
+        assert self.lib.ref_oct_read(os.fsencode(path), _p(xyz4), _p(bgra), cap, C.byref(n), _p(dims)) == 1
+        return xyz4[:n.value], bgra[:n.value], tuple(int(d) for d in dims)
+
+    def load_calibration(self, path):
+        W, H, nd, fe = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        K, d = np.zeros(9), np.zeros(8)
+        rc = self.lib.ref_load_calibration(os.fsencode(path), C.byref(W), C.byref(H), _p(K), _p(d), C.byref(nd), C.byref(fe))
+        if rc != 1:
+            return None
+        return dict(W=W.value, H=H.value, K=K.reshape(3, 3), dist=d[:nd.value].copy(), fisheye=bool(fe.value))
+
+
 _cpu = None
 
 

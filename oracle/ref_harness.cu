@@ -181,4 +181,47 @@ int ref_time_point_kernels(void* hv, int W, int H, int iters, float* ms) {
     return cudaGetLastError() == cudaSuccess ? 1 : -3;
 }
 
+// ---- "next"-row pins (CPU only): the reference's own .oct writer/reader and calibration parser.
+// Builds grid[key] from caller-supplied per-point keys and writes it with OctreeGrid::writeOctreeBinary
+// (Octreegrid.h:53-79).
+int ref_oct_write(const char* path, const float* xyz, const uint8_t* bgr, const int* keys, size_t n, int nx, int ny, int nz) {
+    std::unordered_map<int, OctreeGrid::Block> grid;
+    for (size_t i = 0; i < n; ++i) {
+        OctreeGrid::Block& b = grid[keys[i]];
+        b.positions.emplace_back(cv::Point3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+        b.colors.emplace_back(cv::Vec3b(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]));
+    }
+    return OctreeGrid::writeOctreeBinary(path, grid, nx, ny, nz) ? 1 : -1;
+}
+// OctreeGrid::readOctreeBinary (Octreegrid.h:82-114) + the constructor's flattening (Octreegrid.h:162-180).
+int ref_oct_read(const char* path, float* xyz4_out, uint8_t* bgra_out, size_t cap, size_t* n, int* dims3) {
+    std::unordered_map<int, OctreeGrid::Block> grid;
+    if (!OctreeGrid::readOctreeBinary(path, grid, dims3[0], dims3[1], dims3[2])) return -1;
+    std::vector<float4> v = OctreeGrid::getVertexPositions(grid);
+    std::vector<uchar4> c = OctreeGrid::getVertexColors(grid);
+    *n = v.size();
+    if (v.size() > cap) return -2;
+    std::memcpy(xyz4_out, v.data(), v.size() * sizeof(float4));
+    std::memcpy(bgra_out, c.data(), c.size() * sizeof(uchar4));
+    return 1;
+}
+// CameraCalibration::loadCalibration(file) (CameraCalibration.cpp:101-209).
+int ref_load_calibration(const char* path, int* W, int* H, double* K9, double* dist8, int* n_dist, int* fisheye) {
+    CameraCalibration c;
+    std::ostringstream sink;
+    std::streambuf* e = std::cerr.rdbuf(sink.rdbuf());
+    const bool ok = c.loadCalibration(std::string(path));
+    std::cerr.rdbuf(e);
+    if (!ok) return -1;
+    *W = c.getWidth();
+    *H = c.getHeight();
+    const cv::Matx33d K = c.getIntrinsicsMatrix();
+    for (int i = 0; i < 9; ++i) K9[i] = K.val[i];
+    const std::vector<double> d = c.getDistortionParameters();
+    *n_dist = int(d.size());
+    for (size_t i = 0; i < d.size() && i < 8; ++i) dist8[i] = d[i];
+    *fisheye = c.isFishEye() ? 1 : 0;
+    return 1;
+}
+
 }  // extern "C"

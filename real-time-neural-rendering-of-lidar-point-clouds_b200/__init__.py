@@ -70,6 +70,21 @@ API = {
     "rtr_comm_destroy": (_i, [_vp]),
     "rtr_version": (C.c_char_p, []),
 }
+_ip, _u8pp, _fpp = C.POINTER(_i), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.POINTER(C.c_float))
+# include/rtr_b200_io.h ("next" rows of SURVEY.md §8 f)
+API_IO = {
+    "rtr_load_ply": (_i, [_vp, C.c_char_p, _i]),
+    "rtr_bin_cells": (_i, [_vp, _ip]),
+    "rtr_io_write_ply": (_i, [C.c_char_p, _vp, _vp, _u64]),
+    "rtr_load_oct": (_i, [_vp, C.c_char_p]),
+    "rtr_io_write_oct": (_i, [C.c_char_p, _vp, _vp, _u64]),
+    "rtr_io_read_oct": (_i, [C.c_char_p, _fpp, _u8pp, C.POINTER(_u64), _ip, C.POINTER(_ip), C.POINTER(C.POINTER(_u64))]),
+    "rtr_io_free": (None, [_vp]),
+    "rtr_io_load_calibration": (_i, [C.c_char_p, _ip, _ip, _dp, _dp, _ip, _ip]),
+    "rtr_io_load_trajectory": (_i, [C.c_char_p, _i, _dp, _i, _ip]),
+    "rtr_io_invert_rigid": (_i, [_dp, _dp]),
+    "rtr_postprocess_unet_output": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+}
 
 
 class DeviceBuffers(C.Structure):
@@ -95,7 +110,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     if not os.path.exists(p):
         raise RuntimeError(f"{p} not found: build the CUDA library first (no CPU fallback exists)")
     lib = C.CDLL(p)
-    for name, (res, args) in API.items():
+    for name, (res, args) in list(API.items()) + list(API_IO.items()):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
     if path is None:
@@ -316,6 +331,31 @@ class ProjectCloud:
     def launch_count(self) -> int:
         return int(self._lib.rtr_launch_count(self._h))
 
+    # ---- loaders / post-process (include/rtr_b200_io.h)
+    @classmethod
+    def from_ply(cls, path: str, bin_cells: bool = True, device: int = 0, **kw) -> "ProjectCloud":
+        """CloudReader::loadCloud for a .ply (cloudreader.cpp:122-177), binning on the GPU."""
+        pc = cls(device=device, **kw)
+        pc._check(pc._lib.rtr_load_ply(pc._h, os.fsencode(path), int(bin_cells)))
+        return pc
+
+    @classmethod
+    def from_oct(cls, path: str, device: int = 0, **kw) -> "ProjectCloud":
+        """The pcd.oct cache hit of CloudReader::loadCloud (cloudreader.cpp:182-191)."""
+        pc = cls(device=device, **kw)
+        pc._check(pc._lib.rtr_load_oct(pc._h, os.fsencode(path)))
+        return pc
+
+    def bin_cells(self):
+        d = (_i * 3)()
+        self._check(self._lib.rtr_bin_cells(self._h, d))
+        return tuple(d)
+
+    def postprocess_unet_output(self, device_fp16_chw_ptr: int, W: int, H: int) -> np.ndarray:
+        out = np.empty(W * H * 3, dtype=np.uint8)
+        self._check(self._lib.rtr_postprocess_unet_output(self._h, _vp(device_fp16_chw_ptr), W, H, _ptr(out), None))
+        return out.reshape(H, W, 3)
+
     # ---- point-sharded multi-GPU plumbing (NCCL inside the library)
     def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
         buf = C.create_string_buffer(unique_id, 128)
@@ -358,6 +398,74 @@ class ProjectCloud:
             self.close()
         except Exception:
             pass
+
+
+# ---- file formats on either side of the path (host parsing inside the library)
+def _io_check(rc):
+    if rc != RTR_OK:
+        raise RtrError(rc, (load_library().rtr_last_error(None) or b"").decode())
+
+
+def write_ply(path, xyz, bgr):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    bgr = np.ascontiguousarray(bgr, dtype=np.uint8).reshape(-1, 3)
+    _io_check(load_library().rtr_io_write_ply(os.fsencode(path), _ptr(xyz), _ptr(bgr), len(xyz)))
+
+
+def write_oct(path, xyz, bgr):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    bgr = np.ascontiguousarray(bgr, dtype=np.uint8).reshape(-1, 3)
+    _io_check(load_library().rtr_io_write_oct(os.fsencode(path), _ptr(xyz), _ptr(bgr), len(xyz)))
+
+
+def read_oct(path):
+    """-> dict(xyz (n,3) f32, bgr (n,3) u8, dims (nx,ny,nz), keys, counts) in file order."""
+    lib = load_library()
+    xyz, bgr, n = C.POINTER(C.c_float)(), C.POINTER(C.c_uint8)(), _u64(0)
+    hdr, keys, counts = (_i * 4)(), _ip(), C.POINTER(_u64)()
+    _io_check(lib.rtr_io_read_oct(os.fsencode(path), C.byref(xyz), C.byref(bgr), C.byref(n), hdr, C.byref(keys), C.byref(counts)))
+    nn, nb = int(n.value), hdr[3]
+    out = dict(xyz=np.ctypeslib.as_array(xyz, shape=(nn, 3)).copy() if nn else np.zeros((0, 3), np.float32),
+               bgr=np.ctypeslib.as_array(bgr, shape=(nn, 3)).copy() if nn else np.zeros((0, 3), np.uint8),
+               dims=(hdr[0], hdr[1], hdr[2]),
+               keys=np.ctypeslib.as_array(keys, shape=(nb,)).copy() if nb else np.zeros(0, np.int32),
+               counts=np.ctypeslib.as_array(counts, shape=(nb,)).copy() if nb else np.zeros(0, np.uint64))
+    for p in (xyz, bgr, keys, counts):
+        lib.rtr_io_free(C.cast(p, _vp))
+    return out
+
+
+def load_calibration(path) -> "CameraCalibration":
+    """CameraCalibration::loadCalibration(file) (CameraCalibration.cpp:101-209)."""
+    W, H, nd, fe = _i(0), _i(0), _i(0), _i(0)
+    K, d = np.zeros(9), np.zeros(8)
+    _io_check(load_library().rtr_io_load_calibration(os.fsencode(path), C.byref(W), C.byref(H), K.ctypes.data_as(_dp),
+                                                     d.ctypes.data_as(_dp), C.byref(nd), C.byref(fe)))
+    c = CameraCalibration()
+    c.setIntrinsicsMatrix(K)
+    c._dists = [float(x) for x in d[:nd.value]]
+    c.setWidth(W.value)
+    c.setHeight(H.value)
+    c.fisheye = bool(fe.value)
+    return c
+
+
+def load_trajectory(path, order: int = 0, max_poses: int = 1 << 20) -> np.ndarray:
+    """(n, 4, 4) camera->world poses; order 0 = 'ts tx ty tz qx qy qz qw' (what the example parses,
+    main.cpp:32), 1 = COLMAP images.txt order (README.md:92)."""
+    n = sum(1 for ln in open(path) if ln.strip() and not ln.startswith("#"))
+    n = min(n, max_poses)
+    out = np.zeros((max(n, 1), 16))
+    got = _i(0)
+    _io_check(load_library().rtr_io_load_trajectory(os.fsencode(path), order, out.ctypes.data_as(_dp), n, C.byref(got)))
+    return out[:got.value].reshape(-1, 4, 4)
+
+
+def invert_rigid(pose) -> np.ndarray:
+    p = _as_f64(pose, 16)
+    o = np.zeros(16)
+    _io_check(load_library().rtr_io_invert_rigid(p.ctypes.data_as(_dp), o.ctypes.data_as(_dp)))
+    return o.reshape(4, 4)
 
 
 # ---- host-side helpers shared by bench and tests (pure host logic, no compute)

@@ -136,11 +136,11 @@ __global__ void __launch_bounds__(256) resolve_generic_kernel(const uint4* __res
                                                               uint32_t* __restrict__ overflow, bool gated) {
     pdl_prologue();
     if (gated && *overflow == 0u) return;
-    const uint64_t id = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (id >= cov) return;
-    uint8_t b, g, r;
-    resolve_px(accum_as_u32(accum[id], f32acc, overflow), b, g, r);
-    image[id * 3 + 0] = b; image[id * 3 + 1] = g; image[id * 3 + 2] = r;
+    for (uint64_t id = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; id < cov; id += uint64_t(gridDim.x) * blockDim.x) {
+        uint8_t b, g, r;
+        resolve_px(accum_as_u32(accum[id], f32acc, overflow), b, g, r);
+        image[id * 3 + 0] = b; image[id * 3 + 1] = g; image[id * 3 + 2] = r;
+    }
 }
 
 __global__ void __launch_bounds__(256) minmax_generic_kernel(const uint32_t* __restrict__ zbuf, uint64_t count,
@@ -301,8 +301,8 @@ __global__ void __launch_bounds__(256) up_level_kernel(const float* __restrict__
 cudaError_t launch_resolve_gated(cudaStream_t s, const FrameBuffers& fb, int W, int H) {
     const uint64_t cov = clear_coverage(W, H);
     if (cov == 0) return cudaSuccess;
-    launch_pdl(resolve_generic_kernel, dim3(unsigned((cov + 255) / 256)), dim3(256), s, reinterpret_cast<const uint4*>(fb.accum), fb.image, cov,
-                                                                       false, fb.minmax + 2, true);
+    launch_pdl(resolve_generic_kernel, dim3(148 * 2), dim3(256), s, reinterpret_cast<const uint4*>(fb.accum), fb.image, cov,
+               false, fb.minmax + 2, true);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,72 @@
+// Internal definition of the renderer object shared by rtr_renderer.cu (hot path + C ABI) and
+// rtr_io.cu (loaders / post-process, SURVEY.md §8 f).  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rtr_b200.h"
+#include "rtr_kernels.h"
+
+typedef struct ncclComm* ncclComm_t;
+
+namespace rtr {
+struct FrameSet {
+    FrameBuffers fb{};
+    bool f32acc = false;  // the last frame rendered into this set accumulated colour sums as floats
+    cudaEvent_t rendered = nullptr, copied = nullptr;
+};
+
+}  // namespace rtr
+
+struct rtr_renderer {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // cloud
+    rtr::PointRecord* points = nullptr;
+    uint64_t n_points = 0;
+    bool owns_points = false;
+    uint64_t index_base = 0;  // global index of local point 0 (point sharding)
+    // chunk-level frustum culling (rtr_cull.cu)
+    rtr::ChunkBounds* bounds = nullptr;
+    uint32_t* vis_list = nullptr;
+    rtr::CullState* cull_state = nullptr;
+    uint32_t n_chunks = 0;
+    // camera
+    int W = 0, H = 0;
+    double K[9] = {0};
+    double dist[5] = {0};
+    double E[16] = {0};
+    bool have_K = false, have_E = false, raw_proj = false;
+    float cam_proj[16] = {0};
+    // frame buffers (two sets, see header)
+    rtr::FrameSet set[2];
+    int cur = 0;
+    int alloc_W = 0, alloc_H = 0;
+    rtr::PyramidDims dims{};
+    bool masks_allocated = false, key64_allocated = false;
+    // options
+    int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
+    int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1;
+    cudaEvent_t ev[6] = {nullptr};
+    // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
+    std::vector<cudaEvent_t> ev_pool;
+    int ev_frames = 0;
+    double ev_sum[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t ev_count = 0;
+    uint64_t launches = 0;
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    std::string err;
+};
+
+namespace rtr {
+int renderer_fail(rtr_renderer* r, int code, const std::string& msg);
+// Frees the current cloud and allocates room for n records (r->points, owned).
+int replace_cloud(rtr_renderer* r, uint64_t n);
+// (Re)builds the chunk bounds for the cloud in r->points; every upload path ends with it.
+int build_chunk_bounds(rtr_renderer* r);
+}  // namespace rtr

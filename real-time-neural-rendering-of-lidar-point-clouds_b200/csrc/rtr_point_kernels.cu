@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(kPointBlock) blend_kernel(const PointRecord* _
                                                             const uint32_t* __restrict__ gate) {
     pdl_prologue();
     if (gate && *gate == 0u) return;
-    blend_tile<UNROLL, VARIANT, DISTORT>(pts, n, uint64_t(blockIdx.x) * (kPointBlock * UNROLL) + threadIdx.x, pp, zbuf, accum2);
+    // one tile per CTA in the normal launch; the gated exact re-run uses a small grid and strides
+    const uint64_t n_tiles = (n + kPointBlock * UNROLL - 1) / (kPointBlock * UNROLL);
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        blend_tile<UNROLL, VARIANT, DISTORT>(pts, n, t * (kPointBlock * UNROLL) + threadIdx.x, pp, zbuf, accum2);
 }
 
 template <int VARIANT>
@@ -296,7 +299,7 @@ cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const P
                               const ProjParams& pp, const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf,
                               uint32_t* accum, const uint32_t* gate) {
     if (n == 0) return cudaSuccess;
-    const unsigned grid = unsigned(sm_count) * 8u;
+    const unsigned grid = unsigned(sm_count) * (gate ? 2u : 8u);  // the gated re-run almost always returns at once
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     switch (variant & 6) {
         case 0: launch_pdl((blend_list_kernel<0>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate); break;
@@ -308,7 +311,7 @@ cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const P
 }
 
 cudaError_t launch_clear_accum_gated(cudaStream_t s, int sm_count, uint32_t* accum, uint64_t n_px, const uint32_t* gate) {
-    launch_pdl(clear_accum_gated_kernel, dim3(sm_count * 8), dim3(256), s, reinterpret_cast<uint4*>(accum), n_px, gate);
+    launch_pdl(clear_accum_gated_kernel, dim3(sm_count * 2), dim3(256), s, reinterpret_cast<uint4*>(accum), n_px, gate);
     return cudaGetLastError();
 }
 
@@ -356,7 +359,7 @@ cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointReco
 template <int UNROLL, int VARIANT>
 static cudaError_t launch_blend_uv(cudaStream_t s, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                    const uint32_t* zbuf, uint32_t* accum, const uint32_t* gate) {
-    const unsigned grid = grid_for(n, kPointBlock * UNROLL);
+    const unsigned grid = gate ? 148u * 2u : grid_for(n, kPointBlock * UNROLL);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     if (pp.distort) launch_pdl((blend_kernel<UNROLL, VARIANT, true>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, zbuf, a2, gate);
     else launch_pdl((blend_kernel<UNROLL, VARIANT, false>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, zbuf, a2, gate);

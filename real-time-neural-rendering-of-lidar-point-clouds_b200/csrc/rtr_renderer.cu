@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/rtr_b200.h"
+#include "rtr_internal.h"
 #include "rtr_kernels.h"
 
 using namespace rtr;
@@ -43,7 +44,6 @@ thread_local std::string g_create_error;
 
 // ---- minimal NCCL binding, resolved at run time (libnccl.so.2 — torch's bundled copy when the
 // process already loaded it, else the system one).  Only what the point-sharded path needs.
-typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclUint32_ = 3, ncclUint64_ = 5 };  // ncclDataType_t values (nccl.h)
 enum { ncclSum_ = 0, ncclMin_ = 3 };        // ncclRedOp_t values
@@ -71,56 +71,8 @@ struct NcclApi {
 NcclApi g_nccl;
 std::mutex g_nccl_mu;
 
-struct FrameSet {
-    FrameBuffers fb{};
-    bool f32acc = false;  // the last frame rendered into this set accumulated colour sums as floats
-    cudaEvent_t rendered = nullptr, copied = nullptr;
-};
-
 }  // namespace
 
-struct rtr_renderer {
-    int device = 0;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    // cloud
-    PointRecord* points = nullptr;
-    uint64_t n_points = 0;
-    bool owns_points = false;
-    uint64_t index_base = 0;  // global index of local point 0 (point sharding)
-    // chunk-level frustum culling (rtr_cull.cu)
-    ChunkBounds* bounds = nullptr;
-    uint32_t* vis_list = nullptr;
-    CullState* cull_state = nullptr;
-    uint32_t n_chunks = 0;
-    // camera
-    int W = 0, H = 0;
-    double K[9] = {0};
-    double dist[5] = {0};
-    double E[16] = {0};
-    bool have_K = false, have_E = false, raw_proj = false;
-    float cam_proj[16] = {0};
-    // frame buffers (two sets, see header)
-    FrameSet set[2];
-    int cur = 0;
-    int alloc_W = 0, alloc_H = 0;
-    PyramidDims dims{};
-    bool masks_allocated = false, key64_allocated = false;
-    // options
-    int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
-    int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1;
-    cudaEvent_t ev[6] = {nullptr};
-    // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
-    std::vector<cudaEvent_t> ev_pool;
-    int ev_frames = 0;
-    double ev_sum[6] = {0, 0, 0, 0, 0, 0};
-    uint64_t ev_count = 0;
-    uint64_t launches = 0;
-    // comm
-    ncclComm_t comm = nullptr;
-    int rank = 0, n_ranks = 1;
-    std::string err;
-};
 
 namespace {
 
@@ -128,6 +80,11 @@ int fail(rtr_renderer* r, int code, const std::string& msg) {
     if (r) r->err = msg; else g_create_error = msg;
     return code;
 }
+}  // namespace
+namespace rtr {
+int renderer_fail(rtr_renderer* r, int code, const std::string& msg) { return fail(r, code, msg); }
+}
+namespace {
 int cuda_fail(rtr_renderer* r, cudaError_t e, const char* what) {
     return fail(r, RTR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
@@ -465,7 +422,10 @@ void rtr_destroy(rtr_renderer* r) {
 
 const char* rtr_last_error(const rtr_renderer* r) { return r ? r->err.c_str() : g_create_error.c_str(); }
 
-static int replace_cloud(rtr_renderer* r, uint64_t n) {
+}  // extern "C"
+
+namespace rtr {
+int replace_cloud(rtr_renderer* r, uint64_t n) {
     RTR_CUDA(r, cudaSetDevice(r->device));
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     if (r->owns_points) cudaFree(r->points);
@@ -480,7 +440,7 @@ static int replace_cloud(rtr_renderer* r, uint64_t n) {
 }
 
 // Chunk bounds + visible-list storage for the cloud now in r->points (every upload path ends here).
-static int build_chunk_bounds(rtr_renderer* r) {
+int build_chunk_bounds(rtr_renderer* r) {
     if (r->n_points == 0) return RTR_OK;
     r->n_chunks = uint32_t((r->n_points + kChunkPoints - 1) / kChunkPoints);
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->bounds), size_t(r->n_chunks) * sizeof(ChunkBounds)));
@@ -492,6 +452,9 @@ static int build_chunk_bounds(rtr_renderer* r) {
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     return RTR_OK;
 }
+}  // namespace rtr
+
+extern "C" {
 
 int rtr_upload_cloud_xyz_bgr(rtr_renderer* r, const float* xyz, const uint8_t* bgr, uint64_t n) {
     if (!r) return RTR_ERR_ARG;

@@ -8,7 +8,7 @@ from conftest import ROOT, has_gpu
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "rtr_b200.h")).read()
+    text = open(os.path.join(ROOT, "include", "rtr_b200.h")).read() + open(os.path.join(ROOT, "include", "rtr_b200_io.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(rtr_[a-z0-9_]+)\s*\(", text)))
 
@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), f"librtr_b200.so does not export {s}"
-    assert set(declared_symbols()) == set(pkg.API), "python binding and header disagree"
+    assert set(declared_symbols()) == set(pkg.API) | set(pkg.API_IO), "python binding and headers disagree"
 
 
 def test_no_cpu_fallback(pkg):
