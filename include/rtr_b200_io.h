@@ -30,6 +30,10 @@ int rtr_load_ply(rtr_renderer* r, const char* path, int bin_cells);
  * the reference iterates an unordered_map, i.e. an unspecified order, and no output depends on it).
  * dims3 (may be NULL) receives numBlocks_x/y/z. */
 int rtr_bin_cells(rtr_renderer* r, int* dims3);
+/* Re-order the resident cloud along a 63-bit Morton curve (21 bits per axis over the bounding box): consecutive
+ * records are then neighbours in space, so a warp's points land on neighbouring pixels and the z-buffer gathers /
+ * REDs of the point passes touch far fewer L2 sectors.  No output depends on point order. */
+int rtr_sort_morton(rtr_renderer* r);
 /* Fixture support: write a binary_little_endian PLY (x y z float, red green blue uchar) from B,G,R colours. */
 int rtr_io_write_ply(const char* path, const float* xyz, const uint8_t* bgr, uint64_t n);
 

@@ -165,7 +165,7 @@ class CpuOracle:
 class RefOracle:
     """The reference's ProjectCloud, compiled unmodified (GPU required)."""
 
-    def __init__(self, xyz: np.ndarray, bgr: np.ndarray, stock: bool = False):
+    def __init__(self, xyz: np.ndarray, bgr: np.ndarray, stock: bool = False, model_name: str | None = None):
         path = REF_LIB_STOCK if stock else REF_LIB
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
@@ -183,9 +183,15 @@ class RefOracle:
         xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
         bgr = np.ascontiguousarray(bgr, dtype=np.uint8).reshape(-1, 3)
         self.n = len(xyz)
-        self.h = L.ref_create(_p(xyz), _p(bgr), self.n)
+        L.ref_create_with_model.restype = _vp
+        L.ref_create_with_model.argtypes = [_vp, _vp, C.c_size_t, C.c_char_p]
+        L.ref_compute_full.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp]
+        if model_name:   # the reference looks the file up in $HOME/.render_cache (project_cloud.cu:227)
+            self.h = L.ref_create_with_model(_p(xyz), _p(bgr), self.n, model_name.encode())
+        else:
+            self.h = L.ref_create(_p(xyz), _p(bgr), self.n)
         if not self.h:
-            raise RuntimeError("ref_create failed")
+            raise RuntimeError("ref_create failed" + (f" (is ~/.render_cache/{model_name} there?)" if model_name else ""))
 
     @property
     def block_size(self) -> int:
@@ -204,6 +210,9 @@ class RefOracle:
 
     def computeFilteredRGBD(self, W, H, K, E, **kw):
         return self._call(self.lib.ref_compute_filtered, W, H, K, E, **kw)
+
+    def computeFull(self, W, H, K, E, **kw):
+        return self._call(self.lib.ref_compute_full, W, H, K, E, **kw)
 
     _WHAT = {"zbuf": (0, np.uint32), "accum": (1, np.uint32), "image": (2, np.uint8), "tensor": (3, np.uint16),
              "cam_proj": (4, np.float32), "min": (5, np.uint32), "max": (6, np.uint32)}

@@ -18,6 +18,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <sstream>
 #include <unordered_map>
 #include <vector>
@@ -95,6 +96,40 @@ void* ref_create(const float* xyz, const uint8_t* bgr, size_t n) {
     std::cout.rdbuf(o);
     std::cerr.rdbuf(e);
     return h;
+}
+
+// Same with a TorchScript model: the reference loads $HOME/.render_cache/<model_name> (project_cloud.cu:225-239)
+// and computeFull (project_cloud.cu:437-493) runs it.  Returns NULL if the file is absent (the reference exit()s).
+void* ref_create_with_model(const float* xyz, const uint8_t* bgr, size_t n, const char* model_name) {
+    const char* home = getenv("HOME");
+    if (!home || !std::filesystem::exists(std::filesystem::path(home) / ".render_cache" / model_name)) return nullptr;
+    std::unordered_map<int, OctreeGrid::Block> grid;
+    OctreeGrid::Block& b = grid[0];
+    b.positions.resize(n);
+    b.colors.resize(n);
+    std::memcpy(static_cast<void*>(b.positions.data()), xyz, n * 3 * sizeof(float));
+    std::memcpy(static_cast<void*>(b.colors.data()), bgr, n * 3);
+    std::ostringstream sink;
+    std::streambuf* o = std::cout.rdbuf(sink.rdbuf());
+    std::streambuf* e = std::cerr.rdbuf(sink.rdbuf());
+    RefHandle* h = new RefHandle;
+    h->pc = new ProjectCloud(grid, std::string(model_name));
+    h->n = n;
+    std::cout.rdbuf(o);
+    std::cerr.rdbuf(e);
+    return h;
+}
+
+// computeFull: projection + prefilter + U-Net + 8-bit conversion, host outputs (color H*W*3 uint8, depth H*W float).
+int ref_compute_full(void* hv, int W, int H, const double* K9, const double* E16, uint8_t* color, float* depth) {
+    RefHandle* h = static_cast<RefHandle*>(hv);
+    CameraCalibration c = make_calib(W, H, K9);
+    cv::Mat mc(H, W, CV_8UC3, color), md(H, W, CV_32F, depth);
+    std::ostringstream sink;  // RENDER_TIME print per call (project_cloud.cu:490)
+    std::streambuf* o = std::cout.rdbuf(sink.rdbuf());
+    const int rc = h->pc->computeFull(c, make_E(E16), color ? &mc : nullptr, depth ? &md : nullptr);
+    std::cout.rdbuf(o);
+    return rc;
 }
 
 void ref_destroy(void* hv) {

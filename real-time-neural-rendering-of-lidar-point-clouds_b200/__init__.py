@@ -75,6 +75,7 @@ _ip, _u8pp, _fpp = C.POINTER(_i), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.P
 API_IO = {
     "rtr_load_ply": (_i, [_vp, C.c_char_p, _i]),
     "rtr_bin_cells": (_i, [_vp, _ip]),
+    "rtr_sort_morton": (_i, [_vp]),
     "rtr_io_write_ply": (_i, [C.c_char_p, _vp, _vp, _u64]),
     "rtr_load_oct": (_i, [_vp, C.c_char_p]),
     "rtr_io_write_oct": (_i, [C.c_char_p, _vp, _vp, _u64]),
@@ -350,6 +351,9 @@ class ProjectCloud:
         d = (_i * 3)()
         self._check(self._lib.rtr_bin_cells(self._h, d))
         return tuple(d)
+
+    def sort_morton(self):
+        self._check(self._lib.rtr_sort_morton(self._h))
 
     def postprocess_unet_output(self, device_fp16_chw_ptr: int, W: int, H: int) -> np.ndarray:
         out = np.empty(W * H * 3, dtype=np.uint8)

@@ -106,6 +106,33 @@ __global__ void __launch_bounds__(256) cell_keys_kernel(const PointRecord* __res
     keys[i] = uint32_t(cell_key(c, g)) ^ 0x80000000u;  // signed order for the unsigned radix sort
     idx[i] = uint32_t(i);
 }
+// 63-bit Morton code of the position quantised to 21 bits per axis over the bounding box (rtr_sort_morton).
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {
+    v &= 0x1FFFFFull;
+    v = (v | (v << 32)) & 0x1F00000000FFFFull;
+    v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+    v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+__global__ void __launch_bounds__(256) morton_keys_kernel(const PointRecord* __restrict__ pts, uint64_t n, GridGeom g,
+                                                          unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PointRecord p = pts[i];
+    const float c[3] = {p.x, p.y, p.z};
+    unsigned long long key = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float t = (c[a] - g.mn[a]) / (g.mx[a] - g.mn[a]);
+        t = t >= 0.0f ? (t <= 1.0f ? t : 1.0f) : 0.0f;  // NaN -> 0
+        key |= spread21(static_cast<unsigned long long>(t * 2097151.0f)) << a;
+    }
+    keys[i] = key;
+    idx[i] = uint32_t(i);
+}
+
 __global__ void __launch_bounds__(256) gather_kernel(const PointRecord* __restrict__ src, const uint32_t* __restrict__ idx,
                                                      uint64_t n, PointRecord* __restrict__ dst) {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -260,7 +287,11 @@ int rtr_io_write_ply(const char* path, const float* xyz, const uint8_t* bgr, uin
     return f.good() ? RTR_OK : renderer_fail(nullptr, RTR_ERR_ARG, "write failed");
 }
 
-int rtr_bin_cells(rtr_renderer* r, int* dims3) {
+static int reorder_cloud(rtr_renderer* r, int* dims3, bool morton);
+int rtr_bin_cells(rtr_renderer* r, int* dims3) { return reorder_cloud(r, dims3, false); }
+int rtr_sort_morton(rtr_renderer* r) { return reorder_cloud(r, nullptr, true); }
+
+static int reorder_cloud(rtr_renderer* r, int* dims3, bool morton) {
     if (!r) return RTR_ERR_ARG;
     if (!r->points || r->n_points == 0) return renderer_fail(r, RTR_ERR_STATE, "no cloud uploaded");
     if (!r->owns_points) return renderer_fail(r, RTR_ERR_STATE, "cannot re-order an adopted device cloud");
@@ -278,21 +309,33 @@ int rtr_bin_cells(rtr_renderer* r, int* dims3) {
     cudaFree(d_box);
     const GridGeom g = make_geom(box, box + 3);
     if (dims3) { dims3[0] = g.nb[0]; dims3[1] = g.nb[1]; dims3[2] = g.nb[2]; }
-    uint32_t *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *idx2 = nullptr;
+    uint32_t *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *idx2 = nullptr;  // keys: u32, or u64 for Morton codes
+    unsigned long long* k64 = nullptr;
+    unsigned long long* k64b = nullptr;
     PointRecord* sorted = nullptr;
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&keys), n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&keys2), n * 4);
+    const size_t kb = morton ? 8 : 4;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&keys), n * kb);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&keys2), n * kb);
+    k64 = reinterpret_cast<unsigned long long*>(keys);
+    k64b = reinterpret_cast<unsigned long long*>(keys2);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&idx), n * 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&idx2), n * 4);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sorted), n * sizeof(PointRecord));
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, idx2, n, 0, 32, s);
+    if (e == cudaSuccess)
+        e = morton ? cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k64, k64b, idx, idx2, n, 0, 63, s)
+                   : cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, idx2, n, 0, 32, s);
     if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
     if (e == cudaSuccess) {
         const unsigned grid = unsigned((n + 255) / 256);
-        cell_keys_kernel<<<grid, 256, 0, s>>>(r->points, n, g, keys, idx);
-        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, n, 0, 32, s);  // LSD radix sort: stable
+        if (morton) {
+            morton_keys_kernel<<<grid, 256, 0, s>>>(r->points, n, g, k64, idx);
+            e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k64, k64b, idx, idx2, n, 0, 63, s);
+        } else {
+            cell_keys_kernel<<<grid, 256, 0, s>>>(r->points, n, g, keys, idx);
+            e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, n, 0, 32, s);  // LSD radix sort: stable
+        }
         if (e == cudaSuccess) {
             gather_kernel<<<grid, 256, 0, s>>>(r->points, idx2, n, sorted);
             e = cudaStreamSynchronize(s);
