@@ -173,7 +173,7 @@ class ProjectCloud:
     """
 
     def __init__(self, xyz: Optional[np.ndarray] = None, bgr: Optional[np.ndarray] = None, device: int = 0,
-                 apply_distortion: bool = False):
+                 apply_distortion: bool = False, sort: bool = True):
         self._lib = load_library()
         h = _vp()
         rc = self._lib.rtr_create(device, C.byref(h))
@@ -183,6 +183,8 @@ class ProjectCloud:
         self.device = device
         self.apply_distortion = apply_distortion
         self._keep = None  # keeps adopted device memory alive
+        if not sort:   # default: uploads are Morton-sorted on the GPU (results never depend on point order)
+            self.set_option("sort_on_upload", 0)
         if xyz is not None:
             self.upload(xyz, bgr)
 

@@ -49,7 +49,7 @@ struct rtr_renderer {
     bool masks_allocated = false, key64_allocated = false;
     // options
     int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
-    int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1;
+    int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1, sort_on_upload = 1;
     cudaEvent_t ev[6] = {nullptr};
     // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
     std::vector<cudaEvent_t> ev_pool;
@@ -69,4 +69,8 @@ int renderer_fail(rtr_renderer* r, int code, const std::string& msg);
 int replace_cloud(rtr_renderer* r, uint64_t n);
 // (Re)builds the chunk bounds for the cloud in r->points; every upload path ends with it.
 int build_chunk_bounds(rtr_renderer* r);
+// Morton re-ordering of the owned resident cloud (rtr_io.cu); ends with build_chunk_bounds.
+int reorder_morton(rtr_renderer* r);
+// What every upload path calls last: Morton-sort when option sort_on_upload is set, then the chunk bounds.
+int finish_upload(rtr_renderer* r);
 }  // namespace rtr

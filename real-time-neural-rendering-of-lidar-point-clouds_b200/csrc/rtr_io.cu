@@ -169,7 +169,7 @@ int upload_records(rtr_renderer* r, const std::vector<PointRecord>& rec) {
     if (rc != RTR_OK || rec.empty()) return rc;
     IO_CUDA(r, cudaMemcpyAsync(r->points, rec.data(), rec.size() * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
     IO_CUDA(r, cudaStreamSynchronize(r->stream));
-    return build_chunk_bounds(r);
+    return finish_upload(r);
 }
 
 inline uint32_t pack_bgr(uint8_t b, uint8_t g, uint8_t rr) {
@@ -261,7 +261,10 @@ int rtr_load_ply(rtr_renderer* r, const char* path, int bin_cells) {
         return renderer_fail(r, RTR_ERR_UNSUPPORTED, "PLY format '" + fmt + "' not supported (ascii, binary_little_endian)");
     }
     IO_CUDA(r, cudaSetDevice(r->device));
+    const int sort_opt = r->sort_on_upload;
+    if (bin_cells) r->sort_on_upload = 0;  // the caller asked for the reference's grouping instead
     int rc = upload_records(r, rec);
+    r->sort_on_upload = sort_opt;
     if (rc != RTR_OK || !bin_cells) return rc;
     return rtr_bin_cells(r, nullptr);
 }
@@ -288,6 +291,11 @@ int rtr_io_write_ply(const char* path, const float* xyz, const uint8_t* bgr, uin
 }
 
 static int reorder_cloud(rtr_renderer* r, int* dims3, bool morton);
+}  // extern "C"
+namespace rtr {
+int reorder_morton(rtr_renderer* r) { return reorder_cloud(r, nullptr, true); }
+}
+extern "C" {
 int rtr_bin_cells(rtr_renderer* r, int* dims3) { return reorder_cloud(r, dims3, false); }
 int rtr_sort_morton(rtr_renderer* r) { return reorder_cloud(r, nullptr, true); }
 

@@ -452,6 +452,11 @@ int build_chunk_bounds(rtr_renderer* r) {
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     return RTR_OK;
 }
+
+int finish_upload(rtr_renderer* r) {
+    if (r->sort_on_upload && r->owns_points && r->n_points > 1) return reorder_morton(r);
+    return build_chunk_bounds(r);
+}
 }  // namespace rtr
 
 extern "C" {
@@ -485,7 +490,7 @@ int rtr_upload_cloud_xyz_bgr(rtr_renderer* r, const float* xyz, const uint8_t* b
     }
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
     for (int i = 0; i < 2; ++i) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
-    return build_chunk_bounds(r);
+    return finish_upload(r);
 }
 
 int rtr_upload_cloud_packed16(rtr_renderer* r, const void* host_records, uint64_t n) {
@@ -496,7 +501,7 @@ int rtr_upload_cloud_packed16(rtr_renderer* r, const void* host_records, uint64_
     if (rc != RTR_OK || n == 0) return rc;
     RTR_CUDA(r, cudaMemcpyAsync(r->points, host_records, n * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
-    return build_chunk_bounds(r);
+    return finish_upload(r);
 }
 
 int rtr_adopt_device_cloud_packed16(rtr_renderer* r, void* device_records, uint64_t n) {
@@ -522,7 +527,7 @@ int rtr_synth_cloud(rtr_renderer* r, uint64_t seed, uint64_t n_total, uint64_t f
     r->launches += 1;
     r->index_base = first;
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
-    return build_chunk_bounds(r);
+    return finish_upload(r);
 }
 
 uint64_t rtr_cloud_size(const rtr_renderer* r) { return r ? r->n_points : 0; }
@@ -764,6 +769,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "timing")) return &r->timing;
     if (!std::strcmp(key, "key64")) return &r->key64;
     if (!std::strcmp(key, "chunk_cull")) return &r->chunk_cull;
+    if (!std::strcmp(key, "sort_on_upload")) return &r->sort_on_upload;
     return nullptr;
 }
 

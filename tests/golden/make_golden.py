@@ -32,7 +32,7 @@ def run_case(pkg, cpu, case, out_dir):
     rec = cpu.synth_packed(case.seed, case.n, 0, case.n, case.hall, case.n_boxes)
     xyz, bgr = scenes.split_records(rec)
     ref = oracle.RefOracle(xyz, bgr)
-    mine = pkg.ProjectCloud.from_packed(rec)
+    mine = pkg.ProjectCloud.from_packed(rec, sort=False)   # taps must follow the seeded cloud's own order
     W, H, P = case.W, case.H, case.W * case.H
     data = {"block_size": np.array([ref.block_size], np.int32), "n_frames": np.array([len(case.poses)], np.int32)}
     for fi, E in enumerate(case.poses):

@@ -27,6 +27,10 @@ def frame(pc, pkg, calib, E, P, filtered=True):
     return color, depth.view(np.uint32), pc.read("tensor", np.uint16, P * 5)
 
 
+# key64's tie-break is the point index: keep the seeded order so that shard-local and whole-cloud indices agree
+SORT = False
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -44,9 +48,9 @@ def main():
     if rank == 0:
         uid.copy_(torch.frombuffer(bytearray(pkg.ProjectCloud.comm_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
-    shard = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, first=first, count=count, hall=case.hall, n_boxes=case.n_boxes, device=local)
+    shard = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, first=first, count=count, hall=case.hall, n_boxes=case.n_boxes, device=local, sort=SORT)
     shard.comm_init(uid.cpu().numpy().tobytes(), rank, world)
-    full = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local) if rank == 0 else None
+    full = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local, sort=SORT) if rank == 0 else None
     ok = True
     for key64 in (0, 1):
         shard.set_option("key64", key64)
@@ -67,7 +71,7 @@ def main():
     shard.close()
     # ---- frame-sharded
     poses = pkg.trajectory_w2c(11, center=(6.0, 5.0, 1.5), radius=2.0)
-    rep = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local)
+    rep = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local, sort=SORT)
     mine = pkg.shard_frames(len(poses), rank, world)
     digs = torch.zeros((len(poses), 32), dtype=torch.uint8, device="cuda")
     for f in mine:

@@ -33,7 +33,7 @@ def test_ply_loads_like_the_reference_loader(gpu, shuffled, tmp_path):
     xyz, bgr = scenes.split_records(rec)
     path = str(tmp_path / "cloud.ply")
     gpu.write_ply(path, xyz, bgr)
-    raw = gpu.ProjectCloud.from_ply(path, bin_cells=False)
+    raw = gpu.ProjectCloud.from_ply(path, bin_cells=False, sort=False)
     assert np.array_equal(raw.download_cloud().view(np.uint32), rec.view(np.uint32))       # file order, B,G,R packing
     direct = gpu.ProjectCloud.from_packed(rec)
     want = _frame(gpu, direct, case)
@@ -48,6 +48,9 @@ def test_ply_loads_like_the_reference_loader(gpu, shuffled, tmp_path):
     f1, v1, n1 = raw.cull_stats()
     f2, v2, n2 = binned.cull_stats()
     assert n1 == n2 and v1 / f1 > 0.95 * n1 and v2 / f2 < 0.8 * n2
+    # the default upload (Morton order) culls at least as well as the reference's cell grouping
+    f3, v3, n3 = direct.cull_stats()
+    assert v3 / f3 <= v2 / f2 * 1.1
     for pc in (raw, binned, direct):
         pc.close()
     # ascii flavour with double coordinates and extra properties
@@ -58,7 +61,7 @@ def test_ply_loads_like_the_reference_loader(gpu, shuffled, tmp_path):
                 "property float intensity\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
         for i in range(n):
             f.write(f"{float(xyz[i, 0])!r} {float(xyz[i, 1])!r} {float(xyz[i, 2])!r} 0.5 {bgr[i, 2]} {bgr[i, 1]} {bgr[i, 0]}\n")
-    a = gpu.ProjectCloud.from_ply(str(apath), bin_cells=False)
+    a = gpu.ProjectCloud.from_ply(str(apath), bin_cells=False, sort=False)
     assert np.array_equal(a.download_cloud().view(np.uint32), rec[:n].view(np.uint32))
     a.close()
     with pytest.raises(gpu.RtrError):
@@ -67,7 +70,7 @@ def test_ply_loads_like_the_reference_loader(gpu, shuffled, tmp_path):
 
 def test_bin_cells_on_resident_cloud(gpu, shuffled):
     case, rec = shuffled
-    pc = gpu.ProjectCloud.from_packed(rec)
+    pc = gpu.ProjectCloud.from_packed(rec, sort=False)
     before = _frame(gpu, pc, case)
     keys, dims, _, _ = grid_keys(rec[:, :3])
     assert pc.bin_cells() == dims
@@ -82,7 +85,7 @@ def test_oct_cache_loads(gpu, shuffled, tmp_path):
     xyz, bgr = scenes.split_records(rec)
     path = str(tmp_path / "pcd.oct")
     gpu.write_oct(path, xyz, bgr)
-    pc = gpu.ProjectCloud.from_oct(path)
+    pc = gpu.ProjectCloud.from_oct(path, sort=False)
     keys, _, _, _ = grid_keys(xyz)
     assert np.array_equal(pc.download_cloud().view(np.uint32), rec[np.argsort(keys, kind="stable")].view(np.uint32))
     direct = gpu.ProjectCloud.from_packed(rec)

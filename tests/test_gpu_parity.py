@@ -38,6 +38,7 @@ def render_mine(pkg, case, rec, keep_masks=False, options=None, with_taps=True):
     """Per pose: computeRGBD then computeFilteredRGBD on one renderer (like one reference object).
     Returns (frames, taps, extras)."""
     pc = pkg.ProjectCloud.from_packed(rec)
+    resident = pc.download_cloud() if with_taps else None   # uploads are Morton-sorted: taps follow THIS order
     for k, v in (options or {}).items():
         pc.set_option(k, v)
     if keep_masks:
@@ -56,7 +57,7 @@ def render_mine(pkg, case, rec, keep_masks=False, options=None, with_taps=True):
         o["flt_depth_host"], o["flt_color_host"] = depth.view(np.uint32).copy(), color.copy()
         o["flt_tensor"], o["flt_minmax"] = pc.read("tensor", np.uint16, P * 5), pc.read("minmax", np.uint32, 2)
         frames.append(o)
-        ex = {"cam_proj": pc.get_cam_proj().reshape(16)}
+        ex = {"cam_proj": pc.get_cam_proj().reshape(16), "records": resident}
         if keep_masks:
             b = pc.device_buffers()
             ex["levels"] = {i: pc.read(f"level{i}", np.float32, b.level_w[i] * b.level_h[i]) for i in range(1, 5)}
@@ -86,7 +87,10 @@ def test_cuda_vs_cpu_oracle_all_stages(gpu, cpu_oracle, name):
     # host matrix: K4*E as the reference's glm expression evaluates it
     for E, ex in zip(case.poses, extras):
         assert np.array_equal(ex["cam_proj"], cpu_oracle.cam_proj(case.K, E))
-    gold = scenes.oracle_frames(cpu_oracle, case, rec, taps)
+    resident = extras[0]["records"]
+    assert np.array_equal(np.sort(resident.view(np.uint32).view([("", np.uint32)] * 4).ravel()),
+                          np.sort(rec.view(np.uint32).view([("", np.uint32)] * 4).ravel())), "upload re-ordering lost or changed a record"
+    gold = scenes.oracle_frames(cpu_oracle, case, resident, taps)
     assert_frames_equal(mine, gold, f"{name} CUDA vs CPU oracle")
     # pyramid levels and masks of the last frame (stage taps 4-5)
     f = gold[-1]
@@ -191,7 +195,7 @@ def test_upload_xyz_bgr_equals_packed(gpu, cpu_oracle):
     case = scenes.CASES["small_160x96"]
     rec = cloud_of(cpu_oracle, case)
     xyz, bgr = scenes.split_records(rec)
-    pc = gpu.ProjectCloud(xyz, bgr)
+    pc = gpu.ProjectCloud(xyz, bgr, sort=False)
     assert pc.cloud_size == len(rec)
     assert np.array_equal(pc.download_cloud().view(np.uint32), rec.view(np.uint32))
     pc.close()
@@ -199,11 +203,11 @@ def test_upload_xyz_bgr_equals_packed(gpu, cpu_oracle):
 
 def test_device_synth_equals_oracle_synth(gpu, cpu_oracle):
     n = 300_000
-    pc = gpu.ProjectCloud.synthetic(seed=99, n_total=n, hall=scenes.HALL_LARGE, n_boxes=12)
+    pc = gpu.ProjectCloud.synthetic(seed=99, n_total=n, hall=scenes.HALL_LARGE, n_boxes=12, sort=False)
     rec = cpu_oracle.synth_packed(99, n, 0, n, scenes.HALL_LARGE, 12)
     assert np.array_equal(pc.download_cloud().view(np.uint32), rec.view(np.uint32))
     pc.close()
-    pc = gpu.ProjectCloud.synthetic(seed=99, n_total=n, first=1000, count=5000, hall=scenes.HALL_LARGE, n_boxes=12)
+    pc = gpu.ProjectCloud.synthetic(seed=99, n_total=n, first=1000, count=5000, hall=scenes.HALL_LARGE, n_boxes=12, sort=False)
     assert np.array_equal(pc.download_cloud().view(np.uint32), rec[1000:6000].view(np.uint32))
     pc.close()
 
@@ -212,8 +216,9 @@ def test_key64_depth_is_reference_depth_and_colour_is_nearest_point(gpu, cpu_ora
     case = scenes.CASES["c1_640x480"]
     rec = cloud_of(cpu_oracle, case)
     W, H, P = case.W, case.H, case.W * case.H
-    base, taps, _ = render_mine(gpu, case, rec)
-    pc = gpu.ProjectCloud.from_packed(rec)
+    base, taps, extras = render_mine(gpu, case, rec)
+    rec = extras[0]["records"]                       # the key's point index is the index in the RESIDENT order
+    pc = gpu.ProjectCloud.from_packed(rec, sort=False)
     pc.set_option("key64", 1)
     color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
     assert pc.computeRGBD(calib_of(gpu, case), case.poses[0], color, depth) == 1
@@ -266,7 +271,8 @@ def _render_records(gpu, rec, W, H, m16, filtered=True):
     fn = pc._lib.rtr_render_filtered if filtered else pc._lib.rtr_render_rgbd
     pc._check(fn(pc._h, color.ctypes.data, depth.ctypes.data))
     out = dict(color=color, depth=depth.view(np.uint32), tensor=pc.read("tensor", np.uint16, W * H * 5),
-               accum=pc.read("accum", np.uint32, W * H * 4), minmax=pc.read("minmax", np.uint32, 2))
+               accum=pc.read("accum", np.uint32, W * H * 4), minmax=pc.read("minmax", np.uint32, 2),
+               records=pc.download_cloud())
     tap = pc.project_points()
     pc.close()
     return out, tap
@@ -297,7 +303,7 @@ def test_adversarial_points(gpu, cpu_oracle):
     rec = gpu.pack_records(xyz, bgr)
     for filtered in (False, True):
         out, tap = _render_records(gpu, rec, W, H, m, filtered)
-        gold = _oracle_records(cpu_oracle, rec, W, H, tap, filtered)
+        gold = _oracle_records(cpu_oracle, out["records"], W, H, tap, filtered)
         assert np.array_equal(out["depth"], gold["zbuf"])
         assert np.array_equal(out["accum"], gold["accum"])
         assert np.array_equal(out["color"], gold["image"])
@@ -314,7 +320,7 @@ def test_nothing_in_frustum_and_single_point(gpu, cpu_oracle):
     assert (tap[0] == -1).all()
     assert (out["depth"] == np.float32(-1.0).view(np.uint32)).all() and not out["color"].any()
     assert out["minmax"].tolist() == [0xFFFFFFFF, 0]
-    gold = _oracle_records(cpu_oracle, behind, W, H, tap)
+    gold = _oracle_records(cpu_oracle, out["records"], W, H, tap)
     assert np.array_equal(out["tensor"], gold["tensor"]) and np.array_equal(out["depth"], gold["zbuf"])
     one = gpu.pack_records(np.array([[0.0, 0.0, 2.0]], np.float32), np.array([[10, 20, 30]], np.uint8))
     out, tap = _render_records(gpu, one, W, H, m, filtered=False)
@@ -370,6 +376,7 @@ def test_distortion_matches_opencv_model(gpu, cpu_oracle):
     E = case.poses[0]
     pc.set_camera(calib, E)
     pix, zb = pc.project_points()
+    rec = pc.download_cloud()
     pc.close()
     xyz = rec[:, :3].astype(np.float64)
     cam = xyz @ E[:3, :3].T + E[:3, 3]
@@ -464,7 +471,7 @@ def test_chunk_culling_pixel_boundary_points(gpu):
     rec = gpu.pack_records(xyz, np.full((len(xyz), 3), 77, np.uint8))
     res = []
     for cull in (1, 0):
-        pc = gpu.ProjectCloud.from_packed(rec)
+        pc = gpu.ProjectCloud.from_packed(rec, sort=False)    # keep the one-chunk-per-border-case layout
         pc.set_option("chunk_cull", cull)
         c = gpu.CameraCalibration()
         c.setWidth(W)
@@ -509,8 +516,9 @@ def test_float_accumulator_overflow_falls_back_to_exact_sums(gpu, cpu_oracle):
                 accum = pc.read("accum", np.uint32, W * H * 4)
                 flag = pc.read("minmax", np.uint32, 3)[2]
                 tap = pc.project_points()
+                resident = pc.download_cloud()
                 pc.close()
-                gold = cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(rec), W, H, filtered=filtered)
+                gold = cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(resident), W, H, filtered=filtered)
                 assert accum.reshape(-1, 4)[:, 3].max() == heavy
                 assert np.array_equal(accum, gold["accum"]) and np.array_equal(color, gold["image"])
                 assert np.array_equal(depth.view(np.uint32), gold["zbuf"])
