@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) clear_kernel(uint32_t* __restrict__ zbuf,
         minmax[0] = 0xFFFFFFFFu;
         minmax[1] = 0u;
         minmax[2] = 0u;  // float-accumulator overflow flag of this frame
+        minmax[3] = 0u;  // grid-barrier counter of exact_fixup_kernel
         if (cull) {  // fold the previous frame's visible-chunk count into the running total, reset for this frame
             cull->total_visible += cull->n_visible;
             cull->frames += (cull->armed ? 1u : 0u);
@@ -242,6 +243,59 @@ __global__ void __launch_bounds__(kPointBlock) blend_list_kernel(const PointReco
                                                               pp, zbuf, accum2);
 }
 
+// ---------------------------------------------------------------- exact re-run after a float-accumulator overflow
+// One launch that almost always returns at once.  When resolve flagged a pixel beyond the exact range of
+// the float sums (minmax[2] != 0) it redoes the frame's colour sums with the integer REDs and resolves
+// again: clear accum -> blend (exact) -> resolve, separated by a grid-wide barrier.  The grid is 2 CTAs
+// per SM, all co-resident, so the spin barrier cannot deadlock (CTAs of the preceding kernel still
+// draining do not depend on this grid; PDL schedules the following kernel only after every CTA here
+// has started).
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+template <bool LIST, bool DISTORT>
+__global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                                  const __grid_constant__ ProjParams pp,
+                                                                  const CullState* __restrict__ cull,
+                                                                  const uint32_t* __restrict__ vis_list,
+                                                                  const uint32_t* __restrict__ zbuf,
+                                                                  uint4* __restrict__ accum, uint64_t n_px,
+                                                                  uint8_t* __restrict__ image, uint64_t cov,
+                                                                  uint32_t* __restrict__ minmax) {
+    pdl_prologue();
+    if (minmax[2] == 0u) return;
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
+    grid_barrier(minmax + 3, gridDim.x);
+    unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
+    if constexpr (LIST) {
+        const uint32_t n_vis = cull->n_visible;
+        for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
+            blend_tile<kChunkPoints / kPointBlock, 0, false>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x, pp, zbuf, a2);
+    } else {
+        const uint64_t n_tiles = (n + kChunkPoints - 1) / kChunkPoints;
+        for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+            blend_tile<kChunkPoints / kPointBlock, 0, DISTORT>(pts, n, t * kChunkPoints + threadIdx.x, pp, zbuf, a2);
+    }
+    grid_barrier(minmax + 3, 2u * gridDim.x);
+    for (uint64_t id = tid; id < cov; id += stride) {  // resolvePass on the integer sums (render.cu:147-162)
+        const uint4 a = __ldcg(accum + id);
+        uint8_t b = 0, g = 0, r = 0;
+        if (a.w != 0u) { b = uint8_t(a.x / a.w); g = uint8_t(a.y / a.w); r = uint8_t(a.z / a.w); }
+        image[id * 3 + 0] = b; image[id * 3 + 1] = g; image[id * 3 + 2] = r;
+    }
+}
+
 // ---------------------------------------------------------------- per-point projection dump (tests)
 // Writes (pix or -1, depth bits) for every point: the "hybrid golden" tap of SURVEY.md §8 c.
 template <bool DISTORT>
@@ -307,6 +361,18 @@ cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const P
         case 4: launch_pdl((blend_list_kernel<4>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate); break;
         default: launch_pdl((blend_list_kernel<6>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate); break;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* pts, uint64_t n, const ProjParams& pp,
+                               const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf, uint32_t* accum,
+                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax) {
+    if (n == 0) return cudaSuccess;
+    const dim3 grid(unsigned(sm_count) * 2u), block(kPointBlock);
+    uint4* a4 = reinterpret_cast<uint4*>(accum);
+    if (cull) launch_pdl((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    else if (pp.distort) launch_pdl((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    else launch_pdl((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
     return cudaGetLastError();
 }
 

@@ -324,13 +324,11 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         r->launches += ((r->W % 16) == 0 && !r->force_generic) ? 1 : (filtered ? 6 : 1);
         if (f32acc) {
             // A pixel that collected more than 65793 points leaves the exact range of the float sums; resolve
-            // raised minmax[2] for it.  These three launches return at once unless that happened, in which
-            // case they redo the colour sums of the frame with the integer REDs and resolve again.
-            RTR_CUDA(r, launch_clear_accum_gated(s, r->sm_count, fb.accum, P, fb.minmax + 2));
-            if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv & ~4, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, fb.minmax + 2));
-            else RTR_CUDA(r, launch_blend(s, bv & ~4, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, fb.minmax + 2));
-            RTR_CUDA(r, launch_resolve_gated(s, fb, r->W, r->H));
-            r->launches += 3;
+            // raised minmax[2] for it.  This launch returns at once unless that happened, in which
+            // case it redoes the colour sums of the frame with the integer REDs and resolve again.
+            RTR_CUDA(r, launch_exact_fixup(s, r->sm_count, r->points, r->n_points, pp, cull ? r->cull_state : nullptr,
+                                           cull ? r->vis_list : nullptr, fb.zbuf, fb.accum, P, fb.image, cov, fb.minmax));
+            r->launches += 1;
         }
     }
     if (r->timing) cudaEventRecord(ev[4], s);
