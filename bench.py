@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--stage", default="filtered", choices=["filtered", "rgbd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-points", type=int, default=20_000_000)
+    ap.add_argument("--nccl", action="store_true", help="--mode points: merge with ncclAllReduce instead of the peer-memory kernels")
     ap.add_argument("--opt", action="append", default=[], help="renderer option key=value (repeatable)")
     return ap.parse_args()
 
@@ -284,16 +285,21 @@ def run_b200(args, wl):
     for kv in args.opt:
         k, v = kv.split("=")
         pc.set_option(k, int(v))
+    calib = make_calib(pkg, W, H, f, cx, cy)
+    pc.set_camera(calib)
     if args.mode == "points":
         pc.set_option("index_base", first)
-        if world > 1:
+        if world > 1 and args.nccl:
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
                 uid.copy_(torch.frombuffer(bytearray(pkg.ProjectCloud.comm_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid, 0)
             pc.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
-    calib = make_calib(pkg, W, H, f, cx, cy)
-    pc.set_camera(calib)
+        elif world > 1:   # our own two-shot all-reduce over NVLink peer memory
+            blob = torch.frombuffer(bytearray(pc.peer_export()), dtype=torch.uint8).cuda()
+            blobs = [torch.zeros(512, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(blobs, blob)
+            pc.peer_attach(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs), rank, world)
     poses = trajectory(pkg, hall, n_poses)
     if args.mode == "frames":   # frame f of the (looping) trajectory goes to rank f mod N (SURVEY.md §8 e)
         my = [poses[(i * world + rank) % len(poses)] for i in range(K_steps + Wm)]
@@ -453,13 +459,18 @@ def run_b200(args, wl):
             "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+u32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {points_per_frame} points, {W}x{H}, stage {args.stage}, {n_poses}-pose trajectory",
-                       "sharding": ("frame-sharded, cloud replicated" if args.mode == "frames" else "point-sharded, NCCL min/sum all-reduce"),
+                       "sharding": ("frame-sharded, cloud replicated" if args.mode == "frames" else
+                                    ("point-sharded, ncclAllReduce min/sum" if args.nccl else "point-sharded, two-shot min/sum all-reduce kernels over NVLink peer memory")),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
                        "options": {k: pc.get_option(k) for k in ("chunk_cull", "zmin_variant", "zmin_unroll", "blend_variant", "blend_unroll", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_baseline(args, (n,) + wl[1:], args.cpu_sample_points)
+    if args.mode == "points" and world > 1 and not args.nccl:
+        line["peer_error"] = pc.get_option("peer_error")
+        dist.barrier()
+        pc.peer_detach()
     pc.close()
     if world > 1:
         dist.barrier()

@@ -157,6 +157,17 @@ int rtr_comm_unique_id(void* id128);
 int rtr_comm_init(rtr_renderer* r, const void* id128, int rank, int n_ranks);
 int rtr_comm_destroy(rtr_renderer* r);
 
+/* The same merge without a library collective: every rank maps the others' frame buffers (CUDA IPC) and one
+ * kernel per buffer does a two-shot all-reduce (min / integer sum) straight over NVLink peer memory, with epoch
+ * flags for the cross-GPU barriers (csrc/rtr_peer.cu).  One process per GPU on one node:
+ *   every rank: set the intrinsics, rtr_peer_export(r, blob)  ->  all-gather the 512-byte blobs by any means
+ *   every rank: rtr_peer_attach(r, all_blobs, rank, n_ranks)  ->  every render call now merges across the ranks.
+ * Resolution changes need detach / export / attach again.  Takes precedence over rtr_comm_init. */
+#define RTR_PEER_BLOB_BYTES 512
+int rtr_peer_export(rtr_renderer* r, void* blob512);
+int rtr_peer_attach(rtr_renderer* r, const void* blobs, int rank, int n_ranks);
+int rtr_peer_detach(rtr_renderer* r);
+
 const char* rtr_version(void);
 
 #if defined(__GNUC__)

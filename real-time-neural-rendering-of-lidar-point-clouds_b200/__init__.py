@@ -68,6 +68,9 @@ API = {
     "rtr_comm_unique_id": (_i, [_vp]),
     "rtr_comm_init": (_i, [_vp, _vp, _i, _i]),
     "rtr_comm_destroy": (_i, [_vp]),
+    "rtr_peer_export": (_i, [_vp, _vp]),
+    "rtr_peer_attach": (_i, [_vp, _vp, _i, _i]),
+    "rtr_peer_detach": (_i, [_vp]),
     "rtr_version": (C.c_char_p, []),
 }
 _ip, _u8pp, _fpp = C.POINTER(_i), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.POINTER(C.c_float))
@@ -366,6 +369,19 @@ class ProjectCloud:
     def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self._lib.rtr_comm_init(self._h, buf, rank, n_ranks))
+
+    def peer_export(self) -> bytes:
+        """512-byte blob describing this renderer's frame buffers (intrinsics must be set); all-gather them."""
+        buf = C.create_string_buffer(512)
+        self._check(self._lib.rtr_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, blobs: bytes, rank: int, n_ranks: int):
+        assert len(blobs) == 512 * n_ranks
+        self._check(self._lib.rtr_peer_attach(self._h, C.create_string_buffer(blobs, len(blobs)), rank, n_ranks))
+
+    def peer_detach(self):
+        self._check(self._lib.rtr_peer_detach(self._h))
 
     @staticmethod
     def comm_unique_id() -> bytes:

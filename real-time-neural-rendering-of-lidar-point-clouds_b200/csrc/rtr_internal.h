@@ -57,6 +57,18 @@ struct rtr_renderer {
     double ev_sum[6] = {0, 0, 0, 0, 0, 0};
     uint64_t ev_count = 0;
     uint64_t launches = 0;
+    // point-sharded merge over peer memory (rtr_peer.cu): device pointers of every rank's buffers
+    struct Peer {
+        bool attached = false;
+        int rank = 0, n = 1;
+        uint32_t* flags = nullptr;           // local flag array + [64] local barrier counter + [65] error word
+        uint32_t* peer_flags[rtr::kMaxPeers] = {nullptr};
+        uint32_t* peer_zbuf[2][rtr::kMaxPeers] = {{nullptr}};
+        uint32_t* peer_accum[2][rtr::kMaxPeers] = {{nullptr}};
+        std::vector<void*> opened;           // cudaIpcOpenMemHandle results to close
+        uint32_t epoch = 1, local_base = 0;
+        int W = 0, H = 0;
+    } peer;
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1;

@@ -123,6 +123,21 @@ cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey,
 // up-pass: laplacian + compare (+ resize | + removeMask) per level, 4 launches.
 cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool force_generic);
 
+// ---- point-sharded merge over peer memory (rtr_peer.cu)
+constexpr int kMaxPeers = 16;
+struct PeerMergeParams {
+    uint4* buf[kMaxPeers];       // the buffer to all-reduce on every rank (peer-mapped; [rank] is the local one)
+    uint32_t* flags[kMaxPeers];  // every rank's flag array: flags[p][s] = last epoch rank s signalled to rank p
+    int rank, n_ranks;
+    uint64_t n_vec;              // 16-byte elements in the buffer
+    uint32_t epoch;              // this launch uses epoch, epoch + 1, epoch + 2
+    uint32_t* local_bar;         // local grid-barrier counter (grows by 2 * gridDim.x per launch)
+    uint32_t local_base;         // its value before this launch
+    uint32_t* err;               // raised when a wait timed out
+};
+// op 0: min of u32, op 1: sum of u32.  Grid = 2 CTAs per SM (co-resident, see kernel).
+cudaError_t launch_peer_allreduce(cudaStream_t s, int sm_count, int op, const PeerMergeParams& pm);
+
 // ---- synthetic cloud on the device (rtr_synth.cu; bench/test support, same generator as the oracle)
 cudaError_t launch_synth(cudaStream_t s, uint64_t seed, uint64_t n_total, uint64_t first, uint64_t count, int lx,
                          int ly, int lz, int nbox, PointRecord* out);

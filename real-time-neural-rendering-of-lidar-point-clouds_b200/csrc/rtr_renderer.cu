@@ -233,8 +233,35 @@ int drain_event_pool(rtr_renderer* r) {
     return RTR_OK;
 }
 
+// Two-shot all-reduce of one frame buffer over the peers' memory (rtr_peer.cu).
+int peer_merge(rtr_renderer* r, int si, bool accum, int op) {
+    rtr_renderer::Peer& pe = r->peer;
+    const uint64_t P = uint64_t(r->W) * r->H;
+    PeerMergeParams pm;
+    std::memset(&pm, 0, sizeof(pm));
+    for (int p = 0; p < pe.n; ++p) {
+        pm.buf[p] = reinterpret_cast<uint4*>(accum ? pe.peer_accum[si][p] : pe.peer_zbuf[si][p]);
+        pm.flags[p] = pe.peer_flags[p];
+    }
+    pm.rank = pe.rank;
+    pm.n_ranks = pe.n;
+    pm.n_vec = accum ? P : P / 4;
+    pm.epoch = pe.epoch;
+    pm.local_bar = pe.flags + 64;
+    pm.local_base = pe.local_base;
+    pm.err = pe.flags + 65;
+    pe.epoch += 3;
+    pe.local_base += 2u * unsigned(r->sm_count) * 2u;
+    RTR_CUDA(r, launch_peer_allreduce(r->stream, r->sm_count, op, pm));
+    r->launches += 1;
+    return RTR_OK;
+}
+
 // Enqueue one frame on r->stream into frame set `si`.
 int enqueue_frame(rtr_renderer* r, int stage, int si) {
+    const bool peer = r->peer.attached;
+    if (peer && (r->peer.W != r->W || r->peer.H != r->H)) return fail(r, RTR_ERR_STATE, "resolution changed while peers are attached: rtr_peer_detach first");
+    if (peer && r->key64) return fail(r, RTR_ERR_UNSUPPORTED, "key64 mode merges through rtr_comm_init (NCCL), not rtr_peer_attach");
     if (!r->points || r->n_points == 0) return fail(r, RTR_ERR_STATE, "no cloud uploaded");
     ProjParams pp;
     int rc = make_params(r, pp);
@@ -303,19 +330,23 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, nullptr));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
         r->launches += 1;
-        if (r->comm) {
+        if (peer) {
+            if ((rc = peer_merge(r, si, false, 0)) != RTR_OK) return rc;
+        } else if (r->comm) {
             rc = comm_allreduce(r, fb.zbuf, fb.zbuf, P, ncclUint32_, ncclMin_);
             if (rc != RTR_OK) return rc;
         }
         if (r->timing) cudaEventRecord(ev[2], s);
         // float accumulators (one 16-byte RED per point) unless the sums must be all-reduced as integers
-        const int bv = r->comm ? (r->blend_variant & ~4) : r->blend_variant;
+        const int bv = (r->comm || peer) ? (r->blend_variant & ~4) : r->blend_variant;
         const bool f32acc = (bv & 4) != 0;
         fs.f32acc = f32acc;
         if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, nullptr));
         else RTR_CUDA(r, launch_blend(s, bv, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, nullptr));
         r->launches += 1;
-        if (r->comm) {
+        if (peer) {
+            if ((rc = peer_merge(r, si, true, 1)) != RTR_OK) return rc;
+        } else if (r->comm) {
             rc = comm_allreduce(r, fb.accum, fb.accum, P * 4, ncclUint32_, ncclSum_);
             if (rc != RTR_OK) return rc;
         }
@@ -407,6 +438,8 @@ void rtr_destroy(rtr_renderer* r) {
     cudaStreamSynchronize(r->stream);
     cudaStreamSynchronize(r->copy_stream);
     if (r->comm) g_nccl.CommDestroy(r->comm);
+    rtr_peer_detach(r);
+    cudaFree(r->peer.flags);
     free_frame_sets(r);
     if (r->owns_points) cudaFree(r->points);
     cudaFree(r->bounds); cudaFree(r->vis_list); cudaFree(r->cull_state);
@@ -790,6 +823,11 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
     if (!r || !key) return RTR_ERR_ARG;
     if (!std::strcmp(key, "index_base")) return int64_t(r->index_base);
     if (!std::strcmp(key, "sm_count")) return r->sm_count;
+    if (!std::strcmp(key, "peer_error")) {  // 1 when a cross-GPU wait of the peer merge timed out
+        uint32_t v = 0;
+        if (r->peer.flags) { cudaSetDevice(r->device); cudaStreamSynchronize(r->stream); cudaMemcpy(&v, r->peer.flags + 65, 4, cudaMemcpyDeviceToHost); }
+        return v;
+    }
     const int* slot = option_slot(const_cast<rtr_renderer*>(r), key);
     return slot ? *slot : RTR_ERR_ARG;
 }
@@ -859,6 +897,87 @@ int rtr_comm_init(rtr_renderer* r, const void* id128, int rank, int n_ranks) {
     const int rc = g_nccl.CommInitRank(&r->comm, n_ranks, id, rank);
     if (rc != 0) { r->comm = nullptr; return fail(r, RTR_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); }
     r->rank = rank; r->n_ranks = n_ranks;
+    return RTR_OK;
+}
+
+namespace {
+struct PeerBlob {
+    uint32_t magic;
+    int32_t W, H;
+    cudaIpcMemHandle_t flags, zbuf[2], accum[2];
+};
+static_assert(sizeof(PeerBlob) <= 512, "blob must fit RTR_PEER_BLOB_BYTES");
+}  // namespace
+
+int rtr_peer_export(rtr_renderer* r, void* blob512) {
+    if (!r || !blob512) return RTR_ERR_ARG;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    if (r->W < 16 || r->H < 16) return fail(r, RTR_ERR_STATE, "set the intrinsics before rtr_peer_export");
+    if ((uint64_t(r->W) * r->H) % 4) return fail(r, RTR_ERR_UNSUPPORTED, "peer merge needs W*H divisible by 4");
+    int rc = ensure_buffers(r);
+    if (rc != RTR_OK) return rc;
+    if (!r->peer.flags) {
+        RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->peer.flags), 4096));
+        RTR_CUDA(r, cudaMemset(r->peer.flags, 0, 4096));
+    }
+    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    PeerBlob b;
+    std::memset(&b, 0, sizeof(b));
+    b.magic = 0x52545250u;
+    b.W = r->W; b.H = r->H;
+    RTR_CUDA(r, cudaIpcGetMemHandle(&b.flags, r->peer.flags));
+    for (int i = 0; i < 2; ++i) {
+        RTR_CUDA(r, cudaIpcGetMemHandle(&b.zbuf[i], r->set[i].fb.zbuf));
+        RTR_CUDA(r, cudaIpcGetMemHandle(&b.accum[i], r->set[i].fb.accum));
+    }
+    std::memset(blob512, 0, 512);
+    std::memcpy(blob512, &b, sizeof(b));
+    return RTR_OK;
+}
+
+int rtr_peer_detach(rtr_renderer* r) {
+    if (!r) return RTR_ERR_ARG;
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    for (void* p : r->peer.opened) cudaIpcCloseMemHandle(p);
+    r->peer.opened.clear();
+    r->peer.attached = false;
+    return RTR_OK;
+}
+
+int rtr_peer_attach(rtr_renderer* r, const void* blobs, int rank, int n_ranks) {
+    if (!r || !blobs || n_ranks < 1 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks) return RTR_ERR_ARG;
+    if (!r->peer.flags) return fail(r, RTR_ERR_STATE, "call rtr_peer_export first");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    rtr_peer_detach(r);
+    rtr_renderer::Peer& pe = r->peer;
+    for (int p = 0; p < n_ranks; ++p) {
+        PeerBlob b;
+        std::memcpy(&b, static_cast<const char*>(blobs) + size_t(p) * 512, sizeof(b));
+        if (b.magic != 0x52545250u) return fail(r, RTR_ERR_ARG, "bad peer blob");
+        if (b.W != r->W || b.H != r->H) return fail(r, RTR_ERR_ARG, "peers render different resolutions");
+        if (p == rank) {
+            pe.peer_flags[p] = pe.flags;
+            for (int i = 0; i < 2; ++i) { pe.peer_zbuf[i][p] = r->set[i].fb.zbuf; pe.peer_accum[i][p] = r->set[i].fb.accum; }
+            continue;
+        }
+        auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> cudaError_t {
+            cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) pe.opened.push_back(*out);
+            return e;
+        };
+        void* q = nullptr;
+        RTR_CUDA(r, open(b.flags, &q));
+        pe.peer_flags[p] = static_cast<uint32_t*>(q);
+        for (int i = 0; i < 2; ++i) {
+            RTR_CUDA(r, open(b.zbuf[i], &q));
+            pe.peer_zbuf[i][p] = static_cast<uint32_t*>(q);
+            RTR_CUDA(r, open(b.accum[i], &q));
+            pe.peer_accum[i][p] = static_cast<uint32_t*>(q);
+        }
+    }
+    pe.rank = rank; pe.n = n_ranks; pe.W = r->W; pe.H = r->H;
+    pe.attached = n_ranks > 1;
     return RTR_OK;
 }
 

@@ -69,6 +69,33 @@ def main():
                 print(f"[rank {rank}] point-sharded key64={key64}: frame differs from the single-GPU frame", flush=True)
             ok &= same
     shard.close()
+    # ---- point-sharded, merged by our own two-shot all-reduce over NVLink peer memory (no library collective)
+    peer = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, first=first, count=count, hall=case.hall, n_boxes=case.n_boxes, device=local)
+    peer.set_camera(calib)
+    blob = torch.frombuffer(bytearray(peer.peer_export()), dtype=torch.uint8).cuda()
+    blobs = [torch.zeros(512, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(blobs, blob)
+    peer.peer_attach(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs), rank, world)
+    for rep_i in range(3):   # several frames: the epoch flags must keep working
+        for E in case.poses:
+            got = frame(peer, pkg, calib, E, P)
+            dig = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in got)).digest()
+            t = torch.frombuffer(bytearray(dig), dtype=torch.uint8).cuda()
+            if rank == 0:
+                full.set_option("key64", 0)
+                want = frame(full, pkg, calib, E, P)
+                t = torch.frombuffer(bytearray(hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in want)).digest()), dtype=torch.uint8).cuda()
+            dist.broadcast(t, 0)
+            same = bytes(t.cpu().numpy().tobytes()) == dig
+            if not same:
+                print(f"[rank {rank}] peer merge: frame differs from the single-GPU frame", flush=True)
+            ok &= same
+    if peer.get_option("peer_error") != 0:
+        print(f"[rank {rank}] peer merge: a cross-GPU wait timed out", flush=True)
+        ok = False
+    dist.barrier()
+    peer.peer_detach()
+    peer.close()
     # ---- frame-sharded
     poses = pkg.trajectory_w2c(11, center=(6.0, 5.0, 1.5), radius=2.0)
     rep = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local, sort=SORT)
