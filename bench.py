@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--stage", default="filtered", choices=["filtered", "rgbd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-points", type=int, default=20_000_000)
+    ap.add_argument("--distort", action="store_true", help="apply config 2's k1,k2,p1,p2,k3 = (-0.05, 0.01, 0.0005, -0.0005, 0) (new feature, no reference parity)")
     ap.add_argument("--nccl", action="store_true", help="--mode points: merge with ncclAllReduce instead of the peer-memory kernels")
     ap.add_argument("--opt", action="append", default=[], help="renderer option key=value (repeatable)")
     return ap.parse_args()
@@ -270,7 +271,10 @@ def run_b200(args, wl):
     # pinned HOST memory, and then uploaded through the public C-ABI call, so the renderer's cloud
     # really arrives from the host the way the reference's constructor receives it.
     if args.mode == "points":
-        n_total, first, count = n * world, n * rank, n
+        # every rank holds an independent n-point scan of the WHOLE hall (seed + rank): the union is the N*n-point cloud
+        # and every shard covers the scene uniformly, so the ranks' per-frame work is balanced (a contiguous index range
+        # of one cloud would give one rank the floor and another the ceiling)
+        n_total, first, count, seed = n, 0, n, seed + rank
     else:
         n_total, first, count = n, 0, n
     gen = pkg.ProjectCloud.synthetic(seed=seed, n_total=n_total, first=first, count=count, hall=hall, n_boxes=boxes, device=local)
@@ -286,9 +290,12 @@ def run_b200(args, wl):
         k, v = kv.split("=")
         pc.set_option(k, int(v))
     calib = make_calib(pkg, W, H, f, cx, cy)
+    if args.distort:
+        calib.setDistortionParameters([-0.05, 0.01, 0.0005, -0.0005, 0.0])
+        pc.apply_distortion = True
     pc.set_camera(calib)
     if args.mode == "points":
-        pc.set_option("index_base", first)
+        pc.set_option("index_base", n * rank)
         if world > 1 and args.nccl:
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
@@ -462,6 +469,7 @@ def run_b200(args, wl):
                        "sharding": ("frame-sharded, cloud replicated" if args.mode == "frames" else
                                     ("point-sharded, ncclAllReduce min/sum" if args.nccl else "point-sharded, two-shot min/sum all-reduce kernels over NVLink peer memory")),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
+                       "distortion": bool(args.distort),
                        "options": {k: pc.get_option(k) for k in ("chunk_cull", "zmin_variant", "zmin_unroll", "blend_variant", "blend_unroll", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}

@@ -109,3 +109,25 @@ def test_unet_output_postprocess(gpu):
     with np.errstate(invalid="ignore"):
         want = np.clip(np.nan_to_num(np.rint(v), nan=0.0, posinf=255, neginf=0), 0, 255).astype(np.uint8)
     assert np.array_equal(got, want.transpose(1, 2, 0))
+
+
+def test_config1_ply_file_to_reference_frame(gpu, cpu_oracle, tmp_path):
+    """BASELINE config 1 end to end: a 1 M-point coloured .ply, one 640x480 pinhole pose, projection + z-buffer +
+    prefilter — loaded through the PLY loader (binned like the reference's loader), the frame must equal what the
+    unmodified reference produced for that cloud and pose (golden c1_640x480)."""
+    import os
+    from conftest import ROOT
+    case = scenes.CASES["c1_640x480"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", case.name + ".npz"))
+    rec = cpu_oracle.synth_packed(case.seed, case.n, 0, case.n, case.hall, case.n_boxes)
+    xyz, bgr = scenes.split_records(rec)
+    path = str(tmp_path / "c1.ply")
+    gpu.write_ply(path, xyz, bgr)
+    assert os.path.getsize(path) > 15 * case.n
+    for kw in (dict(bin_cells=True), dict(bin_cells=False)):
+        pc = gpu.ProjectCloud.from_ply(path, **kw)
+        color, depth, tensor = _frame(gpu, pc, case)
+        pc.close()
+        assert scenes.sha(depth) == bytes(g["f0_flt_depth_host_sha"]).decode()
+        assert scenes.sha(color) == bytes(g["f0_flt_color_host_sha"]).decode()
+        assert scenes.sha(tensor) == bytes(g["f0_flt_tensor_sha"]).decode()
