@@ -69,6 +69,9 @@ struct rtr_renderer {
         uint32_t epoch = 1, local_base = 0;
         int W = 0, H = 0;
     } peer;
+    // persistent scratch of rtr_postprocess_unet_output (no per-call cudaMalloc/cudaFree)
+    uint8_t* post_scratch = nullptr;
+    size_t post_scratch_bytes = 0;
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1;

@@ -559,10 +559,15 @@ int rtr_postprocess_unet_output(rtr_renderer* r, const void* device_fp16_chw, in
     IO_CUDA(r, cudaSetDevice(r->device));
     const uint64_t n_px = uint64_t(width) * height;
     uint8_t* out = device_hwc;
-    uint8_t* scratch = nullptr;
     if (!out) {
-        IO_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&scratch), n_px * 3));
-        out = scratch;
+        if (r->post_scratch_bytes < n_px * 3) {
+            cudaFree(r->post_scratch);
+            r->post_scratch = nullptr;
+            r->post_scratch_bytes = 0;
+            IO_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->post_scratch), n_px * 3));
+            r->post_scratch_bytes = n_px * 3;
+        }
+        out = r->post_scratch;
     }
     unet_post_kernel<<<unsigned((n_px + 255) / 256), 256, 0, r->stream>>>(static_cast<const __half*>(device_fp16_chw), n_px, out);
     r->launches += 1;
@@ -571,7 +576,6 @@ int rtr_postprocess_unet_output(rtr_renderer* r, const void* device_fp16_chw, in
         e = cudaMemcpyAsync(host_hwc, out, n_px * 3, cudaMemcpyDeviceToHost, r->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
     }
-    if (scratch) { cudaStreamSynchronize(r->stream); cudaFree(scratch); }
     if (e != cudaSuccess) return renderer_fail(r, RTR_ERR_CUDA, std::string("rtr_postprocess_unet_output: ") + cudaGetErrorString(e));
     return RTR_OK;
 }

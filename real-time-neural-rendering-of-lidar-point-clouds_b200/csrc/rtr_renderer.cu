@@ -440,6 +440,7 @@ void rtr_destroy(rtr_renderer* r) {
     if (r->comm) g_nccl.CommDestroy(r->comm);
     rtr_peer_detach(r);
     cudaFree(r->peer.flags);
+    cudaFree(r->post_scratch);
     free_frame_sets(r);
     if (r->owns_points) cudaFree(r->points);
     cudaFree(r->bounds); cudaFree(r->vis_list); cudaFree(r->cull_state);
