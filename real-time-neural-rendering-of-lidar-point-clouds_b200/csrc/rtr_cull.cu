@@ -96,51 +96,76 @@ __device__ __forceinline__ double row_err(const double f[4], const double mabs[3
     return 9.5367431640625e-7 * (fabs(f[0]) * mabs[0] + fabs(f[1]) * mabs[1] + fabs(f[2]) * mabs[2] + fabs(f[3]));
 }
 
-__global__ void __launch_bounds__(256) classify_chunks_kernel(const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
-                                                              const __grid_constant__ CullParams cp,
-                                                              uint32_t* __restrict__ vis_list,
-                                                              CullState* __restrict__ cull) {
+// true unless the whole box provably fails the reference's per-point test (see file header)
+__device__ __forceinline__ bool chunk_visible(const ChunkBounds& b, const CullParams& cp) {
+    if (b.always_visible) return true;
+    const double lo[3] = {b.lo[0], b.lo[1], b.lo[2]}, hi[3] = {b.hi[0], b.hi[1], b.hi[2]};
+    const double mabs[3] = {fmax(fabs(lo[0]), fabs(hi[0])), fmax(fabs(lo[1]), fabs(hi[1])), fmax(fabs(lo[2]), fabs(hi[2]))};
+    const double ex = row_err(cp.r0, mabs), ey = row_err(cp.r1, mabs), ez = row_err(cp.r2, mabs);
+    const bool sane = (ex < 1e30) & (ey < 1e30) & (ez < 1e30);  // false for NaN / inf / absurd matrices
+    if (!sane) return true;
+    const double cl = 1.5, cr = cp.W + 0.5, cb = cp.H + 0.5;
+    double f[4];
+    bool cut = box_range(cp.r2, lo, hi).hi + ez < 0.0;  // behind
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] + cl * cp.r2[k];
+    cut = cut || (box_range(f, lo, hi).hi + (ex + cl * ez) < 0.0);  // left
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] - cr * cp.r2[k];
+    cut = cut || (box_range(f, lo, hi).lo - (ex + cr * ez) > 0.0);  // right
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] + cl * cp.r2[k];
+    cut = cut || (box_range(f, lo, hi).hi + (ey + cl * ez) < 0.0);  // top
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] - cb * cp.r2[k];
+    cut = cut || (box_range(f, lo, hi).lo - (ey + cb * ez) > 0.0);  // bottom
+    return !cut;
+}
+
+// One launch per frame: fillBuffer + cudaMemset (render.cu:16-31, project_cloud.cu:316-317) and the chunk
+// classification.  The visible-chunk counter is double-buffered by frame parity so that the reset of one counter
+// and the atomic appends to the other need no ordering inside the launch.
+__global__ void __launch_bounds__(256) clear_classify_kernel(uint32_t* __restrict__ zbuf, uint64_t cov,
+                                                             uint4* __restrict__ accum, uint64_t n_px,
+                                                             uint32_t* __restrict__ minmax,
+                                                             const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
+                                                             const __grid_constant__ CullParams cp,
+                                                             uint32_t* __restrict__ vis_list, CullState* __restrict__ cull,
+                                                             uint32_t parity) {
     pdl_prologue();
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    bool visible = false;
-    if (c < n_chunks) {
-        const ChunkBounds b = bounds[c];
-        visible = true;
-        if (!b.always_visible) {
-            const double lo[3] = {b.lo[0], b.lo[1], b.lo[2]}, hi[3] = {b.hi[0], b.hi[1], b.hi[2]};
-            const double mabs[3] = {fmax(fabs(lo[0]), fabs(hi[0])), fmax(fabs(lo[1]), fabs(hi[1])), fmax(fabs(lo[2]), fabs(hi[2]))};
-            const double ex = row_err(cp.r0, mabs), ey = row_err(cp.r1, mabs), ez = row_err(cp.r2, mabs);
-            const bool sane = (ex < 1e30) & (ey < 1e30) & (ez < 1e30);  // false for NaN / inf / absurd matrices
-            if (sane) {
-                const double cl = 1.5, cr = cp.W + 0.5, cb = cp.H + 0.5;
-                double f[4];
-                bool cut = box_range(cp.r2, lo, hi).hi + ez < 0.0;  // behind
-#pragma unroll
-                for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] + cl * cp.r2[k];
-                cut = cut || (box_range(f, lo, hi).hi + (ex + cl * ez) < 0.0);  // left
-#pragma unroll
-                for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] - cr * cp.r2[k];
-                cut = cut || (box_range(f, lo, hi).lo - (ex + cr * ez) > 0.0);  // right
-#pragma unroll
-                for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] + cl * cp.r2[k];
-                cut = cut || (box_range(f, lo, hi).hi + (ey + cl * ez) < 0.0);  // top
-#pragma unroll
-                for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] - cb * cp.r2[k];
-                cut = cut || (box_range(f, lo, hi).lo - (ey + cb * ez) > 0.0);  // bottom
-                visible = !cut;
-            }
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    if (tid == 0) {
+        minmax[0] = 0xFFFFFFFFu;
+        minmax[1] = 0u;
+        minmax[2] = 0u;  // float-accumulator overflow flag of this frame
+        minmax[3] = 0u;  // grid-barrier counter of exact_fixup_kernel
+        // fold the previous culled frame into the running totals, hand its counter over to the next frame
+        if (cull->armed) { cull->total_visible += cull->n_visible[parity ^ 1u]; cull->frames += 1u; }
+        cull->n_visible[parity ^ 1u] = 0u;
+        cull->parity = parity;
+        cull->armed = 1u;
+    }
+    // ---- classification first (its appends are what the next kernel waits for), whole warps at a time
+    const uint32_t n_round = (n_chunks + 31u) & ~31u;
+    for (uint64_t c = tid; c < n_round; c += stride) {
+        const bool visible = c < n_chunks && chunk_visible(bounds[c], cp);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, visible);
+        if (m) {
+            const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&cull->n_visible[parity], uint32_t(__popc(m)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (visible) vis_list[base + __popc(m & ((1u << lane) - 1u))] = uint32_t(c);
         }
     }
-    // warp-aggregated append
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, visible);
-    if (m) {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&cull->n_visible, uint32_t(__popc(m)));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (visible) vis_list[base + __popc(m & ((1u << lane) - 1u))] = c;
-    }
-    if (c == 0) cull->armed = 1u;
+    // ---- clear
+    for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
+    const uint64_t cov4 = cov >> 2;
+    uint4* z4 = reinterpret_cast<uint4*>(zbuf);
+    for (uint64_t i = tid; i < cov4; i += stride)
+        z4[i] = make_uint4(kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits);
+    for (uint64_t i = (cov4 << 2) + tid; i < cov; i += stride) zbuf[i] = kEmptyDepthBits;
 }
 
 cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds) {
@@ -149,10 +174,11 @@ cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_classify_chunks(cudaStream_t s, const ChunkBounds* bounds, uint32_t n_chunks, const CullParams& cp,
-                                   uint32_t* vis_list, CullState* cull) {
-    if (n_chunks == 0) return cudaSuccess;
-    launch_pdl(classify_chunks_kernel, dim3((n_chunks + 255) / 256), dim3(256), s, bounds, n_chunks, cp, vis_list, cull);
+cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum,
+                                  uint64_t n_px, uint32_t* minmax, const ChunkBounds* bounds, uint32_t n_chunks,
+                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity) {
+    launch_pdl(clear_classify_kernel, dim3(sm_count * 8), dim3(256), s, zbuf, cov, reinterpret_cast<uint4*>(accum), n_px, minmax,
+               bounds, n_chunks, cp, vis_list, cull, parity);
     return cudaGetLastError();
 }
 

@@ -297,6 +297,125 @@ __global__ void __launch_bounds__(256) up_level_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- final level, 8 fine pixels per thread
+// Same arithmetic as up_level_kernel<true>; a thread owns the 8 fine pixels of row hy under 4 adjacent coarse
+// pixels, so depth / tensor planes move as 16-byte vectors and the image as three 8-byte words, and the 3x3 coarse
+// neighbourhoods of the four parents share one 3x6 window.  Needs lw % 4 == 0 (true whenever W % 16 == 0).
+__global__ void __launch_bounds__(256) up_final_wide_kernel(const float* __restrict__ lo, int lw, int lh,
+                                                            float* __restrict__ hi, uint8_t* __restrict__ mask_tap,
+                                                            uint8_t* __restrict__ image, uint16_t* __restrict__ tensor,
+                                                            const uint32_t* __restrict__ minmax) {
+    pdl_prologue();
+    const int groups = lw >> 2, hh = lh * 2, hw = lw * 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= groups * hh) return;
+    const int g = t % groups, hy = t / groups, ly = hy >> 1, lx0 = g * 4;
+    const size_t idx = size_t(hy) * hw + size_t(lx0) * 2;
+    const float4 c0 = *reinterpret_cast<const float4*>(hi + idx), c1 = *reinterpret_cast<const float4*>(hi + idx + 4);
+    const float cur[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float thr = __uint_as_float(kMaxFloatThresholdBits);
+    bool keep[8];
+    bool any_cand = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { keep[j] = !(cur[j] >= thr); any_cand |= keep[j]; }  // candidates so far
+    if (any_cand) {
+        // 3 x 6 window of the coarse level around the four parents (clamped loads; out-of-range entries are never used
+        // by an interior parent, and border parents do not use the window at all)
+        float w[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int y = min(max(ly + r - 1, 0), lh - 1);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) w[r][c] = lo[y * lw + min(max(lx0 + c - 1, 0), lw - 1)];
+        }
+        const bool row_border = (ly == 0 || ly == lh - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lx = lx0 + k;
+            if (!(keep[2 * k] || keep[2 * k + 1])) continue;
+            const bool border = row_border || lx == 0 || lx == lw - 1;
+            bool edge = false;
+            if (!border) {
+                float sum = 0.0f;  // nine chained FMAs, k row-major, zero-weight taps included (laplacianKernel as compiled)
+                sum = __fmaf_rn(w[0][k], 0.0f, sum);
+                sum = __fmaf_rn(w[0][k + 1], 1.0f, sum);
+                sum = __fmaf_rn(w[0][k + 2], 0.0f, sum);
+                sum = __fmaf_rn(w[1][k], 1.0f, sum);
+                sum = __fmaf_rn(w[1][k + 1], -4.0f, sum);
+                sum = __fmaf_rn(w[1][k + 2], 1.0f, sum);
+                sum = __fmaf_rn(w[2][k], 0.0f, sum);
+                sum = __fmaf_rn(w[2][k + 1], 1.0f, sum);
+                sum = __fmaf_rn(w[2][k + 2], 0.0f, sum);
+                edge = sum > kGradientFilter;
+            }
+            bool k0 = false, k1 = false;
+            if (edge) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float lim = __fmul_rn(w[r][k + c], kFilterStrength);
+                        k0 = k0 || (cur[2 * k] <= lim);
+                        k1 = k1 || (cur[2 * k + 1] <= lim);
+                    }
+            } else {
+                const float lim = __fmul_rn(w[1][k + 1], kFilterStrength);
+                k0 = cur[2 * k] <= lim;
+                k1 = cur[2 * k + 1] <= lim;
+            }
+            keep[2 * k] = keep[2 * k] && k0;
+            keep[2 * k + 1] = keep[2 * k + 1] && k1;
+        }
+    }
+    if (mask_tap) {
+        uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { m0 |= keep[j] ? (0xFFu << (8 * j)) : 0u; m1 |= keep[4 + j] ? (0xFFu << (8 * j)) : 0u; }
+        *reinterpret_cast<uint2*>(mask_tap + idx) = make_uint2(m0, m1);
+    }
+    // removeMask (project_cloud.cu:163-187)
+    const size_t plane = size_t(hw) * hh;
+    const float dmin = __uint_as_float(minmax[0]), dmax = __uint_as_float(minmax[1]);
+    const float range = __fsub_rn(dmax, dmin);
+    uint2* img8 = reinterpret_cast<uint2*>(image + idx * 3);  // idx % 8 == 0 -> 24-byte group, 8-byte aligned
+    uint2 iw[3] = {img8[0], img8[1], img8[2]};
+    uint8_t* c = reinterpret_cast<uint8_t*>(iw);
+    uint16_t tp[5][8];
+    float dout[8];
+    bool all_keep = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        dout[j] = cur[j];
+        if (!keep[j]) {
+            all_keep = false;
+            dout[j] = -1.0f;
+            c[3 * j] = c[3 * j + 1] = c[3 * j + 2] = 0;
+            tp[0][j] = tp[1][j] = tp[2][j] = tp[3][j] = 0;
+            tp[4][j] = 0xBC00u;  // -1.0h
+        } else {
+            tp[0][j] = half_div(float(c[3 * j + 0]), 255.0f);
+            tp[1][j] = half_div(float(c[3 * j + 1]), 255.0f);
+            tp[2][j] = half_div(float(c[3 * j + 2]), 255.0f);
+            tp[3][j] = half_div(255.0f, 255.0f);
+            tp[4][j] = half_div(__fsub_rn(cur[j], dmin), range);
+        }
+    }
+    if (!all_keep) {
+        *reinterpret_cast<float4*>(hi + idx) = make_float4(dout[0], dout[1], dout[2], dout[3]);
+        *reinterpret_cast<float4*>(hi + idx + 4) = make_float4(dout[4], dout[5], dout[6], dout[7]);
+        img8[0] = iw[0]; img8[1] = iw[1]; img8[2] = iw[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        uint4 v;
+        v.x = uint32_t(tp[k][0]) | (uint32_t(tp[k][1]) << 16);
+        v.y = uint32_t(tp[k][2]) | (uint32_t(tp[k][3]) << 16);
+        v.z = uint32_t(tp[k][4]) | (uint32_t(tp[k][5]) << 16);
+        v.w = uint32_t(tp[k][6]) | (uint32_t(tp[k][7]) << 16);
+        *reinterpret_cast<uint4*>(tensor + plane * k + idx) = v;
+    }
+}
+
 // ---------------------------------------------------------------- launchers
 cudaError_t launch_resolve_gated(cudaStream_t s, const FrameBuffers& fb, int W, int H) {
     const uint64_t cov = clear_coverage(W, H);
@@ -367,12 +486,16 @@ cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey,
     return cudaGetLastError();
 }
 
-cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool /*force_generic*/) {
+cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool force_generic) {
     for (int i = 4; i >= 1; --i) {
         const int pairs = d.uw[i] * d.uh[i] * 2;  // fine pixels / 2
         if (pairs == 0) continue;
         const unsigned grid = (pairs + 255) / 256;
-        if (i > 1)
+        // tensor plane stride (uw[0]*uh[0]) must keep the 16-byte stores aligned: multiples of 8 halfs
+        const bool wide = i == 1 && !force_generic && (d.uw[1] % 4) == 0 && ((size_t(d.uw[0]) * d.uh[0]) % 8) == 0;
+        if (wide)
+            launch_pdl(up_final_wide_kernel, dim3((d.uw[1] / 4 * d.uh[1] * 2 + 255) / 256), dim3(256), s, fb.level[1], d.uw[1], d.uh[1], fb.level[0], fb.mask[0], fb.image, fb.tensor, fb.minmax);
+        else if (i > 1)
             launch_pdl((up_level_kernel<false>), dim3(grid), dim3(256), s, fb.level[i], d.uw[i], d.uh[i], fb.level[i - 1], fb.mask[i - 1], nullptr, nullptr, fb.minmax);
         else
             launch_pdl((up_level_kernel<true>), dim3(grid), dim3(256), s, fb.level[1], d.uw[1], d.uh[1], fb.level[0], fb.mask[0], fb.image, fb.tensor, fb.minmax);

@@ -34,6 +34,7 @@ struct rtr_renderer {
     uint32_t* vis_list = nullptr;
     rtr::CullState* cull_state = nullptr;
     uint32_t n_chunks = 0;
+    uint32_t cull_parity = 0;  // alternates per culled frame (CullState::n_visible double buffer)
     // camera
     int W = 0, H = 0;
     double K[9] = {0};

@@ -20,12 +20,15 @@ struct ChunkBounds {
 };
 // Per-renderer culling state in device memory.
 struct CullState {
-    uint32_t n_visible;            // chunks in vis_list for the frame being rendered
-    uint32_t armed;                // set by classify, cleared when the count is folded into the totals
+    uint32_t n_visible[2];         // [parity]: chunks in vis_list for the frame being rendered; [parity ^ 1] is
+                                   // zeroed meanwhile for the next frame (classification shares a launch with the clear)
+    uint32_t parity;               // which counter the frame in flight uses (written by clear_classify_kernel)
+    uint32_t armed;                // a classified frame has not been folded into the totals yet
     uint32_t frames;               // frames folded into total_visible
     uint32_t pad;
     unsigned long long total_visible;
 };
+__host__ __device__ inline uint32_t cull_count(const CullState* c) { return c->n_visible[c->parity & 1u]; }
 // The frame's camera for the chunk test, in double (exact images of the float camProj rows).
 struct CullParams {
     double r0[4], r1[4], r2[4];
@@ -82,8 +85,10 @@ cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const P
 
 // ---- chunk-level frustum culling (rtr_cull.cu)
 cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds);
-cudaError_t launch_classify_chunks(cudaStream_t s, const ChunkBounds* bounds, uint32_t n_chunks, const CullParams& cp,
-                                   uint32_t* vis_list, CullState* cull);
+// clear (zbuf coverage, accum, minmax) + per-frame chunk classification in ONE launch; parity alternates per frame.
+cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum,
+                                  uint64_t n_px, uint32_t* minmax, const ChunkBounds* bounds, uint32_t n_chunks,
+                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity);
 cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                         uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,

@@ -34,12 +34,7 @@ __global__ void __launch_bounds__(256) clear_kernel(uint32_t* __restrict__ zbuf,
         minmax[1] = 0u;
         minmax[2] = 0u;  // float-accumulator overflow flag of this frame
         minmax[3] = 0u;  // grid-barrier counter of exact_fixup_kernel
-        if (cull) {  // fold the previous frame's visible-chunk count into the running total, reset for this frame
-            cull->total_visible += cull->n_visible;
-            cull->frames += (cull->armed ? 1u : 0u);
-            cull->n_visible = 0u;
-            cull->armed = 0u;
-        }
+        (void)cull;  // frames rendered without culling leave the culling state alone
     }
     if (accum) {
         for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -146,7 +141,7 @@ __global__ void __launch_bounds__(kPointBlock) zmin_list_kernel(const PointRecor
                                                                 uint32_t* __restrict__ zbuf,
                                                                 unsigned long long* __restrict__ zkey) {
     pdl_prologue();
-    const uint32_t n_vis = cull->n_visible;
+    const uint32_t n_vis = cull_count(cull);
     for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
         zmin_tile<kChunkPoints / kPointBlock, VARIANT, false, KEY64>(
             pts, n, index_base, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x, pp, zbuf, zkey);
@@ -237,7 +232,7 @@ __global__ void __launch_bounds__(kPointBlock) blend_list_kernel(const PointReco
                                                                  const uint32_t* __restrict__ gate) {
     pdl_prologue();
     if (gate && *gate == 0u) return;
-    const uint32_t n_vis = cull->n_visible;
+    const uint32_t n_vis = cull_count(cull);
     for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
         blend_tile<kChunkPoints / kPointBlock, VARIANT, false>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x,
                                                               pp, zbuf, accum2);
@@ -279,7 +274,7 @@ __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRec
     grid_barrier(minmax + 3, gridDim.x);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     if constexpr (LIST) {
-        const uint32_t n_vis = cull->n_visible;
+        const uint32_t n_vis = cull_count(cull);
         for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
             blend_tile<kChunkPoints / kPointBlock, 0, false>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x, pp, zbuf, a2);
     } else {

@@ -294,13 +294,14 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     if (r->timing) cudaEventRecord(ev[0], s);
     if (r->key64) {
         fs.f32acc = false;
-        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, cull ? r->cull_state : nullptr));
+        if (cull) {
+            r->cull_parity ^= 1u;
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state, r->cull_parity));
+        } else {
+            RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, nullptr));
+        }
         RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
         r->launches += 2;
-        if (cull) {
-            RTR_CUDA(r, launch_classify_chunks(s, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state));
-            r->launches += 1;
-        }
         if (r->timing) cudaEventRecord(ev[1], s);
         if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, fb.zkey));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
@@ -320,12 +321,13 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         RTR_CUDA(r, launch_resolve_pyramid(s, fb, r->W, r->H, r->dims, filtered, false, r->force_generic != 0));
         r->launches += filtered ? (((r->W % 16) == 0 && !r->force_generic) ? 1 : 5) : 0;
     } else {
-        RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, cull ? r->cull_state : nullptr));
-        r->launches += 1;
         if (cull) {
-            RTR_CUDA(r, launch_classify_chunks(s, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state));
-            r->launches += 1;
+            r->cull_parity ^= 1u;
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state, r->cull_parity));
+        } else {
+            RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, nullptr));
         }
+        r->launches += 1;
         if (r->timing) cudaEventRecord(ev[1], s);
         if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, nullptr));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
@@ -479,6 +481,7 @@ int build_chunk_bounds(rtr_renderer* r) {
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->vis_list), size_t(r->n_chunks) * sizeof(uint32_t)));
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->cull_state), sizeof(CullState)));
     RTR_CUDA(r, cudaMemsetAsync(r->cull_state, 0, sizeof(CullState), r->stream));
+    r->cull_parity = 0;
     RTR_CUDA(r, launch_chunk_bounds(r->stream, r->points, r->n_points, r->bounds));
     r->launches += 1;
     RTR_CUDA(r, cudaStreamSynchronize(r->stream));
@@ -867,8 +870,11 @@ int rtr_get_cull_stats(rtr_renderer* r, uint64_t* frames, uint64_t* visible_chun
     CullState st;
     RTR_CUDA(r, cudaMemcpy(&st, r->cull_state, sizeof(st), cudaMemcpyDeviceToHost));
     *frames = uint64_t(st.frames) + (st.armed ? 1u : 0u);   // the frame in flight is folded at the next clear
-    *visible_chunks_total = st.total_visible + (st.armed ? st.n_visible : 0u);
-    if (reset) RTR_CUDA(r, cudaMemset(r->cull_state, 0, sizeof(CullState)));
+    *visible_chunks_total = st.total_visible + (st.armed ? cull_count(&st) : 0u);
+    if (reset) {
+        RTR_CUDA(r, cudaMemset(r->cull_state, 0, sizeof(CullState)));
+        r->cull_parity = 0;
+    }
     return RTR_OK;
 }
 
