@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../rtr_b200.h"
+#include "../rtr_b200_io.h"
 
 #if defined(__has_include)
 #if __has_include(<opencv2/core.hpp>)
@@ -89,6 +90,26 @@ public:
     int computeTensor(const Intrinsics& c, const double* extrinsics16, void** tensor) {
         int rc = setCamera(c, extrinsics16);
         return rc == RTR_OK ? rtr_render_tensor(h_, tensor) : rc;
+    }
+
+    // computeFull (project_cloud.cu:437-493) with the neural stage supplied by the caller, so that this header needs
+    // no libtorch: `unet(tensor, W, H)` receives the device pointer of the 1x5xHxW fp16 input and returns the device
+    // pointer of the network's 3xHxW fp16 output (e.g. model.forward({from_blob(tensor, ...)}).toTensor()[0]
+    // .contiguous().data_ptr(), kept alive by the caller until this returns).  color: H*W*3 uint8 =
+    // saturate(round(v * 255)) like the reference's convertTo; depth: the filtered depth.  Either may be null.
+    template <typename UNet>
+    int computeFull(const Intrinsics& c, const double* extrinsics16, uint8_t* color, float* depth, UNet&& unet) {
+        void* tensor = nullptr;
+        int rc = computeTensor(c, extrinsics16, &tensor);
+        if (rc != RTR_OK) return rc;
+        const void* out = unet(tensor, c.width, c.height);
+        if (color) {
+            if (!out) return RTR_ERR_ARG;
+            rc = rtr_postprocess_unet_output(h_, out, c.width, c.height, color, nullptr);
+            if (rc != RTR_OK) return rc;
+        }
+        if (depth) rc = rtr_read_buffer(h_, 0, depth, size_t(c.width) * c.height * sizeof(float));
+        return rc;
     }
 
 #ifdef RTR_B200_HAVE_OPENCV

@@ -66,6 +66,8 @@ def test_headers_compile_as_c99_and_cpp17_and_link(pkg, tmp_path):
     cpp = tmp_path / "t.cpp"
     cpp.write_text('#include "rtr_b200/project_cloud.hpp"\n#include <cstdio>\n'
                    'int main() { try { rtr_b200::ProjectCloud pc(0); rtr_b200::Intrinsics k; double E[16] = {1,0,0,0,0,1,0,0,0,0,1,0,0,0,0,1};\n'
+                   '  auto net = [](void* t, int, int) -> const void* { return t; };\n'
+                   '  if (pc.computeFull(k, E, nullptr, nullptr, net) > 0) return 4;   // no cloud uploaded: must fail, not crash\n'
                    '  return pc.computeRGBD(k, E, nullptr, nullptr) == -1 ? 0 : 3; }\n'
                    '  catch (const std::exception& e) { std::puts(e.what()); return 2; } }\n')
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", f"-I{inc}", str(cpp), "-o", str(tmp_path / "t_cpp"),
