@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtr_b200.so")
-SOURCES = ["rtr_point_kernels.cu", "rtr_image_kernels.cu", "rtr_cull.cu", "rtr_peer.cu", "rtr_synth.cu", "rtr_microbench.cu", "rtr_io.cu", "rtr_renderer.cu"]
+SOURCES = ["rtr_point_kernels.cu", "rtr_point_ring.cu", "rtr_image_kernels.cu", "rtr_cull.cu", "rtr_peer.cu", "rtr_synth.cu", "rtr_microbench.cu", "rtr_io.cu", "rtr_renderer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",

@@ -178,8 +178,22 @@ __device__ __forceinline__ float lo_or_m1(const float* __restrict__ lo, int x, i
     return (x >= 0 && x < w && y >= 0 && y < h) ? lo[y * w + x] : -1.0f;  // getPixelValue, project_cloud.cu:81-86
 }
 
+// Accessors of a coarse level: global memory (row stride = the level's up-pass width) or a clipped rectangle of it
+// staged in shared memory (up_fused_kernel).
+struct LoGlobal {
+    const float* __restrict__ p;
+    int w;
+    __device__ __forceinline__ float operator()(int x, int y) const { return p[y * w + x]; }
+};
+struct LoShared {
+    const float* p;
+    int x0, y0, w;
+    __device__ __forceinline__ float operator()(int x, int y) const { return p[(y - y0) * w + (x - x0)]; }
+};
+
 // bilinear hole fill of one fine pixel (resizeKernel, project_cloud.cu:135-160; op order from SASS)
-__device__ __forceinline__ float bilinear_up(const float* __restrict__ lo, int lw, int lh, int x, int y) {
+template <typename Lo>
+__device__ __forceinline__ float bilinear_up_t(const Lo& lo, int lw, int lh, int x, int y) {
     const float inX = __fmaf_rn(__fadd_rn(float(x), 0.5f), 0.5f, -0.5f);
     const float inY = __fmaf_rn(__fadd_rn(float(y), 0.5f), 0.5f, -0.5f);
     int x0 = __float2int_rd(inX), y0 = __float2int_rd(inY);
@@ -190,9 +204,42 @@ __device__ __forceinline__ float bilinear_up(const float* __restrict__ lo, int l
     y1 = y1 < 0 ? 0 : (y1 >= lh ? lh - 1 : y1);
     const float wx = __fsub_rn(inX, float(x0)), wy = __fsub_rn(inY, float(y0));
     const float omx = __fsub_rn(1.0f, wx);
-    const float v0 = __fmaf_rn(wx, lo[y0 * lw + x1], __fmul_rn(omx, lo[y0 * lw + x0]));
-    const float v1 = __fmaf_rn(wx, lo[y1 * lw + x1], __fmul_rn(omx, lo[y1 * lw + x0]));
+    const float v0 = __fmaf_rn(wx, lo(x1, y0), __fmul_rn(omx, lo(x0, y0)));
+    const float v1 = __fmaf_rn(wx, lo(x1, y1), __fmul_rn(omx, lo(x0, y1)));
     return __fmaf_rn(v0, __fsub_rn(1.0f, wy), __fmul_rn(wy, v1));
+}
+__device__ __forceinline__ float bilinear_up(const float* __restrict__ lo, int lw, int lh, int x, int y) {
+    return bilinear_up_t(LoGlobal{lo, lw}, lw, lh, x, y);
+}
+
+// laplacianKernel + compareImgsKernel for ONE fine pixel with value cur under coarse parent (lx, ly)
+// (project_cloud.cu:55-126): true = the pixel keeps its value.
+template <typename Lo>
+__device__ __forceinline__ bool up_keep_t(const Lo& lo, int lw, int lh, int lx, int ly, float cur) {
+    if (cur >= __uint_as_float(kMaxFloatThresholdBits)) return false;  // `if (currentVal >= MAX_FLOAT) mask = 0`
+    const bool border = (lx == 0 || lx == lw - 1 || ly == 0 || ly == lh - 1);  // laplacianKernel border -> 0
+    if (!border) {
+        float nb[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) nb[k] = lo(lx + k % 3 - 1, ly + k / 3 - 1);
+        float sum = 0.0f;  // nine chained FMAs, k row-major, zero-weight taps included (laplacianKernel as compiled)
+        sum = __fmaf_rn(nb[0], 0.0f, sum);
+        sum = __fmaf_rn(nb[1], 1.0f, sum);
+        sum = __fmaf_rn(nb[2], 0.0f, sum);
+        sum = __fmaf_rn(nb[3], 1.0f, sum);
+        sum = __fmaf_rn(nb[4], -4.0f, sum);
+        sum = __fmaf_rn(nb[5], 1.0f, sum);
+        sum = __fmaf_rn(nb[6], 0.0f, sum);
+        sum = __fmaf_rn(nb[7], 1.0f, sum);
+        sum = __fmaf_rn(nb[8], 0.0f, sum);
+        if (sum > kGradientFilter) {
+            bool keep = false;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) keep = keep || (cur <= __fmul_rn(nb[k], kFilterStrength));
+            return keep;
+        }
+    }
+    return cur <= __fmul_rn(lo(lx, ly), kFilterStrength);
 }
 
 __device__ __forceinline__ uint16_t h_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
@@ -301,17 +348,16 @@ __global__ void __launch_bounds__(256) up_level_kernel(const float* __restrict__
 // Same arithmetic as up_level_kernel<true>; a thread owns the 8 fine pixels of row hy under 4 adjacent coarse
 // pixels, so depth / tensor planes move as 16-byte vectors and the image as three 8-byte words, and the 3x3 coarse
 // neighbourhoods of the four parents share one 3x6 window.  Needs lw % 4 == 0 (true whenever W % 16 == 0).
-__global__ void __launch_bounds__(256) up_final_wide_kernel(const float* __restrict__ lo, int lw, int lh,
-                                                            float* __restrict__ hi, uint8_t* __restrict__ mask_tap,
-                                                            uint8_t* __restrict__ image, uint16_t* __restrict__ tensor,
-                                                            const uint32_t* __restrict__ minmax) {
-    pdl_prologue();
-    const int groups = lw >> 2, hh = lh * 2, hw = lw * 2;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= groups * hh) return;
-    const int g = t % groups, hy = t / groups, ly = hy >> 1, lx0 = g * 4;
+// Body shared by up_final_wide_kernel and up_fused_kernel: the 8 fine pixels of row hy under coarse pixels lx0..lx0+3.
+// `c0, c1` = the 8 depths, `iw` = their 24 image bytes (loaded by the caller, possibly long before);
+// `lut`: when not null, lut[v] = half(float(half(v)) / 255) for v = 0..255 (the value removeMask computes per byte).
+template <typename Lo>
+__device__ __forceinline__ void up_final_group(const Lo& lo, int lw, int lh, float* __restrict__ hi,
+                                               uint8_t* __restrict__ mask_tap, uint8_t* __restrict__ image,
+                                               uint16_t* __restrict__ tensor, float dmin, float range, int lx0, int hy,
+                                               const float4 c0, const float4 c1, uint2 (&iw)[3], const uint16_t* lut) {
+    const int hh = lh * 2, hw = lw * 2, ly = hy >> 1;
     const size_t idx = size_t(hy) * hw + size_t(lx0) * 2;
-    const float4 c0 = *reinterpret_cast<const float4*>(hi + idx), c1 = *reinterpret_cast<const float4*>(hi + idx + 4);
     const float cur[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
     const float thr = __uint_as_float(kMaxFloatThresholdBits);
     bool keep[8];
@@ -326,7 +372,7 @@ __global__ void __launch_bounds__(256) up_final_wide_kernel(const float* __restr
         for (int r = 0; r < 3; ++r) {
             const int y = min(max(ly + r - 1, 0), lh - 1);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) w[r][c] = lo[y * lw + min(max(lx0 + c - 1, 0), lw - 1)];
+            for (int c = 0; c < 6; ++c) w[r][c] = lo(min(max(lx0 + c - 1, 0), lw - 1), y);
         }
         const bool row_border = (ly == 0 || ly == lh - 1);
 #pragma unroll
@@ -375,10 +421,7 @@ __global__ void __launch_bounds__(256) up_final_wide_kernel(const float* __restr
     }
     // removeMask (project_cloud.cu:163-187)
     const size_t plane = size_t(hw) * hh;
-    const float dmin = __uint_as_float(minmax[0]), dmax = __uint_as_float(minmax[1]);
-    const float range = __fsub_rn(dmax, dmin);
     uint2* img8 = reinterpret_cast<uint2*>(image + idx * 3);  // idx % 8 == 0 -> 24-byte group, 8-byte aligned
-    uint2 iw[3] = {img8[0], img8[1], img8[2]};
     uint8_t* c = reinterpret_cast<uint8_t*>(iw);
     uint16_t tp[5][8];
     float dout[8];
@@ -393,9 +436,15 @@ __global__ void __launch_bounds__(256) up_final_wide_kernel(const float* __restr
             tp[0][j] = tp[1][j] = tp[2][j] = tp[3][j] = 0;
             tp[4][j] = 0xBC00u;  // -1.0h
         } else {
-            tp[0][j] = half_div(float(c[3 * j + 0]), 255.0f);
-            tp[1][j] = half_div(float(c[3 * j + 1]), 255.0f);
-            tp[2][j] = half_div(float(c[3 * j + 2]), 255.0f);
+            if (lut) {
+                tp[0][j] = lut[c[3 * j + 0]];
+                tp[1][j] = lut[c[3 * j + 1]];
+                tp[2][j] = lut[c[3 * j + 2]];
+            } else {
+                tp[0][j] = half_div(float(c[3 * j + 0]), 255.0f);
+                tp[1][j] = half_div(float(c[3 * j + 1]), 255.0f);
+                tp[2][j] = half_div(float(c[3 * j + 2]), 255.0f);
+            }
             tp[3][j] = half_div(255.0f, 255.0f);
             tp[4][j] = half_div(__fsub_rn(cur[j], dmin), range);
         }
@@ -414,6 +463,103 @@ __global__ void __launch_bounds__(256) up_final_wide_kernel(const float* __restr
         v.w = uint32_t(tp[k][6]) | (uint32_t(tp[k][7]) << 16);
         *reinterpret_cast<uint4*>(tensor + plane * k + idx) = v;
     }
+}
+
+__global__ void __launch_bounds__(256) up_final_wide_kernel(const float* __restrict__ lo, int lw, int lh,
+                                                            float* __restrict__ hi, uint8_t* __restrict__ mask_tap,
+                                                            uint8_t* __restrict__ image, uint16_t* __restrict__ tensor,
+                                                            const uint32_t* __restrict__ minmax) {
+    pdl_prologue();
+    const int groups = lw >> 2, hh = lh * 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= groups * hh) return;
+    const float dmin = __uint_as_float(minmax[0]), dmax = __uint_as_float(minmax[1]);
+    const int lx0 = (t % groups) * 4, hy = t / groups;
+    const size_t idx = size_t(hy) * (lw * 2) + size_t(lx0) * 2;
+    const float4 c0 = *reinterpret_cast<const float4*>(hi + idx), c1 = *reinterpret_cast<const float4*>(hi + idx + 4);
+    const uint2* img8 = reinterpret_cast<const uint2*>(image + idx * 3);
+    uint2 iw[3] = {img8[0], img8[1], img8[2]};
+    up_final_group(LoGlobal{lo, lw}, lw, lh, hi, mask_tap, image, tensor, dmin, __fsub_rn(dmax, dmin), lx0, hy, c0, c1, iw, nullptr);
+}
+
+// ---------------------------------------------------------------- the whole up-pass in one launch
+// The four iterations of the up-pass (levels 4->3, 3->2, 2->1 with hole filling, 1->0 with removeMask) depend on
+// each other only through a one-pixel ring of the coarser level: fine pixel (x, y) reads the 3x3 neighbourhood of its
+// parent (x/2, y/2) (Laplacian, compare) and the bilinear taps floor((x-0.5)/2), +1.  A CTA therefore takes a
+// 64 x 32 tile of level 0 (one 8-pixel group per thread), stages the regions of levels 1..4 that tile depends on in
+// shared memory (34x18, 20x12, 12x8, 8x6 values), fills the holes of levels 3, 2, 1 there — the halo is recomputed by
+// the neighbouring CTAs instead of being exchanged — and finishes with the level-0 pass.  Every global load (the four
+// staged regions, the thread's 8 depths and 24 image bytes) is issued before the first barrier, so one memory latency
+// is exposed instead of five, and the three per-byte IEEE divisions of removeMask come from a 256-entry table
+// computed by the CTA with the same operations.  Levels 1..3 in global memory are only read (no cross-CTA hazard);
+// they keep their down-pass values, so the per-level launches stay the path for keep_masks = 1 (taps of every
+// reference kernel).
+constexpr int kUpT1W = 32, kUpT1H = 16;  // level-1 core of a CTA
+static_assert(kUpT1W / 4 * kUpT1H * 2 == 256, "one 8-pixel group of level 0 per thread");
+struct UpRect { int x0, y0, w, h; };
+// coarse rectangle a fine rectangle depends on, clipped to the coarse level's dims
+__device__ __forceinline__ UpRect up_parent_rect(const UpRect f, int lw, int lh) {
+    const int x0 = max((f.x0 >> 1) - 1, 0), x1 = min(((f.x0 + f.w - 1) >> 1) + 1, lw - 1);
+    const int y0 = max((f.y0 >> 1) - 1, 0), y1 = min(((f.y0 + f.h - 1) >> 1) + 1, lh - 1);
+    return UpRect{x0, y0, x1 - x0 + 1, y1 - y0 + 1};
+}
+__device__ __forceinline__ void up_stage_rect(float* dst, const float* __restrict__ src, int src_w, const UpRect r) {
+    for (int i = threadIdx.x; i < r.w * r.h; i += blockDim.x) dst[i] = src[(r.y0 + i / r.w) * src_w + r.x0 + i % r.w];
+}
+// hole-fill rectangle rf of the fine level in place in shared memory from the staged coarse level
+__device__ __forceinline__ void up_fill_rect(float* fine, const UpRect rf, const float* coarse, const UpRect rc, int lw, int lh) {
+    const LoShared lo{coarse, rc.x0, rc.y0, rc.w};
+    for (int i = threadIdx.x; i < rf.w * rf.h; i += blockDim.x) {
+        const int x = rf.x0 + i % rf.w, y = rf.y0 + i / rf.w;
+        const float cur = fine[i];
+        if (!up_keep_t(lo, lw, lh, x >> 1, y >> 1, cur)) fine[i] = bilinear_up_t(lo, lw, lh, x, y);
+    }
+}
+
+__global__ void __launch_bounds__(256, 4) up_fused_kernel(const float* __restrict__ l1, const float* __restrict__ l2,
+                                                       const float* __restrict__ l3, const float* __restrict__ l4,
+                                                       int w4, int h4, float* __restrict__ l0, uint8_t* __restrict__ image,
+                                                       uint16_t* __restrict__ tensor, const uint32_t* __restrict__ minmax) {
+    __shared__ float s1[(kUpT1W + 2) * (kUpT1H + 2)];
+    __shared__ float s2[(kUpT1W / 2 + 4) * (kUpT1H / 2 + 4)];
+    __shared__ float s3[(kUpT1W / 4 + 4) * (kUpT1H / 4 + 4)];
+    __shared__ float s4[(kUpT1W / 8 + 4) * (kUpT1H / 8 + 4)];
+    __shared__ uint16_t lut[256];
+    lut[threadIdx.x] = half_div(float(threadIdx.x), 255.0f);  // removeMask's value for image byte threadIdx.x
+    pdl_prologue();
+    const int w3 = w4 * 2, h3 = h4 * 2, w2 = w4 * 4, h2 = h4 * 4, w1 = w4 * 8, h1 = h4 * 8;
+    const UpRect core{int(blockIdx.x) * kUpT1W, int(blockIdx.y) * kUpT1H, min(kUpT1W, w1 - int(blockIdx.x) * kUpT1W),
+                      min(kUpT1H, h1 - int(blockIdx.y) * kUpT1H)};
+    // this thread's 8 level-0 pixels: loads issued first, consumed after the shared-memory chain
+    const int groups = core.w >> 2;  // w1 % 4 == 0 and the tile width is a multiple of 4
+    const bool mine = int(threadIdx.x) < groups * core.h * 2;
+    const int lx0 = core.x0 + (mine ? int(threadIdx.x) % groups : 0) * 4, hy = core.y0 * 2 + (mine ? int(threadIdx.x) / groups : 0);
+    const size_t idx = size_t(hy) * (w1 * 2) + size_t(lx0) * 2;
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+    uint2 iw[3] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+    if (mine) {
+        c0 = *reinterpret_cast<const float4*>(l0 + idx);
+        c1 = *reinterpret_cast<const float4*>(l0 + idx + 4);
+        const uint2* img8 = reinterpret_cast<const uint2*>(image + idx * 3);
+        iw[0] = img8[0]; iw[1] = img8[1]; iw[2] = img8[2];
+    }
+    // level-1 pixels the level-0 tile reads: the tile's parents and one ring around them; and so on upwards
+    const UpRect r1 = up_parent_rect(UpRect{core.x0 * 2, core.y0 * 2, core.w * 2, core.h * 2}, w1, h1);
+    const UpRect r2 = up_parent_rect(r1, w2, h2), r3 = up_parent_rect(r2, w3, h3), r4 = up_parent_rect(r3, w4, h4);
+    up_stage_rect(s4, l4, w4, r4);
+    up_stage_rect(s3, l3, w3, r3);
+    up_stage_rect(s2, l2, w2, r2);
+    up_stage_rect(s1, l1, w1, r1);
+    const float dmin = __uint_as_float(minmax[0]), dmax = __uint_as_float(minmax[1]);
+    __syncthreads();
+    up_fill_rect(s3, r3, s4, r4, w4, h4);
+    __syncthreads();
+    up_fill_rect(s2, r2, s3, r3, w3, h3);
+    __syncthreads();
+    up_fill_rect(s1, r1, s2, r2, w2, h2);
+    __syncthreads();
+    if (mine)
+        up_final_group(LoShared{s1, r1.x0, r1.y0, r1.w}, w1, h1, l0, nullptr, image, tensor, dmin, __fsub_rn(dmax, dmin), lx0, hy, c0, c1, iw, lut);
 }
 
 // ---------------------------------------------------------------- launchers
@@ -486,14 +632,21 @@ cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey,
     return cudaGetLastError();
 }
 
-cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool force_generic) {
+cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool force_generic, bool fused) {
+    // tensor plane stride (uw[0]*uh[0]) must keep the 16-byte stores aligned: multiples of 8 halfs
+    const bool wide_ok = !force_generic && (d.uw[1] % 4) == 0 && ((size_t(d.uw[0]) * d.uh[0]) % 8) == 0;
+    const bool taps = fb.mask[0] || fb.mask[1] || fb.mask[2] || fb.mask[3];
+    // one launch for all four levels: needs the flat pyramid to be a true 2-D pyramid (w[i] == uw[i], i.e. W % 16 == 0)
+    if (fused && wide_ok && !taps && d.uw[4] > 0 && d.uh[4] > 0 && d.w[1] == d.uw[1] && d.w[2] == d.uw[2] && d.w[3] == d.uw[3]) {
+        launch_pdl(up_fused_kernel, dim3((d.uw[1] + kUpT1W - 1) / kUpT1W, (d.uh[1] + kUpT1H - 1) / kUpT1H), dim3(256), s,
+                   fb.level[1], fb.level[2], fb.level[3], fb.level[4], d.uw[4], d.uh[4], fb.level[0], fb.image, fb.tensor, fb.minmax);
+        return cudaGetLastError();
+    }
     for (int i = 4; i >= 1; --i) {
         const int pairs = d.uw[i] * d.uh[i] * 2;  // fine pixels / 2
         if (pairs == 0) continue;
         const unsigned grid = (pairs + 255) / 256;
-        // tensor plane stride (uw[0]*uh[0]) must keep the 16-byte stores aligned: multiples of 8 halfs
-        const bool wide = i == 1 && !force_generic && (d.uw[1] % 4) == 0 && ((size_t(d.uw[0]) * d.uh[0]) % 8) == 0;
-        if (wide)
+        if (i == 1 && wide_ok)
             launch_pdl(up_final_wide_kernel, dim3((d.uw[1] / 4 * d.uh[1] * 2 + 255) / 256), dim3(256), s, fb.level[1], d.uw[1], d.uh[1], fb.level[0], fb.mask[0], fb.image, fb.tensor, fb.minmax);
         else if (i > 1)
             launch_pdl((up_level_kernel<false>), dim3(grid), dim3(256), s, fb.level[i], d.uw[i], d.uh[i], fb.level[i - 1], fb.mask[i - 1], nullptr, nullptr, fb.minmax);
@@ -501,6 +654,15 @@ cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const Pyramid
             launch_pdl((up_level_kernel<true>), dim3(grid), dim3(256), s, fb.level[1], d.uw[1], d.uh[1], fb.level[0], fb.mask[0], fb.image, fb.tensor, fb.minmax);
     }
     return cudaGetLastError();
+}
+// launches launch_up_pass issues for these dims (the renderer's launch counter)
+int up_pass_launches(const FrameBuffers& fb, const PyramidDims& d, bool force_generic, bool fused) {
+    const bool wide_ok = !force_generic && (d.uw[1] % 4) == 0 && ((size_t(d.uw[0]) * d.uh[0]) % 8) == 0;
+    const bool taps = fb.mask[0] || fb.mask[1] || fb.mask[2] || fb.mask[3];
+    if (fused && wide_ok && !taps && d.uw[4] > 0 && d.uh[4] > 0 && d.w[1] == d.uw[1] && d.w[2] == d.uw[2] && d.w[3] == d.uw[3]) return 1;
+    int n = 0;
+    for (int i = 4; i >= 1; --i) n += (d.uw[i] * d.uh[i] != 0);
+    return n;
 }
 
 }  // namespace rtr

@@ -35,6 +35,7 @@ struct rtr_renderer {
     rtr::CullState* cull_state = nullptr;
     uint32_t n_chunks = 0;
     uint32_t cull_parity = 0;  // alternates per culled frame (CullState::n_visible double buffer)
+    rtr::RingSchedule ring_sched{};  // stream-all tile order of the ring kernels (rtr_point_ring.cu), fixed at upload
     // camera
     int W = 0, H = 0;
     double K[9] = {0};
@@ -51,6 +52,8 @@ struct rtr_renderer {
     // options
     int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
     int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1, sort_on_upload = 1;
+    int fused_up = 1;  // the four up-pass levels in one launch (needs W % 16 == 0 and keep_masks = 0)
+    int ring = 1;  // point passes through the TMA-fed persistent kernels (0: the per-thread LDG.128 kernels)
     cudaEvent_t ev[6] = {nullptr};
     // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
     std::vector<cudaEvent_t> ev_pool;

@@ -58,11 +58,11 @@ inline uint64_t clear_coverage(int W, int H) {  // fillBuffer/resolvePass grid: 
 // falls back to plain stream serialisation (A/B measurements).
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+inline void launch_pdl_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -70,6 +70,10 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+    launch_pdl_smem(kernel, grid, block, 0, s, static_cast<Args&&>(args)...);
 }
 
 // ---- point passes (rtr_point_kernels.cu)
@@ -82,6 +86,22 @@ cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const Po
 cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
                               const ProjParams& pp, const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf,
                               uint32_t* accum, const uint32_t* gate);
+
+// ---- the point passes as persistent TMA-fed kernels (rtr_point_ring.cu) — the default (option "ring")
+// Tile t of a launch is chunk vis_list[t] (list = true: the frame's visible chunks, count read on the device from
+// `cull`) or chunk (t * perm_mul) mod n_chunks (list = false: every chunk, in a low-discrepancy order).
+struct RingSchedule {
+    const CullState* cull;
+    const uint32_t* vis_list;
+    uint32_t n_chunks;
+    uint32_t perm_mul;
+};
+RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const uint32_t* vis_list);
+cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
+                             uint64_t index_base, const ProjParams& pp, const RingSchedule& sc, bool list, uint32_t* zbuf,
+                             unsigned long long* zkey);
+cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
+                              const ProjParams& pp, const RingSchedule& sc, bool list, const uint32_t* zbuf, uint32_t* accum);
 
 // ---- chunk-level frustum culling (rtr_cull.cu)
 cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds);
@@ -110,7 +130,7 @@ struct FrameBuffers {
     uint16_t* tensor;    // 5P fp16, planes of stride uw[0]*uh[0]
     float* level[5];     // level[0] aliases zbuf; level[1..4] persistent scratch
     uint8_t* mask[4];    // optional taps: mask[i-1] produced by up-pass iteration i (nullptr = not kept)
-    uint32_t* minmax;    // {min, max} of the valid depth bits, [2] = float-accumulator overflow flag
+    uint32_t* minmax;    // {min, max} of the valid depth bits, [2] = float-accumulator overflow flag, [3] = fix-up barrier
     unsigned long long* zkey;  // P u64, only in key64 mode
 };
 // accum -> image over [0, cov) (resolvePass), fused with the 4-level min pyramid (reduce x4) and the
@@ -125,8 +145,10 @@ cudaError_t launch_clear_key64(cudaStream_t s, int sm_count, unsigned long long*
 cudaError_t launch_resolve_key64(cudaStream_t s, const unsigned long long* zkey, const PointRecord* pts,
                                  uint64_t index_base, uint64_t n_local, uint32_t* zbuf, uint8_t* image, uint64_t n_px,
                                  uint64_t cov);
-// up-pass: laplacian + compare (+ resize | + removeMask) per level, 4 launches.
-cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool force_generic);
+// up-pass: laplacian + compare (+ resize | + removeMask).  fused: all four levels in ONE launch (up_fused_kernel) when
+// W % 16 == 0 and no mask taps are requested; otherwise one launch per level.
+cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const PyramidDims& d, bool force_generic, bool fused);
+int up_pass_launches(const FrameBuffers& fb, const PyramidDims& d, bool force_generic, bool fused);
 
 // ---- point-sharded merge over peer memory (rtr_peer.cu)
 constexpr int kMaxPeers = 16;

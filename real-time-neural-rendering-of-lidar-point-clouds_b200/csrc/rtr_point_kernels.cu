@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) clear_accum_gated_kernel(uint4* __restric
 
 // ---------------------------------------------------------------- z-min
 // variant bit 0: early depth test   bit 1: warp aggregation   bit 2: early test through L1 (ld.ca)
+// bit 3: measurement only, no RED issued   bit 4: measurement only, atomicMin builtin instead of the PTX red
 template <int UNROLL, int VARIANT, bool DISTORT, int KEY64>
 __device__ __forceinline__ void zmin_tile(const PointRecord* __restrict__ pts, uint64_t n, uint64_t index_base,
                                           const uint64_t base, const ProjParams& pp, uint32_t* __restrict__ zbuf,
@@ -89,7 +90,10 @@ __device__ __forceinline__ void zmin_tile(const PointRecord* __restrict__ pts, u
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-            if (live[u] && key[u] < cur[u] && !(VARIANT & 8)) atomicMin(zkey + pix[u], key[u]);
+            if (live[u] && key[u] < cur[u] && !(VARIANT & 8)) {
+                if constexpr (VARIANT & 16) atomicMin(zkey + pix[u], key[u]);  // measurement: the builtin (ATOMG after the fence)
+                else red_min_u64(zkey + pix[u], key[u]);
+            }
     } else {
         // phase 3: early depth test, UNROLL gathers in flight
         uint32_t cur[UNROLL];
@@ -107,11 +111,13 @@ __device__ __forceinline__ void zmin_tile(const PointRecord* __restrict__ pts, u
                     const uint32_t mn = __reduce_min_sync(same, dbits[u]);
                     // one lane per (warp, pixel) group issues the RED
                     const unsigned winners = __ballot_sync(same, dbits[u] == mn) & same;
-                    if ((threadIdx.x & 31) == (__ffs(winners) - 1)) atomicMin(zbuf + pix[u], mn);
+                    if ((threadIdx.x & 31) == (__ffs(winners) - 1)) red_min_u32(zbuf + pix[u], mn);
                 } else if constexpr (VARIANT & 8) {  // measurement only: no RED issued (results are wrong)
                     if (dbits[u] == 0x12345678u && pix[u] == 0xFFFFFFFFu) zbuf[0] = 0u;
-                } else {
+                } else if constexpr (VARIANT & 16) {  // measurement: the builtin (ATOMG after the fence)
                     atomicMin(zbuf + pix[u], dbits[u]);
+                } else {
+                    red_min_u32(zbuf + pix[u], dbits[u]);
                 }
             }
         }
@@ -197,12 +203,10 @@ __device__ __forceinline__ void blend_tile(const PointRecord* __restrict__ pts, 
                 // one 16-byte RED.ADD.F32x4 per point: the accumulator holds the same integers as floats,
                 // exact while count <= kF32ExactCount (resolve detects anything beyond and the exact
                 // passes below are re-run for that frame)
-                asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(float(b)), "f"(float(g)), "f"(float(r)),
-                             "f"(float(c))
-                             : "memory");
+                red_add_f32x4(a, float(b), float(g), float(r), float(c));
             } else {
-                atomicAdd(a + 0, static_cast<unsigned long long>(b) | (static_cast<unsigned long long>(g) << 32));
-                atomicAdd(a + 1, static_cast<unsigned long long>(r) | (static_cast<unsigned long long>(c) << 32));
+                red_add_u64(a + 0, static_cast<unsigned long long>(b) | (static_cast<unsigned long long>(g) << 32));
+                red_add_u64(a + 1, static_cast<unsigned long long>(r) | (static_cast<unsigned long long>(c) << 32));
             }
         }
     }
@@ -321,15 +325,13 @@ cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const Po
                              uint64_t index_base, const ProjParams& pp, const CullState* cull, const uint32_t* vis_list,
                              uint32_t* zbuf, unsigned long long* zkey) {
     if (n == 0) return cudaSuccess;
-    unsigned grid = unsigned(sm_count) * 8u;
-    if (variant & 16) grid = unsigned((n + kChunkPoints - 1) / kChunkPoints);  // experiment: one CTA per chunk slot
-    if (variant & 32) grid = unsigned(sm_count) * 4u;
+    const unsigned grid = unsigned(sm_count) * 8u;
 #define RTR_ZL(V)                                                                                                  \
     do {                                                                                                           \
         if (zkey) launch_pdl((zmin_list_kernel<V, 1>), dim3(grid), dim3(kPointBlock), s, pts, n, index_base, pp, cull, vis_list, zbuf, zkey); \
         else launch_pdl((zmin_list_kernel<V, 0>), dim3(grid), dim3(kPointBlock), s, pts, n, index_base, pp, cull, vis_list, zbuf, zkey);      \
     } while (0)
-    switch (variant & 15) {
+    switch (variant & 31) {
         case 0: RTR_ZL(0); break;
         case 1: RTR_ZL(1); break;
         case 2: RTR_ZL(2); break;
@@ -338,6 +340,7 @@ cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const Po
         case 7: RTR_ZL(7); break;
         case 8: RTR_ZL(8); break;
         case 9: RTR_ZL(9); break;
+        case 21: RTR_ZL(21); break;
         default: return cudaErrorInvalidValue;
     }
 #undef RTR_ZL

@@ -291,6 +291,10 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         for (int k = 0; k < 4; ++k) { cp.r0[k] = pp.m[k]; cp.r1[k] = pp.m[4 + k]; cp.r2[k] = pp.m[8 + k]; }
         cp.W = r->W; cp.H = r->H;
     }
+    RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
+    sched.cull = cull ? r->cull_state : nullptr;
+    sched.vis_list = cull ? r->vis_list : nullptr;
+
     if (r->timing) cudaEventRecord(ev[0], s);
     if (r->key64) {
         fs.f32acc = false;
@@ -303,7 +307,8 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
         r->launches += 2;
         if (r->timing) cudaEventRecord(ev[1], s);
-        if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, fb.zkey));
+        if (r->ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, fb.zkey));
+        else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, fb.zkey));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
         r->launches += 1;
         if (r->comm) {
@@ -329,7 +334,8 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         }
         r->launches += 1;
         if (r->timing) cudaEventRecord(ev[1], s);
-        if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, nullptr));
+        if (r->ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, nullptr));
+        else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, nullptr));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
         r->launches += 1;
         if (peer) {
@@ -343,7 +349,8 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         const int bv = (r->comm || peer) ? (r->blend_variant & ~4) : r->blend_variant;
         const bool f32acc = (bv & 4) != 0;
         fs.f32acc = f32acc;
-        if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, nullptr));
+        if (r->ring) RTR_CUDA(r, launch_blend_ring(s, r->sm_count, bv, r->points, r->n_points, pp, sched, cull, fb.zbuf, fb.accum));
+        else if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, nullptr));
         else RTR_CUDA(r, launch_blend(s, bv, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, nullptr));
         r->launches += 1;
         if (peer) {
@@ -366,8 +373,8 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     }
     if (r->timing) cudaEventRecord(ev[4], s);
     if (filtered) {
-        RTR_CUDA(r, launch_up_pass(s, fb, r->dims, r->force_generic != 0));
-        r->launches += 4;
+        RTR_CUDA(r, launch_up_pass(s, fb, r->dims, r->force_generic != 0, r->fused_up != 0));
+        r->launches += uint64_t(up_pass_launches(fb, r->dims, r->force_generic != 0, r->fused_up != 0));
     }
     if (r->timing) cudaEventRecord(ev[5], s);
     if (r->timing == 2) r->ev_frames += 1;
@@ -477,6 +484,7 @@ int replace_cloud(rtr_renderer* r, uint64_t n) {
 int build_chunk_bounds(rtr_renderer* r) {
     if (r->n_points == 0) return RTR_OK;
     r->n_chunks = uint32_t((r->n_points + kChunkPoints - 1) / kChunkPoints);
+    r->ring_sched = make_ring_schedule(r->n_points, nullptr, nullptr);
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->bounds), size_t(r->n_chunks) * sizeof(ChunkBounds)));
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->vis_list), size_t(r->n_chunks) * sizeof(uint32_t)));
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->cull_state), sizeof(CullState)));
@@ -805,6 +813,8 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "key64")) return &r->key64;
     if (!std::strcmp(key, "chunk_cull")) return &r->chunk_cull;
     if (!std::strcmp(key, "sort_on_upload")) return &r->sort_on_upload;
+    if (!std::strcmp(key, "ring")) return &r->ring;
+    if (!std::strcmp(key, "fused_up")) return &r->fused_up;
     return nullptr;
 }
 
@@ -816,9 +826,9 @@ int rtr_set_option(rtr_renderer* r, const char* key, int64_t value) {
     if ((!std::strcmp(key, "zmin_unroll") || !std::strcmp(key, "blend_unroll")) && value != 1 && value != 2 && value != 4 && value != 8)
         return fail(r, RTR_ERR_ARG, "unroll must be 1, 2, 4 or 8");
     if (!std::strcmp(key, "zmin_variant") && !((value & 7) == 0 || (value & 7) == 1 || (value & 7) == 2 || (value & 7) == 3 || (value & 7) == 5 || (value & 7) == 7))
-        return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7 (+8/16/32 measurement bits)");
-    if (!std::strcmp(key, "blend_variant") && (value < 0 || value > 7 || (value & 1)))
-        return fail(r, RTR_ERR_ARG, "blend_variant must be 0, 2, 4 or 6");
+        return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7 (+8/16 measurement bits)");
+    if (!std::strcmp(key, "blend_variant") && (value < 0 || (value & ~38)))
+        return fail(r, RTR_ERR_ARG, "blend_variant must be 0, 2, 4 or 6 (+32 measurement bit)");
     *slot = int(value);
     return RTR_OK;
 }

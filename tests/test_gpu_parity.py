@@ -159,9 +159,13 @@ def test_cuda_vs_live_reference(gpu, cpu_oracle, name):
 
 
 # ------------------------------------------------------------------ invariances / variants
-VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u, chunk_cull=c)
-            for v, u, b, c in [(0, 1, 0, 0), (1, 2, 2, 0), (2, 4, 0, 0), (3, 8, 2, 0), (5, 4, 0, 0), (7, 4, 2, 0),
-                               (0, 4, 2, 1), (1, 4, 0, 1), (3, 4, 0, 1), (7, 4, 2, 1), (5, 4, 4, 1), (5, 4, 6, 0), (5, 2, 4, 0)]]
+# ring = 0: the per-thread LDG.128 kernels (rtr_point_kernels.cu); ring = 1 (default): the TMA-fed persistent kernels
+# (rtr_point_ring.cu) over the visible-chunk list (chunk_cull = 1) or over every chunk in permuted order (0)
+VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u, chunk_cull=c, ring=r)
+            for v, u, b, c, r in [(0, 1, 0, 0, 0), (1, 2, 2, 0, 0), (2, 4, 0, 0, 0), (3, 8, 2, 0, 0), (5, 4, 0, 0, 0), (7, 4, 2, 0, 0),
+                                  (0, 4, 2, 1, 0), (1, 4, 0, 1, 0), (3, 4, 0, 1, 0), (7, 4, 2, 1, 0), (5, 4, 4, 1, 0), (5, 4, 6, 0, 0),
+                                  (5, 2, 4, 0, 0), (21, 4, 4, 1, 0),
+                                  (0, 4, 0, 0, 1), (1, 4, 4, 0, 1), (5, 4, 4, 0, 1), (0, 4, 4, 1, 1), (1, 4, 0, 1, 1), (5, 4, 0, 1, 1)]]
 
 
 @pytest.mark.parametrize("opts", VARIANTS)
@@ -180,6 +184,17 @@ def test_generic_path_equals_fused_path(gpu, cpu_oracle):
         base, _, _ = render_mine(gpu, case, rec, with_taps=False)
         other, _, _ = render_mine(gpu, case, rec, options={"force_generic": 1}, with_taps=False)
         assert_frames_equal(other, base, f"{name} generic vs fused")
+
+
+def test_one_launch_up_pass_equals_per_level_launches(gpu, cpu_oracle):
+    """up_fused_kernel (default when W % 16 == 0) recomputes halos in shared memory instead of running the four
+    levels as four launches; every output must stay identical, incl. partial tiles (1080 rows -> 1072) and 4K."""
+    for name in ("small_160x96", "small_176x104", "c1_640x480", "c2_1280x720", "c3_1920x1080", "c5_3840x2160"):
+        case = scenes.CASES[name]
+        rec = cloud_of(cpu_oracle, case)
+        base, _, _ = render_mine(gpu, case, rec, with_taps=False)
+        other, _, _ = render_mine(gpu, case, rec, options={"fused_up": 0}, with_taps=False)
+        assert_frames_equal(other, base, f"{name} per-level vs one-launch up-pass")
 
 
 def test_point_order_does_not_matter(gpu, cpu_oracle):
