@@ -43,6 +43,7 @@ struct rtr_renderer {
     double E[16] = {0};
     bool have_K = false, have_E = false, raw_proj = false;
     float cam_proj[16] = {0};
+    double cull_rstar = 0;  // distortion: normalised radius beyond which nothing reaches the image (make_params)
     // frame buffers (two sets, see header)
     rtr::FrameSet set[2];
     int cur = 0;

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRec
     if constexpr (LIST) {
         const uint32_t n_vis = cull_count(cull);
         for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
-            blend_tile<kChunkPoints / kPointBlock, 0, false>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x, pp, zbuf, a2);
+            blend_tile<kChunkPoints / kPointBlock, 0, DISTORT>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x, pp, zbuf, a2);
     } else {
         const uint64_t n_tiles = (n + kChunkPoints - 1) / kChunkPoints;
         for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
@@ -368,7 +368,8 @@ cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* 
     if (n == 0) return cudaSuccess;
     const dim3 grid(unsigned(sm_count) * 2u), block(kPointBlock);
     uint4* a4 = reinterpret_cast<uint4*>(accum);
-    if (cull) launch_pdl((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    if (cull && pp.distort) launch_pdl((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    else if (cull) launch_pdl((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
     else if (pp.distort) launch_pdl((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
     else launch_pdl((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
     return cudaGetLastError();

@@ -342,7 +342,10 @@ template <int VARIANT>
 static cudaError_t launch_zmin_ring_v(cudaStream_t s, unsigned grid, const PointRecord* pts, uint64_t n, uint64_t index_base,
                                       const ProjParams& pp, const RingSchedule& sc, bool list, uint32_t* zbuf,
                                       unsigned long long* zkey) {
-    if (list) {
+    if (list && pp.distort) {
+        if (zkey) RTR_RING_LAUNCH((zmin_ring_kernel<VARIANT, true, 1, true>), pts, n, index_base, pp, sc, zbuf, zkey);
+        else RTR_RING_LAUNCH((zmin_ring_kernel<VARIANT, true, 0, true>), pts, n, index_base, pp, sc, zbuf, zkey);
+    } else if (list) {
         if (zkey) RTR_RING_LAUNCH((zmin_ring_kernel<VARIANT, false, 1, true>), pts, n, index_base, pp, sc, zbuf, zkey);
         else RTR_RING_LAUNCH((zmin_ring_kernel<VARIANT, false, 0, true>), pts, n, index_base, pp, sc, zbuf, zkey);
     } else if (pp.distort) {
@@ -378,11 +381,14 @@ cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const P
     const unsigned grid = ring_grid(sm_count, sc, list);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     const bool f32 = (variant & 4) != 0;
-    if (list && f32 && (variant & 32)) {  // measurement: no in-register merge
+    if (list && !pp.distort && f32 && (variant & 32)) {  // measurement: no in-register merge
         RTR_RING_LAUNCH((blend_ring_kernel<36, false, true>), pts, n, pp, sc, zbuf, a2);
         return cudaGetLastError();
     }
-    if (list) {
+    if (list && pp.distort) {
+        if (f32) RTR_RING_LAUNCH((blend_ring_kernel<4, true, true>), pts, n, pp, sc, zbuf, a2);
+        else RTR_RING_LAUNCH((blend_ring_kernel<0, true, true>), pts, n, pp, sc, zbuf, a2);
+    } else if (list) {
         if (f32) RTR_RING_LAUNCH((blend_ring_kernel<4, false, true>), pts, n, pp, sc, zbuf, a2);
         else RTR_RING_LAUNCH((blend_ring_kernel<0, false, true>), pts, n, pp, sc, zbuf, a2);
     } else if (pp.distort) {

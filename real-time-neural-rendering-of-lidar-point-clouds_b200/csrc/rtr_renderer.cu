@@ -202,6 +202,27 @@ int make_params(rtr_renderer* r, ProjParams& pp) {
             if (deriv <= 0) { lim = lim * (i - 1) / 4096.0; break; }
         }
         pp.r2_max = float(lim);
+        // Radius r* (normalised, undistorted) beyond which no point can land in the image — what chunk culling uses
+        // under distortion (enqueue_frame).  A visible point has (xd, yd) inside the image's parallelogram in
+        // normalised distorted coordinates, i.e. |(xd, yd)| <= R_d, and |(xd, yd)| >= r |radial(r^2)| - T r^2 with
+        // T = 4.3 (|p1| + |p2|) bounding the tangential terms.  r* = the largest sampled r in [0, sqrt(r2_max)] that
+        // still satisfies g(r) = r |radial| - T r^2 <= R_d (with 0.1 % slack), plus 1 %.
+        const double p1 = r->dist[2], p2 = r->dist[3], T = 4.3 * (std::fabs(p1) + std::fabs(p2));
+        double Rd = 0;
+        const double us[2] = {-0.5, r->W - 0.5}, vs[2] = {-0.5, r->H - 0.5};
+        for (double v : vs) for (double u : us) {
+            const double yd = (v - r->K[5]) / r->K[4], xd = (u - r->K[2] - r->K[1] * yd) / r->K[0];
+            Rd = std::fmax(Rd, std::sqrt(xd * xd + yd * yd));
+        }
+        const double rmax = std::sqrt(lim);
+        double rstar = 0;
+        for (int i = 0; i <= 8192; ++i) {
+            const double rr = rmax * i / 8192.0, q = rr * rr;
+            const double g = rr * std::fabs(1 + k1 * q + k2 * q * q + k3 * q * q * q) - T * q;
+            if (g <= Rd * 1.001) rstar = rr;
+        }
+        r->cull_rstar = std::fmin(rstar + rmax / 8192.0, rmax) * 1.01;
+        if (!(Rd > 0) || !std::isfinite(r->cull_rstar)) r->cull_rstar = 0;  // 0 = no culling under this camera
     }
     return RTR_OK;
 }
@@ -284,12 +305,22 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         if (r->ev_frames == kEvPoolFrames && (rc = drain_event_pool(r)) != RTR_OK) return rc;
         ev = &r->ev_pool[size_t(r->ev_frames) * 6];
     }
-    // chunk-level frustum culling: exact (conservative) for the pinhole path; the distorted path streams everything
-    const bool cull = r->chunk_cull && !pp.distort && r->bounds;
+    // chunk-level frustum culling: exact (conservative) for the pinhole path.  Under distortion (ring kernels only)
+    // the chunk test runs against the square [-r*, r*]^2 of normalised coordinates that contains every point able to
+    // reach the image (make_params), written as a pinhole camera of 2001 x 2001 "pixels" of r*/1000 each.
+    const bool cull = r->chunk_cull && r->bounds && (!pp.distort || (r->ring && r->cull_rstar > 0));
     CullParams cp;
-    if (cull) {
+    if (cull && !pp.distort) {
         for (int k = 0; k < 4; ++k) { cp.r0[k] = pp.m[k]; cp.r1[k] = pp.m[4 + k]; cp.r2[k] = pp.m[8 + k]; }
         cp.W = r->W; cp.H = r->H;
+    } else if (cull) {
+        const double a = 1000.0 / r->cull_rstar;
+        for (int k = 0; k < 4; ++k) {
+            cp.r0[k] = a * double(pp.e[k]) + 1000.0 * double(pp.e[8 + k]);
+            cp.r1[k] = a * double(pp.e[4 + k]) + 1000.0 * double(pp.e[8 + k]);
+            cp.r2[k] = double(pp.e[8 + k]);
+        }
+        cp.W = 2001.0; cp.H = 2001.0;
     }
     RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
     sched.cull = cull ? r->cull_state : nullptr;

@@ -465,6 +465,45 @@ def test_chunk_culling_never_changes_a_frame(gpu, cpu_oracle):
     off.close()
 
 
+def test_chunk_culling_under_distortion_never_changes_a_frame(gpu, cpu_oracle):
+    """Distorted cameras cull chunks against the square of normalised coordinates that bounds every point able to
+    reach the image (rtr_renderer.cu make_params): culling on vs off must give identical buffers for barrel,
+    pincushion, tangential and strong mixed distortion, cameras inside and outside the cloud."""
+    case = scenes.CASES["c1_640x480"]
+    rec = cloud_of(cpu_oracle, case)[:400_000].copy()
+    rec[5000, 0] = np.nan
+    rec[200001, :3] = [1e20, -1e20, 1e20]
+    rng = np.random.default_rng(23)
+    W, H, P = 320, 208, 320 * 208
+    on = gpu.ProjectCloud.from_packed(rec, apply_distortion=True)
+    off = gpu.ProjectCloud.from_packed(rec, apply_distortion=True)
+    off.set_option("chunk_cull", 0)
+    dists = [[-0.05, 0.01, 0.0005, -0.0005, 0.0], [0.2, 0.05, 0.0, 0.0, 0.01], [-0.3, 0.1, 0.0, 0.0, -0.01],
+             [0.0, 0.0, 0.02, -0.03, 0.0], [-0.2, 0.03, 0.01, 0.01, 0.001], [1e-9, 0.0, 0.0, 0.0, 0.0]]
+    culled_any = False
+    for it in range(48):
+        f = float(rng.choice([120.0, 230.0, 600.0]))
+        calib = gpu.CameraCalibration()
+        calib.loadCalibration(f, f * rng.uniform(0.9, 1.1), rng.uniform(0.3 * W, 0.7 * W), rng.uniform(0.3 * H, 0.7 * H),
+                              dists[it % len(dists)], W, H)
+        eye = rng.uniform([-2, -2, 0], [10, 8, 3])
+        E = gpu.look_at_w2c(eye, rng.standard_normal(3), up=(0.0, 0.3, 1.0))
+        outs = []
+        for pc in (on, off):
+            pc.set_camera(calib, E)
+            pc.render_device(gpu.STAGE_FILTERED)
+            outs.append((pc.read("zbuf", np.uint32, P), pc.read("accum", np.uint32, P * 4), pc.read("image", np.uint8, P * 3),
+                         pc.read("tensor", np.uint16, P * 5)))
+        for a, b, what in zip(outs[0], outs[1], ("zbuf", "accum", "image", "tensor")):
+            assert np.array_equal(a, b), f"camera {it} dist {dists[it % len(dists)]}: {what} changed by chunk culling"
+        fr, vis, nch = on.cull_stats(reset=True)
+        assert fr == 1 and 0 < vis <= nch
+        culled_any |= vis < nch
+    assert culled_any
+    on.close()
+    off.close()
+
+
 def test_chunk_culling_pixel_boundary_points(gpu):
     """Points placed exactly on and one ulp around the four image borders and the z = 0 plane, one chunk
     each, with a camera whose rows make u and v land on k + 0.5 ties: cull on == cull off."""
