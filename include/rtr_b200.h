@@ -123,7 +123,7 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
 
 /* ---- options / introspection.  Known keys: "zmin_variant" (bit0 early test, bit1 warp
  * aggregation, bit2 L1-cached test), "zmin_unroll", "blend_variant", "blend_unroll",
- * "force_generic", "keep_masks", "timing", "key64", "chunk_cull", "sort_on_upload" (default 1: every upload
+ * "force_generic", "keep_masks", "timing", "key64", "chunk_cull", "ring", "fused_up", "sort_on_upload" (default 1: every upload
  * re-orders the cloud along a Morton curve on the GPU — no output depends on point order; set 0 BEFORE uploading
  * to keep the input order, e.g. when the point index of the 64-bit key must be the caller's index). */
 int rtr_set_option(rtr_renderer* r, const char* key, int64_t value);
@@ -147,6 +147,12 @@ uint64_t rtr_launch_count(const rtr_renderer* r);
  * of REDs really issued).  Returns the mean CUDA-event time of one launch. */
 int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int iters, float* ms_per_launch,
                       uint64_t* live_ops);
+
+/* Device self-test of the ring kernels' perspective divide: for n_pairs random bit patterns (a, b) (every class of
+ * float: NaN, inf, denormal, huge) checks on the GPU that whenever !(|b| < 2^-126) the directly issued
+ * MUFU.RCP + FMUL gives the same bits as __fdividef(a, b) (what the reference compiles, render.cu:65-66), and the same
+ * rounded pixel coordinate.  *mismatches = number of pairs that differ (must be 0). */
+int rtr_selftest_fast_divide(rtr_renderer* r, uint64_t n_pairs, uint64_t seed, uint64_t* mismatches);
 
 /* ---- point-sharded multi-GPU (one process per GPU; plumbing by the caller, e.g. torch.distributed).
  * rtr_comm_unique_id fills a 128-byte NCCL id on rank 0; broadcast it, then every rank calls

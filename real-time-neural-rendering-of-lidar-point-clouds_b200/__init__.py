@@ -65,6 +65,7 @@ API = {
     "rtr_get_cull_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _i]),
     "rtr_launch_count": (_u64, [_vp]),
     "rtr_bench_red_min": (_i, [_vp, _i, _u64, _i, _i, _fp, C.POINTER(_u64)]),
+    "rtr_selftest_fast_divide": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),
     "rtr_comm_unique_id": (_i, [_vp]),
     "rtr_comm_init": (_i, [_vp, _vp, _i, _i]),
     "rtr_comm_destroy": (_i, [_vp]),
@@ -328,6 +329,12 @@ class ProjectCloud:
         ms, live = C.c_float(0), _u64(0)
         self._check(self._lib.rtr_bench_red_min(self._h, mode, n_ops, int(key64), iters, C.byref(ms), C.byref(live)))
         return float(ms.value), int(live.value)
+
+    def selftest_fast_divide(self, n_pairs: int, seed: int = 1) -> int:
+        """Pairs (of n_pairs random bit patterns) for which the ring kernels' MUFU.RCP + FMUL differs from __fdividef."""
+        bad = _u64(0)
+        self._check(self._lib.rtr_selftest_fast_divide(self._h, n_pairs, seed, C.byref(bad)))
+        return int(bad.value)
 
     @property
     def cloud_size(self) -> int:

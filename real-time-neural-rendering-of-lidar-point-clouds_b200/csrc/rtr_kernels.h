@@ -173,4 +173,6 @@ cudaError_t launch_synth(cudaStream_t s, uint64_t seed, uint64_t n_total, uint64
 cudaError_t launch_red_bench(cudaStream_t s, int sm_count, int mode, bool key64, const int32_t* pix, uint64_t n_ops,
                              uint32_t n_px, uint32_t* z32, unsigned long long* z64);
 
+cudaError_t launch_fast_divide_selftest(cudaStream_t s, int sm_count, uint64_t n_pairs, uint64_t seed, unsigned long long* mismatches);
+
 }  // namespace rtr

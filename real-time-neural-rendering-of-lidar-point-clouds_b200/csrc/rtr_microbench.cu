@@ -52,6 +52,28 @@ __global__ void __launch_bounds__(256) red_accum_kernel(uint64_t n_ops, uint32_t
     }
 }
 
+// rtr_selftest_fast_divide: project4's fast path against __fdividef on raw random bit patterns.
+__global__ void __launch_bounds__(256) fast_divide_selftest_kernel(uint64_t n_pairs, uint64_t seed,
+                                                                   unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pairs; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t h = rtr_splitmix64(seed + i);
+        uint32_t ab = uint32_t(h), bb = uint32_t(h >> 32);
+        if ((i & 7) == 1) bb = (bb & 0x807FFFFFu) | ((i >> 3) % 3 == 0 ? 0u : ((i >> 3) % 3 == 1 ? 0x00800000u : 0x7E800000u));  // denormal / smallest normal / huge b
+        if ((i & 7) == 2) ab = (ab & 0x807FFFFFu);                                                                            // denormal a
+        const float a = __uint_as_float(ab), b = __uint_as_float(bb);
+        if (fabsf(b) < 1.17549435e-38f) continue;  // the warp takes __fdividef itself there
+        const float q_ref = __fdividef(a, b), q_fast = __fmul_rn(mufu_rcp(b), a);
+        const bool same_bits = __float_as_uint(q_ref) == __float_as_uint(q_fast) || (q_ref != q_ref && q_fast != q_fast);
+        if (!same_bits || __float2int_rn(q_ref) != __float2int_rn(q_fast)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+cudaError_t launch_fast_divide_selftest(cudaStream_t s, int sm_count, uint64_t n_pairs, uint64_t seed, unsigned long long* mismatches) {
+    fast_divide_selftest_kernel<<<unsigned(sm_count) * 8u, 256, 0, s>>>(n_pairs, seed, mismatches);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_red_bench(cudaStream_t s, int sm_count, int mode, bool key64, const int32_t* pix, uint64_t n_ops,
                              uint32_t n_px, uint32_t* z32, unsigned long long* z64) {
     const unsigned grid = unsigned(sm_count) * 8u;

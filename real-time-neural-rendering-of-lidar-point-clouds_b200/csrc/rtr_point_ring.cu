@@ -30,11 +30,11 @@
 
 namespace rtr {
 
-constexpr int kRingStages = 4;
+constexpr int kRingStages = 6;
 constexpr int kRingGroups = 2;                        // consumer groups per CTA, each takes every kRingGroups-th tile
 constexpr int kRingConsumers = kPointBlock;           // a group: 256 threads x 4 consecutive records = one chunk
 constexpr int kRingThreads = kRingGroups * kRingConsumers;  // 512: no dedicated producer warp, thread 0 of a group refills its stages
-constexpr int kRingCtasPerSm = 3;                     // 3 x (64 KB ring + barriers) fit the 227 KB of an SM: 48 warps, <= 40 registers
+constexpr int kRingCtasPerSm = 2;                     // 2 x (96 KB ring + barriers) per SM: 32 warps, up to 64 registers
 constexpr int kRingPerThread = kChunkPoints / kRingConsumers;
 static_assert(kRingStages % kRingGroups == 0, "every group must own a fixed subset of the stages");
 static_assert(kRingPerThread == 4, "the bank-conflict-free rotation below assumes 4 records per thread");
@@ -91,8 +91,8 @@ __device__ __forceinline__ uint32_t tile_chunk(const RingSchedule& sc, uint32_t 
     else return uint32_t((uint64_t(t) * sc.perm_mul) % sc.n_chunks);
 }
 
-// Producer / consumer skeleton shared by both passes.  consume(p, first, rot, valid): p[s] is record
-// first + ((s + rot) & 3) of the cloud and exists iff ((s + rot) & 3) < valid.
+// Producer / consumer skeleton shared by both passes.  consume(p, chunk, first, rot, valid): p[s] is record
+// chunk * kChunkPoints + first + (s ^ rot) of the cloud and exists iff (s ^ rot) < valid.
 //
 // Tile k of a CTA is tile blockIdx.x + k * gridDim.x of the launch and lands in stage k % kRingStages.  (Handing
 // tiles out through an atomic counter instead was measured slower — the counter's round trip sits on the refilling
@@ -128,8 +128,13 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
         }
     }
     // Thread i of a group owns records 4i..4i+3 of the chunk.  A 128-bit LDS is served 8 lanes at a time; lane l reads
-    // its record (s + (l >> 1)) & 3 at step s, so that the 8 lanes of a phase touch 8 different 16-byte bank groups
-    // (address/16 mod 8 = 4(l&1) + ((s + (l>>1)) & 3)): conflict-free without padding.
+    // its record s ^ ((l >> 1) & 3) at step s, so that the 8 lanes of a phase touch 8 different 16-byte bank groups
+    // (address/16 mod 8 = 4(l&1) + (s ^ (l>>1 & 3))): conflict-free without padding, one XOR per load.
+    const uint32_t lds0 = smem_addr(&sm.rec[0][0]) + ((tid * kRingPerThread + rot) << 4);
+    const uint32_t last_chunk = uint32_t((n - 1) / kChunkPoints);
+    // how many of this thread's four records exist in the LAST chunk of the cloud (stale bytes follow them in the stage)
+    const uint64_t tail_first = uint64_t(last_chunk) * kChunkPoints + tid * kRingPerThread;
+    const uint32_t tail_valid = tail_first + kRingPerThread <= n ? uint32_t(kRingPerThread) : (tail_first < n ? uint32_t(n - tail_first) : 0u);
     for (uint32_t k = group, t = blockIdx.x + group * G; t < n_tiles; k += kRingGroups, t += kRingGroups * G) {
         const uint32_t stage = k % kRingStages, parity = (k / kRingStages) & 1u;
         const uint32_t t_refill = t + kRingStages * G;
@@ -137,11 +142,12 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
         if (leader && t_refill < n_tiles) refill_chunk = tile_chunk<LIST>(sc, t_refill);  // in flight during the wait below
         mbar_wait(&sm.full[stage], parity);
         const uint32_t chunk = sm.chunk[stage];
-        const uint4* src = reinterpret_cast<const uint4*>(&sm.rec[stage][0]) + tid * kRingPerThread;
+        const uint32_t a = lds0 + stage * uint32_t(kChunkPoints * sizeof(PointRecord));
         PointRecord p[kRingPerThread];
 #pragma unroll
         for (int s = 0; s < kRingPerThread; ++s) {
-            const uint4 v = src[(uint32_t(s) + rot) & 3u];
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a ^ (uint32_t(s) << 4)));
             p[s].x = __uint_as_float(v.x); p[s].y = __uint_as_float(v.y); p[s].z = __uint_as_float(v.z); p[s].bgra = v.w;
         }
         __syncwarp();
@@ -150,10 +156,7 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
             mbar_wait(&sm.empty[stage], parity);  // the group's other warps are a few instructions behind at most
             issue(stage, refill_chunk);
         }
-        // records past the end of the cloud (last chunk only) hold stale bytes: `valid` = how many of this thread's four exist
-        const uint64_t first = uint64_t(chunk) * kChunkPoints + tid * kRingPerThread;
-        const uint32_t valid = first + kRingPerThread <= n ? uint32_t(kRingPerThread) : (first < n ? uint32_t(n - first) : 0u);
-        consume(p, first, rot, valid);
+        consume(p, chunk, tid * kRingPerThread, rot, chunk == last_chunk ? tail_valid : uint32_t(kRingPerThread));
     }
 }
 
@@ -184,21 +187,27 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) zmin_ring_kernel
                                                                  unsigned long long* __restrict__ zkey) {
     RingSmem& sm = ring_setup();  // touches shared memory only: overlaps the previous grid's tail
     pdl_prologue();
-    ring_walk<LIST>(pts, n, sc, sm, [&](const PointRecord (&p)[kRingPerThread], uint64_t first, uint32_t rot, uint32_t valid) {
+    ring_walk<LIST>(pts, n, sc, sm, [&](const PointRecord (&p)[kRingPerThread], uint32_t chunk, uint32_t first, uint32_t rot, uint32_t valid) {
         uint32_t pix[kRingPerThread];
         using Key = std::conditional_t<KEY64 != 0, unsigned long long, uint32_t>;
         Key key[kRingPerThread];  // KEY64: (depth bits << 32) | global index ; else the depth bits
         bool live[kRingPerThread];
+        {
+            const float x[4] = {p[0].x, p[1].x, p[2].x, p[3].x}, y[4] = {p[0].y, p[1].y, p[2].y, p[3].y}, z[4] = {p[0].z, p[1].z, p[2].z, p[3].z};
+            float depth[4];
+            project4<DISTORT>(pp, x, y, z, pix, depth, live);
 #pragma unroll
-        for (int s = 0; s < kRingPerThread; ++s) {
-            const uint32_t slot = (uint32_t(s) + rot) & 3u;
-            float depth;
-            live[s] = project<DISTORT>(pp, p[s].x, p[s].y, p[s].z, pix[s], depth) & (slot < valid);
-            key[s] = __float_as_uint(depth);
-            if constexpr (KEY64) key[s] = (key[s] << 32) | static_cast<unsigned long long>(uint32_t(index_base + first + slot));
-            (void)index_base;
-            (void)first;
+            for (int s = 0; s < kRingPerThread; ++s) {
+                const uint32_t slot = uint32_t(s) ^ rot;
+                live[s] = live[s] & (slot < valid);
+                key[s] = __float_as_uint(depth[s]);
+                if constexpr (KEY64)
+                    key[s] = (key[s] << 32) | static_cast<unsigned long long>(uint32_t(index_base + uint64_t(chunk) * kChunkPoints + first + slot));
+            }
+            (void)index_base; (void)chunk; (void)first;
         }
+        // a warp whose 128 records all fell outside the frustum is done (most warps of a stream-all pass, the rim of a culled one)
+        if (!__any_sync(0xFFFFFFFFu, live[0] | live[1] | live[2] | live[3])) return;
         // neighbours that landed in the same pixel: keep the smallest key in the first of them
 #pragma unroll
         for (int j = 1; j < ((VARIANT & 32) ? 0 : kRingPerThread); ++j) {
@@ -251,14 +260,17 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) blend_ring_kerne
                                                                   unsigned long long* __restrict__ accum2) {
     RingSmem& sm = ring_setup();
     pdl_prologue();
-    ring_walk<LIST>(pts, n, sc, sm, [&](const PointRecord (&p)[kRingPerThread], uint64_t, uint32_t rot, uint32_t valid) {
+    ring_walk<LIST>(pts, n, sc, sm, [&](const PointRecord (&p)[kRingPerThread], uint32_t, uint32_t, uint32_t rot, uint32_t valid) {
         uint32_t pix[kRingPerThread];
         float depth[kRingPerThread];
         bool live[kRingPerThread];
+        {
+            const float x[4] = {p[0].x, p[1].x, p[2].x, p[3].x}, y[4] = {p[0].y, p[1].y, p[2].y, p[3].y}, z[4] = {p[0].z, p[1].z, p[2].z, p[3].z};
+            project4<DISTORT>(pp, x, y, z, pix, depth, live);
 #pragma unroll
-        for (int s = 0; s < kRingPerThread; ++s) {
-            live[s] = project<DISTORT>(pp, p[s].x, p[s].y, p[s].z, pix[s], depth[s]) & (((uint32_t(s) + rot) & 3u) < valid);
+            for (int s = 0; s < kRingPerThread; ++s) live[s] = live[s] & ((uint32_t(s) ^ rot) < valid);
         }
+        if (!__any_sync(0xFFFFFFFFu, live[0] | live[1] | live[2] | live[3])) return;  // nothing of this warp is in the frustum
         uint32_t zmin[kRingPerThread];
 #pragma unroll
         for (int s = 0; s < kRingPerThread; ++s) {

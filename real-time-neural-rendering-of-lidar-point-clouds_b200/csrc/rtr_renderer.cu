@@ -309,6 +309,9 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     // the chunk test runs against the square [-r*, r*]^2 of normalised coordinates that contains every point able to
     // reach the image (make_params), written as a pinhole camera of 2001 x 2001 "pixels" of r*/1000 each.
     const bool cull = r->chunk_cull && r->bounds && (!pp.distort || (r->ring && r->cull_rstar > 0));
+    // ring = 1: the TMA-fed kernels for culled frames, the per-thread LDG.128 kernels when every chunk is streamed
+    // (measured 3 % faster there, profiles/r01h_exp_ring_c3.json); ring = 2: always; ring = 0: never
+    const bool use_ring = r->ring == 2 || (r->ring == 1 && cull);
     CullParams cp;
     if (cull && !pp.distort) {
         for (int k = 0; k < 4; ++k) { cp.r0[k] = pp.m[k]; cp.r1[k] = pp.m[4 + k]; cp.r2[k] = pp.m[8 + k]; }
@@ -323,6 +326,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         cp.W = 2001.0; cp.H = 2001.0;
     }
     RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
+    if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
     sched.cull = cull ? r->cull_state : nullptr;
     sched.vis_list = cull ? r->vis_list : nullptr;
 
@@ -338,7 +342,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
         r->launches += 2;
         if (r->timing) cudaEventRecord(ev[1], s);
-        if (r->ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, fb.zkey));
+        if (use_ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, fb.zkey));
         else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, fb.zkey));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
         r->launches += 1;
@@ -365,7 +369,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         }
         r->launches += 1;
         if (r->timing) cudaEventRecord(ev[1], s);
-        if (r->ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, nullptr));
+        if (use_ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, nullptr));
         else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, nullptr));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
         r->launches += 1;
@@ -380,7 +384,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         const int bv = (r->comm || peer) ? (r->blend_variant & ~4) : r->blend_variant;
         const bool f32acc = (bv & 4) != 0;
         fs.f32acc = f32acc;
-        if (r->ring) RTR_CUDA(r, launch_blend_ring(s, r->sm_count, bv, r->points, r->n_points, pp, sched, cull, fb.zbuf, fb.accum));
+        if (use_ring) RTR_CUDA(r, launch_blend_ring(s, r->sm_count, bv, r->points, r->n_points, pp, sched, cull, fb.zbuf, fb.accum));
         else if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, nullptr));
         else RTR_CUDA(r, launch_blend(s, bv, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, nullptr));
         r->launches += 1;
@@ -833,6 +837,23 @@ int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int 
     return RTR_OK;
 }
 
+int rtr_selftest_fast_divide(rtr_renderer* r, uint64_t n_pairs, uint64_t seed, uint64_t* mismatches) {
+    if (!r || !mismatches) return RTR_ERR_ARG;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    unsigned long long* d = nullptr;
+    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&d), 8));
+    cudaError_t e = cudaMemsetAsync(d, 0, 8, r->stream);
+    if (e == cudaSuccess) e = launch_fast_divide_selftest(r->stream, r->sm_count, n_pairs, seed, d);
+    r->launches += 1;
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, r->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(r, e, "rtr_selftest_fast_divide");
+    *mismatches = h;
+    return RTR_OK;
+}
+
 static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "zmin_variant")) return &r->zmin_variant;
     if (!std::strcmp(key, "zmin_unroll")) return &r->zmin_unroll;
@@ -846,6 +867,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "sort_on_upload")) return &r->sort_on_upload;
     if (!std::strcmp(key, "ring")) return &r->ring;
     if (!std::strcmp(key, "fused_up")) return &r->fused_up;
+    if (!std::strcmp(key, "ring_perm")) return &r->ring_perm;
     return nullptr;
 }
 

@@ -160,12 +160,12 @@ def test_cuda_vs_live_reference(gpu, cpu_oracle, name):
 
 # ------------------------------------------------------------------ invariances / variants
 # ring = 0: the per-thread LDG.128 kernels (rtr_point_kernels.cu); ring = 1 (default): the TMA-fed persistent kernels
-# (rtr_point_ring.cu) over the visible-chunk list (chunk_cull = 1) or over every chunk in permuted order (0)
+# (rtr_point_ring.cu) over the visible-chunk list when chunk_cull = 1; ring = 2: also over every chunk (permuted order)
 VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u, chunk_cull=c, ring=r)
             for v, u, b, c, r in [(0, 1, 0, 0, 0), (1, 2, 2, 0, 0), (2, 4, 0, 0, 0), (3, 8, 2, 0, 0), (5, 4, 0, 0, 0), (7, 4, 2, 0, 0),
                                   (0, 4, 2, 1, 0), (1, 4, 0, 1, 0), (3, 4, 0, 1, 0), (7, 4, 2, 1, 0), (5, 4, 4, 1, 0), (5, 4, 6, 0, 0),
                                   (5, 2, 4, 0, 0), (21, 4, 4, 1, 0),
-                                  (0, 4, 0, 0, 1), (1, 4, 4, 0, 1), (5, 4, 4, 0, 1), (0, 4, 4, 1, 1), (1, 4, 0, 1, 1), (5, 4, 0, 1, 1)]]
+                                  (0, 4, 0, 0, 2), (1, 4, 4, 0, 2), (5, 4, 4, 0, 2), (0, 4, 4, 1, 1), (1, 4, 0, 1, 1), (5, 4, 0, 1, 2)]]
 
 
 @pytest.mark.parametrize("opts", VARIANTS)
@@ -195,6 +195,15 @@ def test_one_launch_up_pass_equals_per_level_launches(gpu, cpu_oracle):
         base, _, _ = render_mine(gpu, case, rec, with_taps=False)
         other, _, _ = render_mine(gpu, case, rec, options={"fused_up": 0}, with_taps=False)
         assert_frames_equal(other, base, f"{name} per-level vs one-launch up-pass")
+
+
+def test_fast_divide_path_is_the_reference_divide(gpu, cpu_oracle):
+    """The ring kernels issue MUFU.RCP + FMUL directly when no depth of the warp is denormal (rtr_common.cuh project4):
+    on 200 M random bit patterns (NaN, inf, denormal, huge included) the quotient bits and the rounded pixel must equal
+    __fdividef's, which is what the reference compiles."""
+    pc = gpu.ProjectCloud.from_packed(cloud_of(cpu_oracle, scenes.CASES["small_160x96"]))
+    assert pc.selftest_fast_divide(200_000_000, seed=3) == 0
+    pc.close()
 
 
 def test_point_order_does_not_matter(gpu, cpu_oracle):

@@ -35,10 +35,12 @@ def main():
         ("ring_intblend", dict(blend_variant=0)),
         ("ldg_red", dict(ring=0)),
         ("ldg_atomg", dict(ring=0, zmin_variant=21)),
-        ("all_ring", dict(chunk_cull=0)),
+        ("all_ring", dict(chunk_cull=0, ring=2)),
+        ("all_ring_noperm", dict(chunk_cull=0, ring=2, ring_perm=0)),
+        ("all_ring_nored", dict(chunk_cull=0, ring=2, zmin_variant=13)),
         ("all_ldg_red", dict(ring=0, chunk_cull=0)),
     ]
-    defaults = dict(ring=1, zmin_variant=5, blend_variant=4, chunk_cull=1, fused_up=1)
+    defaults = dict(ring=1, zmin_variant=5, blend_variant=4, chunk_cull=1, fused_up=1, ring_perm=1)
     stage_times(pc, pkg, poses, len(poses))  # warm-up
     for name, opts in combos:
         for k, v in {**defaults, **opts}.items():
