@@ -383,9 +383,9 @@ def run_b200(args, wl):
     dom_ms = max(stage_ms[1], stage_ms[2])
     kl = kernel_line(dom_ms, streamed)
     roofline = {"bound": "hbm",
-                "kernel": (f"{dom}_list_kernel (walks the frame's visible 1024-point chunks: 16 B/point read for the "
-                           f"{streamed / count * 100:.1f}% of the cloud inside or near the frustum)") if culling
-                else f"{dom}_kernel (every point streamed, 16 B/point read)",
+                "kernel": (f"{dom}_{'ring' if pc.get_option('ring') else 'list'}_kernel (walks the frame's visible 1024-point chunks: 16 B/point "
+                           f"read for the {streamed / count * 100:.1f}% of the cloud inside or near the frustum)") if culling
+                else f"{dom}_{'ring_' if pc.get_option('ring') == 2 else ''}kernel (every point streamed, 16 B/point read)",
                 "achieved": kl["achieved"], "peak": peak, "unit": "GB/s", "frac": kl["frac"],
                 "frac_of_nominal_8TBps": kl["frac_of_nominal_8TBps"], "peak_source": peak_src, "traffic": None,
                 "launch_ms": dom_ms, "algorithmic_bytes_per_launch": 16.0 * streamed,
@@ -470,7 +470,7 @@ def run_b200(args, wl):
                                     ("point-sharded, ncclAllReduce min/sum" if args.nccl else "point-sharded, two-shot min/sum all-reduce kernels over NVLink peer memory")),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
                        "distortion": bool(args.distort),
-                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "zmin_variant", "zmin_unroll", "blend_variant", "blend_unroll", "key64")}},
+                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "fused_up", "zmin_variant", "blend_variant", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

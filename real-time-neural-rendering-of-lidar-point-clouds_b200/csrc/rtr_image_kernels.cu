@@ -46,6 +46,27 @@ __device__ __forceinline__ uint4 accum_as_u32(const uint4 raw, bool f32acc, uint
                       __float2uint_rz(__uint_as_float(raw.z)), __float2uint_rz(c));
 }
 
+// resolvePass on float accumulators: floor(sum / count) per channel without the three 32-bit integer divisions.
+// sum and count are exact integers (sum < 2^24, count <= kF32ExactCount, else the frame is flagged and redone with
+// integer sums), so q = floor(sum * rcp(count)) is off by at most one (|error| <= 255 * 2^-22) and the remainder
+// sum - q * count, exact in one FMA, says which way.
+__device__ __forceinline__ uint8_t floor_div_exact(float s, float c, float rc) {
+    float q = floorf(__fmul_rn(s, rc));
+    const float rem = __fmaf_rn(-q, c, s);
+    if (rem < 0.0f) q -= 1.0f;
+    else if (rem >= c) q += 1.0f;
+    return uint8_t(__float2uint_rz(q));
+}
+__device__ __forceinline__ void resolve_px_f32(const uint4 raw, uint32_t* __restrict__ overflow, uint8_t& b, uint8_t& g, uint8_t& r) {
+    const float c = __uint_as_float(raw.w);
+    if (c > kF32ExactCount) *overflow = 1u;
+    if (c == 0.0f) { b = g = r = 0; return; }  // render.cu:147-154
+    const float rc = __frcp_rn(c);
+    b = floor_div_exact(__uint_as_float(raw.x), c, rc);
+    g = floor_div_exact(__uint_as_float(raw.y), c, rc);
+    r = floor_div_exact(__uint_as_float(raw.z), c, rc);
+}
+
 template <bool PYRAMID, bool RESOLVE, bool F32ACC>
 __global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __restrict__ zbuf,
                                                               const uint4* __restrict__ accum,
@@ -69,13 +90,19 @@ __global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __
         const uint2 z0 = *reinterpret_cast<const uint2*>(zbuf + p0);
         const uint2 z1 = *reinterpret_cast<const uint2*>(zbuf + p1);
         if constexpr (RESOLVE) {
-            const uint4 a00 = accum_as_u32(accum[p0], F32ACC, minmax + 2), a01 = accum_as_u32(accum[p0 + 1], F32ACC, minmax + 2),
-                        a10 = accum_as_u32(accum[p1], F32ACC, minmax + 2), a11 = accum_as_u32(accum[p1 + 1], F32ACC, minmax + 2);
+            const uint4 a00 = accum[p0], a01 = accum[p0 + 1], a10 = accum[p1], a11 = accum[p1 + 1];
             uint8_t c[12];
-            resolve_px(a00, c[0], c[1], c[2]);
-            resolve_px(a01, c[3], c[4], c[5]);
-            resolve_px(a10, c[6], c[7], c[8]);
-            resolve_px(a11, c[9], c[10], c[11]);
+            if constexpr (F32ACC) {
+                resolve_px_f32(a00, minmax + 2, c[0], c[1], c[2]);
+                resolve_px_f32(a01, minmax + 2, c[3], c[4], c[5]);
+                resolve_px_f32(a10, minmax + 2, c[6], c[7], c[8]);
+                resolve_px_f32(a11, minmax + 2, c[9], c[10], c[11]);
+            } else {
+                resolve_px(a00, c[0], c[1], c[2]);
+                resolve_px(a01, c[3], c[4], c[5]);
+                resolve_px(a10, c[6], c[7], c[8]);
+                resolve_px(a11, c[9], c[10], c[11]);
+            }
             uint16_t* o0 = reinterpret_cast<uint16_t*>(image + p0 * 3);  // p0 is even -> 2-byte aligned
             uint16_t* o1 = reinterpret_cast<uint16_t*>(image + p1 * 3);
             o0[0] = uint16_t(c[0] | (c[1] << 8)); o0[1] = uint16_t(c[2] | (c[3] << 8)); o0[2] = uint16_t(c[4] | (c[5] << 8));
@@ -185,10 +212,11 @@ struct LoGlobal {
     int w;
     __device__ __forceinline__ float operator()(int x, int y) const { return p[y * w + x]; }
 };
+template <int STRIDE>  // compile-time row stride: the staged rectangle sits in the top-left corner of a fixed-size array
 struct LoShared {
     const float* p;
-    int x0, y0, w;
-    __device__ __forceinline__ float operator()(int x, int y) const { return p[(y - y0) * w + (x - x0)]; }
+    int x0, y0;
+    __device__ __forceinline__ float operator()(int x, int y) const { return p[(y - y0) * STRIDE + (x - x0)]; }
 };
 
 // bilinear hole fill of one fine pixel (resizeKernel, project_cloud.cu:135-160; op order from SASS)
@@ -330,7 +358,7 @@ __global__ void __launch_bounds__(256) up_level_kernel(const float* __restrict__
                 t[0][j] = half_div(float(c[3 * j + 0]), 255.0f);
                 t[1][j] = half_div(float(c[3 * j + 1]), 255.0f);
                 t[2][j] = half_div(float(c[3 * j + 2]), 255.0f);
-                t[3][j] = half_div(255.0f, 255.0f);
+                t[3][j] = 0x3C00u;  // half(float(half(255)) / 255) = 1.0h
                 t[4][j] = half_div(__fsub_rn(cur[j], dmin), range);
             }
         }
@@ -445,7 +473,7 @@ __device__ __forceinline__ void up_final_group(const Lo& lo, int lw, int lh, flo
                 tp[1][j] = half_div(float(c[3 * j + 1]), 255.0f);
                 tp[2][j] = half_div(float(c[3 * j + 2]), 255.0f);
             }
-            tp[3][j] = half_div(255.0f, 255.0f);
+            tp[3][j] = 0x3C00u;  // half(float(half(255)) / 255) = 1.0h: x / x is exactly 1 in IEEE arithmetic
             tp[4][j] = half_div(__fsub_rn(cur[j], dmin), range);
         }
     }
@@ -503,16 +531,27 @@ __device__ __forceinline__ UpRect up_parent_rect(const UpRect f, int lw, int lh)
     const int y0 = max((f.y0 >> 1) - 1, 0), y1 = min(((f.y0 + f.h - 1) >> 1) + 1, lh - 1);
     return UpRect{x0, y0, x1 - x0 + 1, y1 - y0 + 1};
 }
+// SW x SH = the array's fixed size (>= the clipped rectangle r); thread t handles local pixel (t % SW, t / SW)
+template <int SW, int SH>
 __device__ __forceinline__ void up_stage_rect(float* dst, const float* __restrict__ src, int src_w, const UpRect r) {
-    for (int i = threadIdx.x; i < r.w * r.h; i += blockDim.x) dst[i] = src[(r.y0 + i / r.w) * src_w + r.x0 + i % r.w];
+#pragma unroll
+    for (int i = threadIdx.x; i < SW * SH; i += 256) {
+        const int lx = i % SW, ly = i / SW;
+        if (lx < r.w && ly < r.h) dst[i] = src[(r.y0 + ly) * src_w + r.x0 + lx];
+    }
 }
 // hole-fill rectangle rf of the fine level in place in shared memory from the staged coarse level
+template <int FW, int FH, int CW>
 __device__ __forceinline__ void up_fill_rect(float* fine, const UpRect rf, const float* coarse, const UpRect rc, int lw, int lh) {
-    const LoShared lo{coarse, rc.x0, rc.y0, rc.w};
-    for (int i = threadIdx.x; i < rf.w * rf.h; i += blockDim.x) {
-        const int x = rf.x0 + i % rf.w, y = rf.y0 + i / rf.w;
-        const float cur = fine[i];
-        if (!up_keep_t(lo, lw, lh, x >> 1, y >> 1, cur)) fine[i] = bilinear_up_t(lo, lw, lh, x, y);
+    const LoShared<CW> lo{coarse, rc.x0, rc.y0};
+#pragma unroll
+    for (int i = threadIdx.x; i < FW * FH; i += 256) {
+        const int lx = i % FW, ly = i / FW;
+        if (lx < rf.w && ly < rf.h) {
+            const int x = rf.x0 + lx, y = rf.y0 + ly;
+            const float cur = fine[i];
+            if (!up_keep_t(lo, lw, lh, x >> 1, y >> 1, cur)) fine[i] = bilinear_up_t(lo, lw, lh, x, y);
+        }
     }
 }
 
@@ -520,10 +559,12 @@ __global__ void __launch_bounds__(256, 4) up_fused_kernel(const float* __restric
                                                        const float* __restrict__ l3, const float* __restrict__ l4,
                                                        int w4, int h4, float* __restrict__ l0, uint8_t* __restrict__ image,
                                                        uint16_t* __restrict__ tensor, const uint32_t* __restrict__ minmax) {
-    __shared__ float s1[(kUpT1W + 2) * (kUpT1H + 2)];
-    __shared__ float s2[(kUpT1W / 2 + 4) * (kUpT1H / 2 + 4)];
-    __shared__ float s3[(kUpT1W / 4 + 4) * (kUpT1H / 4 + 4)];
-    __shared__ float s4[(kUpT1W / 8 + 4) * (kUpT1H / 8 + 4)];
+    constexpr int S1W = kUpT1W + 2, S1H = kUpT1H + 2, S2W = kUpT1W / 2 + 4, S2H = kUpT1H / 2 + 4, S3W = kUpT1W / 4 + 4,
+                  S3H = kUpT1H / 4 + 4, S4W = kUpT1W / 8 + 4, S4H = kUpT1H / 8 + 4;
+    __shared__ float s1[S1W * S1H];
+    __shared__ float s2[S2W * S2H];
+    __shared__ float s3[S3W * S3H];
+    __shared__ float s4[S4W * S4H];
     __shared__ uint16_t lut[256];
     lut[threadIdx.x] = half_div(float(threadIdx.x), 255.0f);  // removeMask's value for image byte threadIdx.x
     pdl_prologue();
@@ -546,20 +587,20 @@ __global__ void __launch_bounds__(256, 4) up_fused_kernel(const float* __restric
     // level-1 pixels the level-0 tile reads: the tile's parents and one ring around them; and so on upwards
     const UpRect r1 = up_parent_rect(UpRect{core.x0 * 2, core.y0 * 2, core.w * 2, core.h * 2}, w1, h1);
     const UpRect r2 = up_parent_rect(r1, w2, h2), r3 = up_parent_rect(r2, w3, h3), r4 = up_parent_rect(r3, w4, h4);
-    up_stage_rect(s4, l4, w4, r4);
-    up_stage_rect(s3, l3, w3, r3);
-    up_stage_rect(s2, l2, w2, r2);
-    up_stage_rect(s1, l1, w1, r1);
+    up_stage_rect<S4W, S4H>(s4, l4, w4, r4);
+    up_stage_rect<S3W, S3H>(s3, l3, w3, r3);
+    up_stage_rect<S2W, S2H>(s2, l2, w2, r2);
+    up_stage_rect<S1W, S1H>(s1, l1, w1, r1);
     const float dmin = __uint_as_float(minmax[0]), dmax = __uint_as_float(minmax[1]);
     __syncthreads();
-    up_fill_rect(s3, r3, s4, r4, w4, h4);
+    up_fill_rect<S3W, S3H, S4W>(s3, r3, s4, r4, w4, h4);
     __syncthreads();
-    up_fill_rect(s2, r2, s3, r3, w3, h3);
+    up_fill_rect<S2W, S2H, S3W>(s2, r2, s3, r3, w3, h3);
     __syncthreads();
-    up_fill_rect(s1, r1, s2, r2, w2, h2);
+    up_fill_rect<S1W, S1H, S2W>(s1, r1, s2, r2, w2, h2);
     __syncthreads();
     if (mine)
-        up_final_group(LoShared{s1, r1.x0, r1.y0, r1.w}, w1, h1, l0, nullptr, image, tensor, dmin, __fsub_rn(dmax, dmin), lx0, hy, c0, c1, iw, lut);
+        up_final_group(LoShared<S1W>{s1, r1.x0, r1.y0}, w1, h1, l0, nullptr, image, tensor, dmin, __fsub_rn(dmax, dmin), lx0, hy, c0, c1, iw, lut);
 }
 
 // ---------------------------------------------------------------- launchers

@@ -54,6 +54,7 @@ struct rtr_renderer {
     int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
     int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1, sort_on_upload = 1;
     int fused_up = 1;  // the four up-pass levels in one launch (needs W % 16 == 0 and keep_masks = 0)
+    int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)
     int ring_perm = 1;  // stream-all ring passes visit the chunks in a low-discrepancy order (0: storage order)
     int ring = 1;  // point passes through the TMA-fed persistent kernels: 1 = for culled frames, 2 = always, 0 = never
     cudaEvent_t ev[6] = {nullptr};

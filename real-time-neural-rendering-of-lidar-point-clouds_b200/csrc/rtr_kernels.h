@@ -95,6 +95,7 @@ struct RingSchedule {
     const uint32_t* vis_list;
     uint32_t n_chunks;
     uint32_t perm_mul;
+    uint32_t early;  // blend pass over the list: request the first chunks before the PDL wait (0: measurement only)
 };
 RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const uint32_t* vis_list);
 cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,

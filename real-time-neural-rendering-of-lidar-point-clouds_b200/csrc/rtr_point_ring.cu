@@ -84,10 +84,11 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint3
         : "memory");
 }
 
-// Which chunk tile number t of this launch is.
+// Which chunk tile number t of this launch is.  l2 = true: read the list through L2 (used before the PDL wait, when
+// this SM's L1 may still hold last frame's list).
 template <bool LIST>
-__device__ __forceinline__ uint32_t tile_chunk(const RingSchedule& sc, uint32_t t) {
-    if constexpr (LIST) return __ldg(sc.vis_list + t);
+__device__ __forceinline__ uint32_t tile_chunk(const RingSchedule& sc, uint32_t t, bool l2 = false) {
+    if constexpr (LIST) return l2 ? __ldcg(sc.vis_list + t) : __ldg(sc.vis_list + t);
     else return uint32_t((uint64_t(t) * sc.perm_mul) % sc.n_chunks);
 }
 
@@ -98,10 +99,19 @@ __device__ __forceinline__ uint32_t tile_chunk(const RingSchedule& sc, uint32_t 
 // tiles out through an atomic counter instead was measured slower — the counter's round trip sits on the refilling
 // thread's path — and leaving the z-min pass's last chunks in L2 for a backwards blend pass was slower too: the
 // streamed lines displace the z-buffer / accumulator lines the REDs need.  profiles/r01h_exp_ring_dynamic.json)
+//
+// early: the tile list is older than the previous grid (the blend pass: the list was built before the z-min pass),
+// so the first kRingStages chunks of the CTA are requested BEFORE the PDL wait and land while the previous grid drains.
+// Either way this function executes the PDL prologue exactly once for every thread.
 template <bool LIST, typename Consume>
 __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, uint64_t n, const RingSchedule& sc,
-                                          RingSmem& sm, Consume&& consume) {
-    const uint32_t n_tiles = LIST ? cull_count(sc.cull) : sc.n_chunks;
+                                          RingSmem& sm, const bool early, Consume&& consume) {
+    if (!early) pdl_prologue();
+    uint32_t n_tiles = sc.n_chunks;
+    if constexpr (LIST) {
+        const uint32_t* nv = sc.cull->n_visible;
+        n_tiles = early ? __ldcg(nv + (__ldcg(&sc.cull->parity) & 1u)) : cull_count(sc.cull);
+    }
     const uint32_t G = gridDim.x;
     // Group g takes k = g, g + kRingGroups, ...; its thread 0 is also the producer of those tiles: once every warp of
     // the group has copied a tile's records into registers (the stage's `empty` barrier) it streams the tile
@@ -124,9 +134,10 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
 #pragma unroll
         for (uint32_t k = group; k < uint32_t(kRingStages); k += kRingGroups) {
             const uint32_t t = blockIdx.x + k * G;
-            if (t < n_tiles) issue(k, tile_chunk<LIST>(sc, t));
+            if (t < n_tiles) issue(k, tile_chunk<LIST>(sc, t, early));
         }
     }
+    if (early) pdl_prologue();
     // Thread i of a group owns records 4i..4i+3 of the chunk.  A 128-bit LDS is served 8 lanes at a time; lane l reads
     // its record s ^ ((l >> 1) & 3) at step s, so that the 8 lanes of a phase touch 8 different 16-byte bank groups
     // (address/16 mod 8 = 4(l&1) + (s ^ (l>>1 & 3))): conflict-free without padding, one XOR per load.
@@ -186,8 +197,7 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) zmin_ring_kernel
                                                                  uint32_t* __restrict__ zbuf,
                                                                  unsigned long long* __restrict__ zkey) {
     RingSmem& sm = ring_setup();  // touches shared memory only: overlaps the previous grid's tail
-    pdl_prologue();
-    ring_walk<LIST>(pts, n, sc, sm, [&](const PointRecord (&p)[kRingPerThread], uint32_t chunk, uint32_t first, uint32_t rot, uint32_t valid) {
+    ring_walk<LIST>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t chunk, uint32_t first, uint32_t rot, uint32_t valid) {
         uint32_t pix[kRingPerThread];
         using Key = std::conditional_t<KEY64 != 0, unsigned long long, uint32_t>;
         Key key[kRingPerThread];  // KEY64: (depth bits << 32) | global index ; else the depth bits
@@ -259,8 +269,9 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) blend_ring_kerne
                                                                   const uint32_t* __restrict__ zbuf,
                                                                   unsigned long long* __restrict__ accum2) {
     RingSmem& sm = ring_setup();
-    pdl_prologue();
-    ring_walk<LIST>(pts, n, sc, sm, [&](const PointRecord (&p)[kRingPerThread], uint32_t, uint32_t, uint32_t rot, uint32_t valid) {
+    // early: the visible list this pass walks is older than the grid in front of it (the z-min pass or the merge of
+    // the same frame), so its first chunks are requested before the PDL wait
+    ring_walk<LIST>(pts, n, sc, sm, LIST && sc.early != 0u, [&](const PointRecord (&p)[kRingPerThread], uint32_t, uint32_t, uint32_t rot, uint32_t valid) {
         uint32_t pix[kRingPerThread];
         float depth[kRingPerThread];
         bool live[kRingPerThread];
@@ -314,6 +325,7 @@ RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const 
     RingSchedule sc;
     sc.cull = cull;
     sc.vis_list = vis_list;
+    sc.early = 1;
     sc.n_chunks = uint32_t((n_points + kChunkPoints - 1) / kChunkPoints);
     // golden-ratio stride, made coprime with n_chunks: t -> (t * mul) mod n_chunks is a permutation whose every
     // window of consecutive t is spread evenly over the cloud

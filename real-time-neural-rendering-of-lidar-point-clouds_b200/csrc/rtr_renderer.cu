@@ -327,6 +327,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     }
     RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
     if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
+    sched.early = r->ring_early ? 1u : 0u;
     sched.cull = cull ? r->cull_state : nullptr;
     sched.vis_list = cull ? r->vis_list : nullptr;
 
@@ -868,6 +869,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "ring")) return &r->ring;
     if (!std::strcmp(key, "fused_up")) return &r->fused_up;
     if (!std::strcmp(key, "ring_perm")) return &r->ring_perm;
+    if (!std::strcmp(key, "ring_early")) return &r->ring_early;
     return nullptr;
 }
 
