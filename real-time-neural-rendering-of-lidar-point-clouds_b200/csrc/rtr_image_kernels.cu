@@ -211,12 +211,14 @@ struct LoGlobal {
     const float* __restrict__ p;
     int w;
     __device__ __forceinline__ float operator()(int x, int y) const { return p[y * w + x]; }
+    __device__ __forceinline__ const float* row(int y) const { return p + y * w; }  // row(y)[x] == (*this)(x, y)
 };
 template <int STRIDE>  // compile-time row stride: the staged rectangle sits in the top-left corner of a fixed-size array
 struct LoShared {
     const float* p;
     int x0, y0;
     __device__ __forceinline__ float operator()(int x, int y) const { return p[(y - y0) * STRIDE + (x - x0)]; }
+    __device__ __forceinline__ const float* row(int y) const { return p + ((y - y0) * STRIDE - x0); }
 };
 
 // bilinear hole fill of one fine pixel (resizeKernel, project_cloud.cu:135-160; op order from SASS)
@@ -397,10 +399,14 @@ __device__ __forceinline__ void up_final_group(const Lo& lo, int lw, int lh, flo
         // by an interior parent, and border parents do not use the window at all)
         float w[3][6];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int y = min(max(ly + r - 1, 0), lh - 1);
+        const int xl = max(lx0 - 1, 0), xr = min(lx0 + 4, lw - 1);  // only the window's outer columns can leave the level
 #pragma unroll
-            for (int c = 0; c < 6; ++c) w[r][c] = lo(min(max(lx0 + c - 1, 0), lw - 1), y);
+        for (int r = 0; r < 3; ++r) {
+            const float* row = lo.row(min(max(ly + r - 1, 0), lh - 1));
+            w[r][0] = row[xl];
+#pragma unroll
+            for (int c = 1; c < 5; ++c) w[r][c] = row[lx0 + c - 1];
+            w[r][5] = row[xr];
         }
         const bool row_border = (ly == 0 || ly == lh - 1);
 #pragma unroll
