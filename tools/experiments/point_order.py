@@ -2,8 +2,9 @@
 """Experiment: effect of point order (synthetic patch order / cell-binned / Morton) on the point passes."""
 import json, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import __graft_entry__ as entry
 import bench
 from sweep import stage_times

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Experiment: RED flavours for the blend accumulator (measurement only)."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import __graft_entry__ as entry
 import bench
 pkg = entry.load_package()

@@ -8,11 +8,12 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import __graft_entry__ as entry  # noqa: E402
 import bench  # noqa: E402
-from tools.sweep import stage_times  # noqa: E402
+from sweep import stage_times  # noqa: E402
 
 NAMES = ["clear_classify", "zmin", "blend", "resolve_pyramid", "up_pass", "frame"]
 

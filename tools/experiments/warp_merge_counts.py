@@ -3,8 +3,9 @@
 Counts, over the in-frustum points of a few poses: lanes, adjacent-equal runs per 32-lane warp, distinct pixels per warp."""
 import json, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import __graft_entry__ as entry
 import bench
 pkg = entry.load_package()
