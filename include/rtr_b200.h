@@ -148,6 +148,12 @@ uint64_t rtr_launch_count(const rtr_renderer* r);
 int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int iters, float* ms_per_launch,
                       uint64_t* live_ops);
 
+/* Host-only helper (no GPU needed; what the renderer uses internally for a camera with distortion coefficients):
+ * r2_max = squared normalised radius beyond which the distorted projection culls a point (fold-back guard),
+ * rstar  = normalised, undistorted radius beyond which no point can reach the W x H image (0: unknown) — the bound
+ * the chunk-level culling tests against.  K9 row-major 3x3, dist5 = k1, k2, p1, p2, k3. */
+int rtr_host_distortion_bounds(int width, int height, const double* K9, const double* dist5, double* r2_max, double* rstar);
+
 /* Device self-test of the ring kernels' perspective divide: for n_pairs random bit patterns (a, b) (every class of
  * float: NaN, inf, denormal, huge) checks on the GPU that whenever !(|b| < 2^-126) the directly issued
  * MUFU.RCP + FMUL gives the same bits as __fdividef(a, b) (what the reference compiles, render.cu:65-66), and the same

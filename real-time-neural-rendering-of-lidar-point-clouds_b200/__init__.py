@@ -66,6 +66,7 @@ API = {
     "rtr_launch_count": (_u64, [_vp]),
     "rtr_bench_red_min": (_i, [_vp, _i, _u64, _i, _i, _fp, C.POINTER(_u64)]),
     "rtr_selftest_fast_divide": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),
+    "rtr_host_distortion_bounds": (_i, [_i, _i, _dp, _dp, _dp, _dp]),
     "rtr_comm_unique_id": (_i, [_vp]),
     "rtr_comm_init": (_i, [_vp, _vp, _i, _i]),
     "rtr_comm_destroy": (_i, [_vp]),

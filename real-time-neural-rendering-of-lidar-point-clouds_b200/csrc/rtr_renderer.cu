@@ -188,41 +188,10 @@ int make_params(rtr_renderer* r, ProjParams& pp) {
         pp.fy = float(r->K[4]); pp.cy = float(r->K[5]);
         pp.k1 = float(r->dist[0]); pp.k2 = float(r->dist[1]); pp.p1 = float(r->dist[2]);
         pp.p2 = float(r->dist[3]); pp.k3 = float(r->dist[4]);
-        // Cull beyond 1.5x the farthest image corner in normalised coordinates, or where the
-        // radial polynomial stops being monotone (fold-back of far off-axis points).
-        double rmax2 = 0;
-        const double xs[2] = {(0 - r->K[2]) / r->K[0], (r->W - 1 - r->K[2]) / r->K[0]};
-        const double ys[2] = {(0 - r->K[5]) / r->K[4], (r->H - 1 - r->K[5]) / r->K[4]};
-        for (double x : xs) for (double y : ys) rmax2 = std::fmax(rmax2, x * x + y * y);
-        double lim = rmax2 * 2.25 * 4.0;  // undistorted radius can exceed the distorted one; generous
-        const double k1 = r->dist[0], k2 = r->dist[1], k3 = r->dist[4];
-        for (int i = 1; i <= 4096; ++i) {  // first r2 where d/dr [ r (1 + k1 r2 + k2 r4 + k3 r6) ] <= 0
-            const double r2 = lim * i / 4096.0;
-            const double deriv = 1 + 3 * k1 * r2 + 5 * k2 * r2 * r2 + 7 * k3 * r2 * r2 * r2;
-            if (deriv <= 0) { lim = lim * (i - 1) / 4096.0; break; }
-        }
-        pp.r2_max = float(lim);
-        // Radius r* (normalised, undistorted) beyond which no point can land in the image — what chunk culling uses
-        // under distortion (enqueue_frame).  A visible point has (xd, yd) inside the image's parallelogram in
-        // normalised distorted coordinates, i.e. |(xd, yd)| <= R_d, and |(xd, yd)| >= r |radial(r^2)| - T r^2 with
-        // T = 4.3 (|p1| + |p2|) bounding the tangential terms.  r* = the largest sampled r in [0, sqrt(r2_max)] that
-        // still satisfies g(r) = r |radial| - T r^2 <= R_d (with 0.1 % slack), plus 1 %.
-        const double p1 = r->dist[2], p2 = r->dist[3], T = 4.3 * (std::fabs(p1) + std::fabs(p2));
-        double Rd = 0;
-        const double us[2] = {-0.5, r->W - 0.5}, vs[2] = {-0.5, r->H - 0.5};
-        for (double v : vs) for (double u : us) {
-            const double yd = (v - r->K[5]) / r->K[4], xd = (u - r->K[2] - r->K[1] * yd) / r->K[0];
-            Rd = std::fmax(Rd, std::sqrt(xd * xd + yd * yd));
-        }
-        const double rmax = std::sqrt(lim);
-        double rstar = 0;
-        for (int i = 0; i <= 8192; ++i) {
-            const double rr = rmax * i / 8192.0, q = rr * rr;
-            const double g = rr * std::fabs(1 + k1 * q + k2 * q * q + k3 * q * q * q) - T * q;
-            if (g <= Rd * 1.001) rstar = rr;
-        }
-        r->cull_rstar = std::fmin(rstar + rmax / 8192.0, rmax) * 1.01;
-        if (!(Rd > 0) || !std::isfinite(r->cull_rstar)) r->cull_rstar = 0;  // 0 = no culling under this camera
+        double r2_max = 0, rstar = 0;
+        rtr_host_distortion_bounds(r->W, r->H, r->K, r->dist, &r2_max, &rstar);
+        pp.r2_max = float(r2_max);
+        r->cull_rstar = rstar;
     }
     return RTR_OK;
 }
@@ -442,6 +411,47 @@ int render_to_host(rtr_renderer* r, int stage, uint8_t* bgr, float* depth) {
 }
 
 }  // namespace
+
+extern "C" int rtr_host_distortion_bounds(int W, int H, const double* K9, const double* dist5, double* r2_max, double* rstar) {
+    if (!K9 || !dist5 || !r2_max || !rstar || W < 1 || H < 1) return RTR_ERR_ARG;
+    const double* K = K9;
+    // r2_max: points are culled beyond 3x the farthest image corner in normalised coordinates, or where the radial
+    // polynomial stops being monotone (fold-back of far off-axis points).
+    double rmax2 = 0;
+    const double xs[2] = {(0 - K[2]) / K[0], (W - 1 - K[2]) / K[0]};
+    const double ys[2] = {(0 - K[5]) / K[4], (H - 1 - K[5]) / K[4]};
+    for (double x : xs) for (double y : ys) rmax2 = std::fmax(rmax2, x * x + y * y);
+    double lim = rmax2 * 2.25 * 4.0;  // undistorted radius can exceed the distorted one; generous
+    const double k1 = dist5[0], k2 = dist5[1], k3 = dist5[4];
+    for (int i = 1; i <= 4096; ++i) {  // first r2 where d/dr [ r (1 + k1 r2 + k2 r4 + k3 r6) ] <= 0
+        const double r2 = lim * i / 4096.0;
+        const double deriv = 1 + 3 * k1 * r2 + 5 * k2 * r2 * r2 + 7 * k3 * r2 * r2 * r2;
+        if (deriv <= 0) { lim = lim * (i - 1) / 4096.0; break; }
+    }
+    *r2_max = double(float(lim));  // the kernel compares in float
+    // r*: radius (normalised, undistorted) beyond which no point can land in the image — what chunk culling uses under
+    // distortion (enqueue_frame).  A visible point has (xd, yd) inside the image's parallelogram in normalised
+    // distorted coordinates, i.e. |(xd, yd)| <= R_d, and |(xd, yd)| >= r |radial(r^2)| - T r^2, where
+    // T = 4.3 (|p1| + |p2|) >= sqrt(10) (|p1| + |p2|) bounds the tangential terms.  r* = the largest sampled r in
+    // [0, sqrt(r2_max)] that still satisfies g(r) = r |radial| - T r^2 <= R_d (0.1 % slack), plus one step and 1 %.
+    const double p1 = dist5[2], p2 = dist5[3], T = 4.3 * (std::fabs(p1) + std::fabs(p2));
+    double Rd = 0;
+    const double us[2] = {-0.5, W - 0.5}, vs[2] = {-0.5, H - 0.5};
+    for (double v : vs) for (double u : us) {
+        const double yd = (v - K[5]) / K[4], xd = (u - K[2] - K[1] * yd) / K[0];
+        Rd = std::fmax(Rd, std::sqrt(xd * xd + yd * yd));
+    }
+    const double rmax = std::sqrt(*r2_max);
+    double best = 0;
+    for (int i = 0; i <= 8192; ++i) {
+        const double rr = rmax * i / 8192.0, q = rr * rr;
+        const double g = rr * std::fabs(1 + k1 * q + k2 * q * q + k3 * q * q * q) - T * q;
+        if (g <= Rd * 1.001) best = rr;
+    }
+    *rstar = std::fmin(best + rmax / 8192.0, rmax) * 1.01;
+    if (!(Rd > 0) || !std::isfinite(*rstar)) *rstar = 0;  // 0 = no culling under this camera
+    return RTR_OK;
+}
 
 extern "C" {
 

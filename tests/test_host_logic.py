@@ -53,3 +53,36 @@ def test_device_buffers_struct_matches_header(pkg):
     import ctypes as C
     # rtr_device_buffers: 6 pointers + 5 + 4 pointers, 2 ints, 4 x 5 ints, u64, pointer
     assert C.sizeof(pkg.DeviceBuffers) == 15 * 8 + 2 * 4 + 20 * 4 + 8 + 8
+
+
+def test_distortion_cull_radius_bounds_every_visible_point(pkg):
+    """rtr_host_distortion_bounds (host code, what chunk culling under lens distortion rests on): no point whose
+    distorted projection (OpenCV model, float64) rounds to a pixel of the image may lie beyond r*."""
+    import ctypes as C
+    lib = pkg.load_library()
+    rng = np.random.default_rng(5)
+    dists = [[-0.05, 0.01, 0.0005, -0.0005, 0.0], [0.2, 0.05, 0.0, 0.0, 0.01], [-0.3, 0.1, 0.0, 0.0, -0.01],
+             [0.0, 0.0, 0.02, -0.03, 0.0], [-0.2, 0.03, 0.01, 0.01, 0.001], [1e-9, 0.0, 0.0, 0.0, 0.0], [0.5, 0.0, 0.05, 0.05, 0.0]]
+    effective = 0
+    for it in range(40):
+        W, H = int(rng.choice([320, 640, 1280, 1920])), int(rng.choice([208, 480, 720, 1080]))
+        f = float(rng.uniform(0.3, 1.5) * W)
+        K = np.array([f, float(rng.uniform(-2, 2)), rng.uniform(0.3 * W, 0.7 * W), 0, f * rng.uniform(0.9, 1.1), rng.uniform(0.3 * H, 0.7 * H), 0, 0, 1], np.float64)
+        d = np.array(dists[it % len(dists)], np.float64)
+        r2max, rstar = C.c_double(0), C.c_double(0)
+        assert lib.rtr_host_distortion_bounds(W, H, K.ctypes.data_as(pkg._dp), d.ctypes.data_as(pkg._dp), C.byref(r2max), C.byref(rstar)) == pkg.RTR_OK
+        rmax = np.sqrt(r2max.value)
+        rr = np.linspace(0, rmax, 1500)[:, None]
+        th = np.linspace(0, 2 * np.pi, 720, endpoint=False)[None, :]
+        x, y = rr * np.cos(th), rr * np.sin(th)
+        r2 = x * x + y * y
+        radial = 1 + d[0] * r2 + d[1] * r2 ** 2 + d[4] * r2 ** 3
+        xd = x * radial + 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x)
+        yd = y * radial + d[2] * (r2 + 2 * y * y) + 2 * d[3] * x * y
+        u, v = np.rint(K[0] * xd + K[1] * yd + K[2]), np.rint(K[4] * yd + K[5])
+        vis = (u >= 0) & (u < W) & (v >= 0) & (v < H)
+        assert vis.any()
+        far = np.sqrt(r2[vis]).max()
+        assert rstar.value == 0 or far <= rstar.value, (it, far, rstar.value)
+        effective += 0 < rstar.value < 0.8 * rmax
+    assert effective >= 30      # the bound is tight enough to cull for most cameras
