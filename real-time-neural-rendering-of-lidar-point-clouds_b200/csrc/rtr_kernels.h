@@ -71,6 +71,31 @@ inline void launch_pdl_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// For kernels with a grid-wide spin barrier (exact_fixup_kernel): the cooperative attribute makes the driver guarantee
+// that all CTAs are co-resident — or run the grid after whatever occupies the SMs — also when another renderer shares
+// the GPU.  Falls back to the plain PDL launch if the driver rejects the combination of attributes.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+    static bool coop_ok = true;
+    if (coop_ok) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        if (cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...) == cudaSuccess) return;
+        (void)cudaGetLastError();
+        coop_ok = false;
+    }
+    launch_pdl_smem(kernel, grid, block, 0, s, static_cast<Args&&>(args)...);
+}
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
     launch_pdl_smem(kernel, grid, block, 0, s, static_cast<Args&&>(args)...);

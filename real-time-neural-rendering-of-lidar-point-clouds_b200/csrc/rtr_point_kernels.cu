@@ -246,9 +246,9 @@ __global__ void __launch_bounds__(kPointBlock) blend_list_kernel(const PointReco
 // One launch that almost always returns at once.  When resolve flagged a pixel beyond the exact range of
 // the float sums (minmax[2] != 0) it redoes the frame's colour sums with the integer REDs and resolves
 // again: clear accum -> blend (exact) -> resolve, separated by a grid-wide barrier.  The grid is 2 CTAs
-// per SM, all co-resident, so the spin barrier cannot deadlock (CTAs of the preceding kernel still
-// draining do not depend on this grid; PDL schedules the following kernel only after every CTA here
-// has started).
+// per SM and launched with the cooperative attribute, so all CTAs are co-resident and the spin barrier
+// cannot deadlock (CTAs of the preceding kernel still draining do not depend on this grid; PDL schedules
+// the following kernel only after every CTA here has started).
 __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -368,10 +368,10 @@ cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* 
     if (n == 0) return cudaSuccess;
     const dim3 grid(unsigned(sm_count) * 2u), block(kPointBlock);
     uint4* a4 = reinterpret_cast<uint4*>(accum);
-    if (cull && pp.distort) launch_pdl((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
-    else if (cull) launch_pdl((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
-    else if (pp.distort) launch_pdl((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
-    else launch_pdl((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    if (cull && pp.distort) launch_pdl_cooperative((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    else if (cull) launch_pdl_cooperative((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    else if (pp.distort) launch_pdl_cooperative((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    else launch_pdl_cooperative((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
     return cudaGetLastError();
 }
 
