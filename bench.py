@@ -418,7 +418,17 @@ def run_b200(args, wl):
     tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(f"{dom}_{args.workload}")
+            tj = json.load(open(tr))
+            roofline["traffic"] = tj.get(f"{dom}_{args.workload}")
+            ncu_at = tj.get(f"ncu_atomics_{args.workload}")
+            if ncu_at and "l2_atomics" in roofline and culling and pc.get_option("ring"):
+                # REDs really issued (ncu counters of the committed capture) against the measured random-address RED rate
+                # (one 32-byte sector per lane there): what fraction of the pass the reduction path alone accounts for
+                for name, st in (("zmin", stage_ms[1]), ("blend", stage_ms[2])):
+                    c = ncu_at.get(f"{name}_ring_kernel")
+                    if c:
+                        roofline["l2_atomics"][f"{name}_ncu"] = dict(c, red_sector_time_ms_at_measured_peak=c["red_sectors"] / (red_peak * 1e6),
+                                                                    frac_of_launch=c["red_sectors"] / (red_peak * 1e6) / st)
         except Exception:
             pass
 
