@@ -354,6 +354,36 @@ def test_nothing_in_frustum_and_single_point(gpu, cpu_oracle):
     assert (np.delete(out["depth"], pix) == 0x7F7FFFFF).all()
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 255, 1023, 1024, 1025, 2047, 4099, 6 * 1024 * 3 + 1])
+def test_cloud_sizes_around_chunk_and_ring_boundaries(gpu, cpu_oracle, n):
+    """Clouds of 1 .. a few chunks (partial last chunk, fewer chunks than ring stages, fewer tiles than CTAs): the
+    TMA-fed ring kernels (culled list and stream-all), the per-thread kernels and the CPU oracle must agree, in blend
+    and in 64-bit-key mode."""
+    case = scenes.CASES["small_160x96"]
+    rec = cpu_oracle.synth_packed(77, 20_000, 0, 20_000, case.hall, case.n_boxes)[:n].copy()
+    W, H, P = case.W, case.H, case.W * case.H
+    calib, E = calib_of(gpu, case), case.poses[0]
+    outs = {}
+    for name, opts in (("ring_list", dict(ring=1)), ("ring_all", dict(ring=2, chunk_cull=0)), ("ldg_list", dict(ring=0)),
+                       ("ldg_all", dict(ring=0, chunk_cull=0)), ("ring_key64", dict(ring=2, key64=1)), ("ldg_key64", dict(ring=0, key64=1))):
+        pc = gpu.ProjectCloud.from_packed(rec, sort=False)
+        for k, v in opts.items():
+            pc.set_option(k, v)
+        color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        assert pc.computeFilteredRGBD(calib, E, color, depth) == 1
+        outs[name] = (color, depth.view(np.uint32).copy(), pc.read("tensor", np.uint16, P * 5))
+        if name == "ring_list":
+            tap = pc.project_points()
+        pc.close()
+    gold = cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(rec), W, H, filtered=True)
+    for name in ("ring_list", "ring_all", "ldg_list", "ldg_all"):
+        assert np.array_equal(outs[name][0], gold["image"]) and np.array_equal(outs[name][1], gold["zbuf"]), name
+        assert np.array_equal(outs[name][2], gold["tensor"]), name
+    for a, b in zip(outs["ring_key64"], outs["ldg_key64"]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(outs["ring_key64"][1], gold["zbuf"])      # key64's depth is the reference depth
+
+
 def test_error_behaviour(gpu):
     pc = gpu.ProjectCloud()
     calib = gpu.CameraCalibration()
