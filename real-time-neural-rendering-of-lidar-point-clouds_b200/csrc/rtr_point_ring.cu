@@ -1,29 +1,28 @@
-// The two point passes as persistent, TMA-fed kernels (sm_100a) — the default since round 1h.
+// The two point passes as persistent, TMA-fed kernels (sm_100a) — the default for culled frames since round 1h.
 //
 //   zmin_ring_kernel   <- minDepthPass   (render.cu:53-83)
 //   blend_ring_kernel  <- accumulatePass (render.cu:85-130)
 //
-// What bounds the passes on B200 (ncu, profiles/r01g): not HBM but the SM's reduction path — a REDG
-// costs about 1.3 LSU cycles per active lane whatever its width — and, before this file, load
-// latency: with the cloud coming in through per-thread LDG.128 every warp serialised "chunk id ->
-// 16-byte records -> z-buffer gather -> RED" and sat on the long scoreboard.  Here
+// What bounded the passes on B200 (ncu, profiles/r01g): not HBM but load latency — with the cloud coming in through
+// per-thread LDG.128 every warp serialised "chunk id -> 16-byte records -> z-buffer gather -> atomic" and sat on the
+// long scoreboard — and the SM's reduction path (REDs leave an SM at about one 32-byte sector per clock).  Here
 //
-//  * whole 1024-record chunks (16 KB) are streamed into a 4-stage shared-memory ring with
-//    cp.async.bulk (TMA, L2 evict-first) signalled through mbarriers: a CTA is two groups of 256
-//    threads, each group consumes every other tile and its thread 0 refills a stage the moment the
-//    group has copied it into registers, so the HBM stream runs ahead of the arithmetic and costs no
-//    registers or LSU issue slots (3 CTAs = 48 warps and 12 chunks = 192 KB in flight per SM);
-//  * each thread of a group takes FOUR CONSECUTIVE records of the chunk.  The cloud is
-//    Morton-ordered, so these are spatial neighbours and mostly project to the same pixel wherever
-//    the scan is denser than the pixel grid (5 points per pixel on average at C3): they are merged
-//    in registers (min of the depth bits / sums of the colour bytes — both exact and order-free)
-//    before anything touches memory, which removes REDs rather than speeding them up;
+//  * whole 1024-record chunks (16 KB) are streamed into a 6-stage shared-memory ring with cp.async.bulk (TMA, L2
+//    evict-first) signalled through mbarriers: a CTA is two groups of 256 threads, each group consumes every other
+//    tile and its thread 0 refills a stage the moment the group has copied it into registers, so the HBM stream runs
+//    ahead of the arithmetic and costs no registers or LSU issue slots (2 CTAs = 32 warps and 12 chunks = 192 KB in
+//    flight per SM; 3 CTAs x 4 stages and a dedicated producer warp measured the same);
+//  * each thread of a group takes FOUR CONSECUTIVE records of the chunk.  The cloud is Morton-ordered, so these are
+//    spatial neighbours and mostly project to the same pixel wherever the scan is denser than the pixel grid (5
+//    points per pixel on average at C3): they are merged in registers (min of the depth bits / sums of the colour
+//    bytes — both exact and order-free) before anything touches memory, which removes REDs rather than speeding them
+//    up;
 //  * the survivors do the early depth test through L1 and one REDG each.
 //
-// The same kernels serve the culled frame (tiles = the frame's visible-chunk list) and the
-// stream-all frame (every chunk; tiles are visited in a low-discrepancy order so that at any moment
-// the CTAs in flight hold a mix of in-frustum and out-of-frustum chunks and the RED-bound and the
-// HBM-bound parts of the pass overlap instead of alternating).
+// The same kernels serve the culled frame (tiles = the frame's visible-chunk list; what option ring = 1 uses them
+// for) and, with ring = 2, the stream-all frame (every chunk, visited in a low-discrepancy order so that the CTAs in
+// flight hold a mix of in-frustum and out-of-frustum chunks; the per-thread LDG.128 kernels stream 4 % faster there
+// and stay the default for it).
 #include <type_traits>
 
 #include "rtr_kernels.h"
@@ -37,10 +36,10 @@ constexpr int kRingThreads = kRingGroups * kRingConsumers;  // 512: no dedicated
 constexpr int kRingCtasPerSm = 2;                     // 2 x (96 KB ring + barriers) per SM: 32 warps, up to 64 registers
 constexpr int kRingPerThread = kChunkPoints / kRingConsumers;
 static_assert(kRingStages % kRingGroups == 0, "every group must own a fixed subset of the stages");
-static_assert(kRingPerThread == 4, "the bank-conflict-free rotation below assumes 4 records per thread");
+static_assert(kRingPerThread == 4, "the bank-conflict-free XOR swizzle below assumes 4 records per thread");
 
 struct RingSmem {
-    PointRecord rec[kRingStages][kChunkPoints];  // 4 x 16 KB
+    PointRecord rec[kRingStages][kChunkPoints];  // 6 x 16 KB
     unsigned long long full[kRingStages];        // producer -> consumers: the chunk's bytes have landed
     unsigned long long empty[kRingStages];       // consumers -> producer: every warp of the group has its records in registers
     uint32_t chunk[kRingStages];                 // chunk id staged in the slot
