@@ -339,6 +339,7 @@ def run_b200(args, wl):
         for i in range(K_steps):
             set_pose(Wm + i)
             pc.render_device(stage)
+        pc.device_buffers()   # consecutive frames alternate between two streams: make `stream` wait for both before the end event
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1), pc.launch_count - l0
@@ -480,7 +481,7 @@ def run_b200(args, wl):
                                     ("point-sharded, ncclAllReduce min/sum" if args.nccl else "point-sharded, two-shot min/sum all-reduce kernels over NVLink peer memory")),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
                        "distortion": bool(args.distort),
-                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "fused_up", "zmin_variant", "blend_variant", "key64")}},
+                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "fused_up", "pipeline", "zmin_variant", "blend_variant", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -89,7 +89,10 @@ int rtr_render_filtered(rtr_renderer* r, uint8_t* bgr, float* depth);  /* comput
  * 1x5xHxW fp16 U-Net input (torch::from_blob it, project_cloud.cu:471).  Stream-synchronised. */
 int rtr_render_tensor(rtr_renderer* r, void** device_fp16);
 
-/* ---- device-resident / asynchronous variants (no host copies, no sync) */
+/* ---- device-resident / asynchronous variants (no host copies, no sync).  Back-to-back frames alternate between the
+ * renderer's two frame-buffer sets and two streams (option "pipeline", default 1), so that one frame's point passes
+ * overlap the previous frame's image passes; rtr_get_device_buffers / rtr_read_buffer always refer to the frame
+ * enqueued last, and rtr_get_device_buffers makes `stream` wait for the frames in flight on either stream. */
 int rtr_render_device(rtr_renderer* r, int stage);
 int rtr_sync(rtr_renderer* r);
 /* Render n_frames poses (n_frames x 16 doubles, world->camera) back to back.  bgr/depth, when not
@@ -123,7 +126,7 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
 
 /* ---- options / introspection.  Known keys: "zmin_variant" (bit0 early test, bit1 warp
  * aggregation, bit2 L1-cached test), "zmin_unroll", "blend_variant", "blend_unroll",
- * "force_generic", "keep_masks", "timing", "key64", "chunk_cull", "ring", "fused_up", "sort_on_upload" (default 1: every upload
+ * "force_generic", "keep_masks", "timing", "key64", "chunk_cull", "ring", "fused_up", "pipeline", "sort_on_upload" (default 1: every upload
  * re-orders the cloud along a Morton curve on the GPU — no output depends on point order; set 0 BEFORE uploading
  * to keep the input order, e.g. when the point index of the 64-bit key must be the caller's index). */
 int rtr_set_option(rtr_renderer* r, const char* key, int64_t value);

@@ -16,6 +16,11 @@ struct FrameSet {
     FrameBuffers fb{};
     bool f32acc = false;  // the last frame rendered into this set accumulated colour sums as floats
     cudaEvent_t rendered = nullptr, copied = nullptr;
+    // chunk-level frustum culling state of the frame rendered into this set (rtr_cull.cu); per set so that two frames
+    // can be in flight on two streams
+    uint32_t* vis_list = nullptr;
+    CullState* cull_state = nullptr;
+    uint32_t cull_parity = 0;  // alternates per culled frame (CullState::n_visible double buffer)
 };
 
 }  // namespace rtr
@@ -23,7 +28,8 @@ struct FrameSet {
 struct rtr_renderer {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // `stream`: everything; `stream2`: every other frame of an asynchronous frame sequence (option "pipeline")
+    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
     // cloud
     rtr::PointRecord* points = nullptr;
     uint64_t n_points = 0;
@@ -31,10 +37,7 @@ struct rtr_renderer {
     uint64_t index_base = 0;  // global index of local point 0 (point sharding)
     // chunk-level frustum culling (rtr_cull.cu)
     rtr::ChunkBounds* bounds = nullptr;
-    uint32_t* vis_list = nullptr;
-    rtr::CullState* cull_state = nullptr;
     uint32_t n_chunks = 0;
-    uint32_t cull_parity = 0;  // alternates per culled frame (CullState::n_visible double buffer)
     rtr::RingSchedule ring_sched{};  // stream-all tile order of the ring kernels (rtr_point_ring.cu), fixed at upload
     // camera
     int W = 0, H = 0;
@@ -54,6 +57,8 @@ struct rtr_renderer {
     int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
     int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1, sort_on_upload = 1;
     int fused_up = 1;  // the four up-pass levels in one launch (needs W % 16 == 0 and keep_masks = 0)
+    int pipeline = 1;  // asynchronous frame sequences (rtr_render_device, rtr_render_trajectory) alternate between the two frame
+                       // sets AND two streams, so frame i+1's point passes overlap frame i's image passes (off with peers / NCCL / timing)
     int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)
     int ring_perm = 1;  // stream-all ring passes visit the chunks in a low-discrepancy order (0: storage order)
     int ring = 1;  // point passes through the TMA-fed persistent kernels: 1 = for culled frames, 2 = always, 0 = never
@@ -87,6 +92,10 @@ struct rtr_renderer {
 
 namespace rtr {
 int renderer_fail(rtr_renderer* r, int code, const std::string& msg);
+// Frees the chunk bounds and both frame sets' visible-list storage.
+void free_cull_storage(rtr_renderer* r);
+// Waits until both compute streams are idle.
+cudaError_t sync_compute(rtr_renderer* r);
 // Frees the current cloud and allocates room for n records (r->points, owned).
 int replace_cloud(rtr_renderer* r, uint64_t n);
 // (Re)builds the chunk bounds for the cloud in r->points; every upload path ends with it.

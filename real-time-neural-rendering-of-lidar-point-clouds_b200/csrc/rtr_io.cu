@@ -168,7 +168,7 @@ int upload_records(rtr_renderer* r, const std::vector<PointRecord>& rec) {
     int rc = replace_cloud(r, rec.size());
     if (rc != RTR_OK || rec.empty()) return rc;
     IO_CUDA(r, cudaMemcpyAsync(r->points, rec.data(), rec.size() * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
-    IO_CUDA(r, cudaStreamSynchronize(r->stream));
+    IO_CUDA(r, sync_compute(r));
     return finish_upload(r);
 }
 
@@ -354,8 +354,7 @@ static int reorder_cloud(rtr_renderer* r, int* dims3, bool morton) {
     if (e != cudaSuccess) { cudaFree(sorted); return renderer_fail(r, RTR_ERR_CUDA, std::string("rtr_bin_cells: ") + cudaGetErrorString(e)); }
     cudaFree(r->points);
     r->points = sorted;
-    cudaFree(r->bounds); cudaFree(r->vis_list); cudaFree(r->cull_state);
-    r->bounds = nullptr; r->vis_list = nullptr; r->cull_state = nullptr;
+    free_cull_storage(r);
     return build_chunk_bounds(r);
 }
 
@@ -574,7 +573,7 @@ int rtr_postprocess_unet_output(rtr_renderer* r, const void* device_fp16_chw, in
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && host_hwc) {
         e = cudaMemcpyAsync(host_hwc, out, n_px * 3, cudaMemcpyDeviceToHost, r->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+        if (e == cudaSuccess) e = sync_compute(r);
     }
     if (e != cudaSuccess) return renderer_fail(r, RTR_ERR_CUDA, std::string("rtr_postprocess_unet_output: ") + cudaGetErrorString(e));
     return RTR_OK;

@@ -94,6 +94,27 @@ int cuda_fail(rtr_renderer* r, cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail((r), e__, #call); \
     } while (0)
 
+}  // namespace
+namespace rtr {
+// Frees the chunk bounds and both frame sets' visible-list storage (the cloud is about to change).
+void free_cull_storage(rtr_renderer* r) {
+    cudaFree(r->bounds);
+    r->bounds = nullptr;
+    for (auto& s : r->set) {
+        cudaFree(s.vis_list); cudaFree(s.cull_state);
+        s.vis_list = nullptr; s.cull_state = nullptr; s.cull_parity = 0;
+    }
+}
+// Both compute streams idle (stream2 only ever holds frames of a pipelined sequence).
+cudaError_t sync_compute(rtr_renderer* r) {
+    cudaError_t e = cudaStreamSynchronize(r->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream2);
+    return e;
+}
+}  // namespace rtr
+namespace {
+bool pipelined(const rtr_renderer* r) { return r->pipeline && !r->peer.attached && !r->comm && !r->timing; }
+
 void free_frame_sets(rtr_renderer* r) {
     for (auto& s : r->set) {
         cudaFree(s.fb.zbuf); cudaFree(s.fb.accum); cudaFree(s.fb.image); cudaFree(s.fb.tensor); cudaFree(s.fb.minmax);
@@ -117,7 +138,7 @@ template <typename T> cudaError_t zalloc(T** p, size_t bytes, cudaStream_t s) {
 int ensure_buffers(rtr_renderer* r) {
     const int W = r->W, H = r->H;
     if (r->alloc_W != W || r->alloc_H != H) {
-        RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+        RTR_CUDA(r, sync_compute(r));
         RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
         free_frame_sets(r);
         r->dims = make_pyramid_dims(W, H);
@@ -132,15 +153,18 @@ int ensure_buffers(rtr_renderer* r) {
             for (int i = 1; i <= 4; ++i) RTR_CUDA(r, zalloc(&s.fb.level[i], size_t(r->dims.w[i]) * r->dims.h[i] * 4, r->stream));
         }
         r->alloc_W = W; r->alloc_H = H;
+        RTR_CUDA(r, sync_compute(r));  // the zero-fills ran on `stream`; frames may start on either stream
     }
     if (r->keep_masks && !r->masks_allocated) {
         for (auto& s : r->set)
             for (int i = 0; i < 4; ++i) RTR_CUDA(r, zalloc(&s.fb.mask[i], size_t(r->dims.uw[i]) * r->dims.uh[i], r->stream));
         r->masks_allocated = true;
+        RTR_CUDA(r, sync_compute(r));
     }
     if (r->key64 && !r->key64_allocated) {
         for (auto& s : r->set) RTR_CUDA(r, zalloc(&s.fb.zkey, size_t(W) * H * 8, r->stream));
         r->key64_allocated = true;
+        RTR_CUDA(r, sync_compute(r));
     }
     return RTR_OK;
 }
@@ -247,8 +271,8 @@ int peer_merge(rtr_renderer* r, int si, bool accum, int op) {
     return RTR_OK;
 }
 
-// Enqueue one frame on r->stream into frame set `si`.
-int enqueue_frame(rtr_renderer* r, int stage, int si) {
+// Enqueue one frame into frame set `si`: on `stream`, or — second set of a pipelined sequence — on `stream2`.
+int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = false) {
     const bool peer = r->peer.attached;
     if (peer && (r->peer.W != r->W || r->peer.H != r->H)) return fail(r, RTR_ERR_STATE, "resolution changed while peers are attached: rtr_peer_detach first");
     if (peer && r->key64) return fail(r, RTR_ERR_UNSUPPORTED, "key64 mode merges through rtr_comm_init (NCCL), not rtr_peer_attach");
@@ -263,7 +287,8 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     if (!r->keep_masks) for (auto& m : fb.mask) m = nullptr;
     const uint64_t P = uint64_t(r->W) * r->H, cov = clear_coverage(r->W, r->H);
     const bool filtered = stage == RTR_STAGE_FILTERED;
-    cudaStream_t s = r->stream;
+    cudaStream_t s = (allow_pipeline && si == 1 && pipelined(r)) ? r->stream2 : r->stream;
+    RTR_CUDA(r, cudaStreamWaitEvent(s, fs.rendered, 0));               // this set's previous frame (may have run on the other stream)
     if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, fs.copied, 0));  // previous D2H of this set must be done
     cudaEvent_t* ev = r->ev;
     if (r->timing == 2) {
@@ -297,15 +322,15 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
     RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
     if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
     sched.early = r->ring_early ? 1u : 0u;
-    sched.cull = cull ? r->cull_state : nullptr;
-    sched.vis_list = cull ? r->vis_list : nullptr;
+    sched.cull = cull ? fs.cull_state : nullptr;
+    sched.vis_list = cull ? fs.vis_list : nullptr;
 
     if (r->timing) cudaEventRecord(ev[0], s);
     if (r->key64) {
         fs.f32acc = false;
         if (cull) {
-            r->cull_parity ^= 1u;
-            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state, r->cull_parity));
+            fs.cull_parity ^= 1u;
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity));
         } else {
             RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, nullptr));
         }
@@ -313,7 +338,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         r->launches += 2;
         if (r->timing) cudaEventRecord(ev[1], s);
         if (use_ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, fb.zkey));
-        else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, fb.zkey));
+        else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, fs.cull_state, fs.vis_list, fb.zbuf, fb.zkey));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
         r->launches += 1;
         if (r->comm) {
@@ -332,15 +357,15 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         r->launches += filtered ? (((r->W % 16) == 0 && !r->force_generic) ? 1 : 5) : 0;
     } else {
         if (cull) {
-            r->cull_parity ^= 1u;
-            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, r->bounds, r->n_chunks, cp, r->vis_list, r->cull_state, r->cull_parity));
+            fs.cull_parity ^= 1u;
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity));
         } else {
             RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, nullptr));
         }
         r->launches += 1;
         if (r->timing) cudaEventRecord(ev[1], s);
         if (use_ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, nullptr));
-        else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, r->cull_state, r->vis_list, fb.zbuf, nullptr));
+        else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, fs.cull_state, fs.vis_list, fb.zbuf, nullptr));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
         r->launches += 1;
         if (peer) {
@@ -355,7 +380,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
         const bool f32acc = (bv & 4) != 0;
         fs.f32acc = f32acc;
         if (use_ring) RTR_CUDA(r, launch_blend_ring(s, r->sm_count, bv, r->points, r->n_points, pp, sched, cull, fb.zbuf, fb.accum));
-        else if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, r->cull_state, r->vis_list, fb.zbuf, fb.accum, nullptr));
+        else if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, fs.cull_state, fs.vis_list, fb.zbuf, fb.accum, nullptr));
         else RTR_CUDA(r, launch_blend(s, bv, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, nullptr));
         r->launches += 1;
         if (peer) {
@@ -371,8 +396,8 @@ int enqueue_frame(rtr_renderer* r, int stage, int si) {
             // A pixel that collected more than 65793 points leaves the exact range of the float sums; resolve
             // raised minmax[2] for it.  This launch returns at once unless that happened, in which
             // case it redoes the colour sums of the frame with the integer REDs and resolve again.
-            RTR_CUDA(r, launch_exact_fixup(s, r->sm_count, r->points, r->n_points, pp, cull ? r->cull_state : nullptr,
-                                           cull ? r->vis_list : nullptr, fb.zbuf, fb.accum, P, fb.image, cov, fb.minmax));
+            RTR_CUDA(r, launch_exact_fixup(s, r->sm_count, r->points, r->n_points, pp, cull ? fs.cull_state : nullptr,
+                                           cull ? fs.vis_list : nullptr, fb.zbuf, fb.accum, P, fb.image, cov, fb.minmax));
             r->launches += 1;
         }
     }
@@ -474,6 +499,7 @@ int rtr_create(int device, rtr_renderer** out) {
     r->sm_count = prop.multiProcessorCount;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete r;
         return cuda_fail(nullptr, e, "stream creation");
@@ -490,7 +516,7 @@ int rtr_create(int device, rtr_renderer** out) {
 void rtr_destroy(rtr_renderer* r) {
     if (!r) return;
     cudaSetDevice(r->device);
-    cudaStreamSynchronize(r->stream);
+    sync_compute(r);
     cudaStreamSynchronize(r->copy_stream);
     if (r->comm) g_nccl.CommDestroy(r->comm);
     rtr_peer_detach(r);
@@ -498,11 +524,12 @@ void rtr_destroy(rtr_renderer* r) {
     cudaFree(r->post_scratch);
     free_frame_sets(r);
     if (r->owns_points) cudaFree(r->points);
-    cudaFree(r->bounds); cudaFree(r->vis_list); cudaFree(r->cull_state);
+    free_cull_storage(r);
     for (auto& s : r->set) { cudaEventDestroy(s.rendered); cudaEventDestroy(s.copied); }
     for (auto& ev : r->ev) cudaEventDestroy(ev);
     for (auto& ev : r->ev_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(r->stream);
+    cudaStreamDestroy(r->stream2);
     cudaStreamDestroy(r->copy_stream);
     delete r;
 }
@@ -514,10 +541,10 @@ const char* rtr_last_error(const rtr_renderer* r) { return r ? r->err.c_str() : 
 namespace rtr {
 int replace_cloud(rtr_renderer* r, uint64_t n) {
     RTR_CUDA(r, cudaSetDevice(r->device));
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     if (r->owns_points) cudaFree(r->points);
-    cudaFree(r->bounds); cudaFree(r->vis_list); cudaFree(r->cull_state);
-    r->bounds = nullptr; r->vis_list = nullptr; r->cull_state = nullptr; r->n_chunks = 0;
+    free_cull_storage(r);
+    r->n_chunks = 0;
     r->points = nullptr; r->n_points = 0; r->owns_points = false;
     if (n == 0) return RTR_OK;
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->points), n * sizeof(PointRecord)));
@@ -532,13 +559,15 @@ int build_chunk_bounds(rtr_renderer* r) {
     r->n_chunks = uint32_t((r->n_points + kChunkPoints - 1) / kChunkPoints);
     r->ring_sched = make_ring_schedule(r->n_points, nullptr, nullptr);
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->bounds), size_t(r->n_chunks) * sizeof(ChunkBounds)));
-    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->vis_list), size_t(r->n_chunks) * sizeof(uint32_t)));
-    RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->cull_state), sizeof(CullState)));
-    RTR_CUDA(r, cudaMemsetAsync(r->cull_state, 0, sizeof(CullState), r->stream));
-    r->cull_parity = 0;
+    for (auto& fs : r->set) {
+        RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.vis_list), size_t(r->n_chunks) * sizeof(uint32_t)));
+        RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.cull_state), sizeof(CullState)));
+        RTR_CUDA(r, cudaMemsetAsync(fs.cull_state, 0, sizeof(CullState), r->stream));
+        fs.cull_parity = 0;
+    }
     RTR_CUDA(r, launch_chunk_bounds(r->stream, r->points, r->n_points, r->bounds));
     r->launches += 1;
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     return RTR_OK;
 }
 
@@ -577,7 +606,7 @@ int rtr_upload_cloud_xyz_bgr(rtr_renderer* r, const float* xyz, const uint8_t* b
         RTR_CUDA(r, cudaMemcpyAsync(r->points + off, stage[b], m * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
         cudaEventRecord(done[b], r->stream);
     }
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     for (int i = 0; i < 2; ++i) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
     return finish_upload(r);
 }
@@ -589,7 +618,7 @@ int rtr_upload_cloud_packed16(rtr_renderer* r, const void* host_records, uint64_
     int rc = replace_cloud(r, n);
     if (rc != RTR_OK || n == 0) return rc;
     RTR_CUDA(r, cudaMemcpyAsync(r->points, host_records, n * sizeof(PointRecord), cudaMemcpyHostToDevice, r->stream));
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     return finish_upload(r);
 }
 
@@ -615,7 +644,7 @@ int rtr_synth_cloud(rtr_renderer* r, uint64_t seed, uint64_t n_total, uint64_t f
     RTR_CUDA(r, launch_synth(r->stream, seed, n_total, first, count, lx, ly, lz, nbox, r->points));
     r->launches += 1;
     r->index_base = first;
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     return finish_upload(r);
 }
 
@@ -626,7 +655,7 @@ int rtr_download_cloud_packed16(rtr_renderer* r, uint64_t first, uint64_t count,
     if (first + count > r->n_points) return fail(r, RTR_ERR_ARG, "range exceeds cloud");
     RTR_CUDA(r, cudaSetDevice(r->device));
     RTR_CUDA(r, cudaMemcpyAsync(host_records, r->points + first, count * sizeof(PointRecord), cudaMemcpyDeviceToHost, r->stream));
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     return RTR_OK;
 }
 
@@ -677,7 +706,7 @@ int rtr_render_tensor(rtr_renderer* r, void** device_fp16) {
     RTR_CUDA(r, cudaSetDevice(r->device));
     int rc = enqueue_frame(r, RTR_STAGE_FILTERED, r->cur);
     if (rc != RTR_OK) return rc;
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     *device_fp16 = r->set[r->cur].fb.tensor;
     return RTR_OK;
 }
@@ -686,13 +715,18 @@ int rtr_render_device(rtr_renderer* r, int stage) {
     if (!r) return RTR_ERR_ARG;
     if (stage != RTR_STAGE_RGBD && stage != RTR_STAGE_FILTERED) return fail(r, RTR_ERR_ARG, "bad stage");
     RTR_CUDA(r, cudaSetDevice(r->device));
-    return enqueue_frame(r, stage, r->cur);
+    // back-to-back asynchronous frames alternate between the two frame sets and the two streams: the point passes of
+    // one frame overlap the image passes of the previous one.  r->cur = the set of the frame enqueued last.
+    const int si = pipelined(r) ? (r->cur ^ 1) : r->cur;
+    const int rc = enqueue_frame(r, stage, si, true);
+    if (rc == RTR_OK) r->cur = si;
+    return rc;
 }
 
 int rtr_sync(rtr_renderer* r) {
     if (!r) return RTR_ERR_ARG;
     RTR_CUDA(r, cudaSetDevice(r->device));
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
     return RTR_OK;
 }
@@ -705,16 +739,16 @@ int rtr_render_trajectory(rtr_renderer* r, int stage, const double* poses, int n
     for (int f = 0; f < n_frames; ++f) {
         int rc = rtr_set_pose_w2c(r, poses + size_t(f) * 16);
         if (rc != RTR_OK) return rc;
-        const int si = r->cur;
-        rc = enqueue_frame(r, stage, si);
+        const int si = (bgr || depth || pipelined(r)) ? (r->cur ^ 1) : r->cur;  // the other set: this one may still drain over PCIe
+        rc = enqueue_frame(r, stage, si, true);
         if (rc != RTR_OK) return rc;
+        r->cur = si;
         if (bgr || depth) {
             rc = enqueue_copy(r, si, bgr ? bgr + size_t(f) * P * 3 : nullptr, depth ? depth + size_t(f) * P : nullptr);
             if (rc != RTR_OK) return rc;
-            r->cur ^= 1;  // next frame renders into the other set while this one drains over PCIe
         }
     }
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
     return RTR_OK;
 }
@@ -734,6 +768,8 @@ int rtr_get_device_buffers(rtr_renderer* r, rtr_device_buffers* out) {
     for (int i = 0; i < 4; ++i) out->mask[i] = r->keep_masks ? fb.mask[i] : nullptr;
     out->width = r->alloc_W; out->height = r->alloc_H;
     out->tensor_plane = uint64_t(r->dims.uw[0]) * r->dims.uh[0];
+    // work the caller orders on `stream` after this call must see the frame(s) in flight, whichever stream they run on
+    for (auto& fs : r->set) RTR_CUDA(r, cudaStreamWaitEvent(r->stream, fs.rendered, 0));
     out->stream = r->stream;
     return RTR_OK;
 }
@@ -755,7 +791,7 @@ int rtr_read_buffer(rtr_renderer* r, int what, void* dst, size_t bytes) {
     if (!src) return fail(r, RTR_ERR_ARG, "buffer not available");
     if (bytes > cap) return fail(r, RTR_ERR_ARG, "read exceeds buffer");
     RTR_CUDA(r, cudaSetDevice(r->device));
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     RTR_CUDA(r, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     if (what == 1 && r->set[r->cur].f32acc) {  // always hand out the reference's layout: {b,g,r,count} as u32
         uint32_t flag = 0;
@@ -787,7 +823,7 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
     r->launches += 1;
     if (e == cudaSuccess) e = cudaMemcpyAsync(pix_host, d_pix, r->n_points * 4, cudaMemcpyDeviceToHost, r->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(zbits_host, d_z, r->n_points * 4, cudaMemcpyDeviceToHost, r->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    if (e == cudaSuccess) e = sync_compute(r);
     cudaFree(d_pix); cudaFree(d_z);
     if (e != cudaSuccess) return cuda_fail(r, e, "project dump");
     return RTR_OK;
@@ -858,7 +894,7 @@ int rtr_selftest_fast_divide(rtr_renderer* r, uint64_t n_pairs, uint64_t seed, u
     r->launches += 1;
     unsigned long long h = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, r->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    if (e == cudaSuccess) e = sync_compute(r);
     cudaFree(d);
     if (e != cudaSuccess) return cuda_fail(r, e, "rtr_selftest_fast_divide");
     *mismatches = h;
@@ -880,6 +916,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "fused_up")) return &r->fused_up;
     if (!std::strcmp(key, "ring_perm")) return &r->ring_perm;
     if (!std::strcmp(key, "ring_early")) return &r->ring_early;
+    if (!std::strcmp(key, "pipeline")) return &r->pipeline;
     return nullptr;
 }
 
@@ -904,7 +941,7 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "sm_count")) return r->sm_count;
     if (!std::strcmp(key, "peer_error")) {  // 1 when a cross-GPU wait of the peer merge timed out
         uint32_t v = 0;
-        if (r->peer.flags) { cudaSetDevice(r->device); cudaStreamSynchronize(r->stream); cudaMemcpy(&v, r->peer.flags + 65, 4, cudaMemcpyDeviceToHost); }
+        if (r->peer.flags) { cudaSetDevice(r->device); sync_compute(const_cast<rtr_renderer*>(r)); cudaMemcpy(&v, r->peer.flags + 65, 4, cudaMemcpyDeviceToHost); }
         return v;
     }
     const int* slot = option_slot(const_cast<rtr_renderer*>(r), key);
@@ -939,16 +976,18 @@ int rtr_get_cull_stats(rtr_renderer* r, uint64_t* frames, uint64_t* visible_chun
     if (!r || !frames || !visible_chunks_total || !n_chunks) return RTR_ERR_ARG;
     *frames = *visible_chunks_total = 0;
     *n_chunks = r->n_chunks;
-    if (!r->cull_state) return RTR_OK;
+    if (!r->set[0].cull_state) return RTR_OK;
     RTR_CUDA(r, cudaSetDevice(r->device));
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
-    CullState st;
-    RTR_CUDA(r, cudaMemcpy(&st, r->cull_state, sizeof(st), cudaMemcpyDeviceToHost));
-    *frames = uint64_t(st.frames) + (st.armed ? 1u : 0u);   // the frame in flight is folded at the next clear
-    *visible_chunks_total = st.total_visible + (st.armed ? cull_count(&st) : 0u);
-    if (reset) {
-        RTR_CUDA(r, cudaMemset(r->cull_state, 0, sizeof(CullState)));
-        r->cull_parity = 0;
+    RTR_CUDA(r, sync_compute(r));
+    for (auto& fs : r->set) {  // frames of a pipelined sequence alternate between the two sets
+        CullState st;
+        RTR_CUDA(r, cudaMemcpy(&st, fs.cull_state, sizeof(st), cudaMemcpyDeviceToHost));
+        *frames += uint64_t(st.frames) + (st.armed ? 1u : 0u);   // the frame in flight is folded at the next clear
+        *visible_chunks_total += st.total_visible + (st.armed ? cull_count(&st) : 0u);
+        if (reset) {
+            RTR_CUDA(r, cudaMemset(fs.cull_state, 0, sizeof(CullState)));
+            fs.cull_parity = 0;
+        }
     }
     return RTR_OK;
 }
@@ -1002,7 +1041,7 @@ int rtr_peer_export(rtr_renderer* r, void* blob512) {
         RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->peer.flags), 4096));
         RTR_CUDA(r, cudaMemset(r->peer.flags, 0, 4096));
     }
-    RTR_CUDA(r, cudaStreamSynchronize(r->stream));
+    RTR_CUDA(r, sync_compute(r));
     PeerBlob b;
     std::memset(&b, 0, sizeof(b));
     b.magic = 0x52545250u;
@@ -1020,7 +1059,7 @@ int rtr_peer_export(rtr_renderer* r, void* blob512) {
 int rtr_peer_detach(rtr_renderer* r) {
     if (!r) return RTR_ERR_ARG;
     cudaSetDevice(r->device);
-    cudaStreamSynchronize(r->stream);
+    sync_compute(r);
     for (void* p : r->peer.opened) cudaIpcCloseMemHandle(p);
     r->peer.opened.clear();
     r->peer.attached = false;
@@ -1066,7 +1105,7 @@ int rtr_peer_attach(rtr_renderer* r, const void* blobs, int rank, int n_ranks) {
 int rtr_comm_destroy(rtr_renderer* r) {
     if (!r) return RTR_ERR_ARG;
     if (r->comm) {
-        cudaStreamSynchronize(r->stream);
+        sync_compute(r);
         g_nccl.CommDestroy(r->comm);
         r->comm = nullptr;
     }
