@@ -384,6 +384,45 @@ def test_cloud_sizes_around_chunk_and_ring_boundaries(gpu, cpu_oracle, n):
     assert np.array_equal(outs["ring_key64"][1], gold["zbuf"])      # key64's depth is the reference depth
 
 
+def test_large_cloud_ring_equals_per_thread_kernels(gpu):
+    """30 M points seen from a corner of the hall (most chunks visible: ~100 tiles per CTA, i.e. the ring's refill path
+    runs deep) and from inside: the TMA-fed kernels, the per-thread kernels over the list and the stream-all kernels
+    must produce identical frames, also with two frames in flight."""
+    n, W, H = 30_000_000, 1280, 720
+    P = W * H
+    calib = gpu.CameraCalibration()
+    calib.loadCalibration(500.0, 500.0, 639.5, 359.5, [0.0] * 5, W, H)
+    poses = [gpu.look_at_w2c((0.3, 0.3, 2.7), (1.0, 0.8, -0.2)), gpu.look_at_w2c((6.0, 5.0, 1.5), (1.0, 0.3, 0.0))]
+    pc = gpu.ProjectCloud.synthetic(seed=4242, n_total=n, hall=scenes.HALL_LARGE, n_boxes=12)
+    digests = {}
+    for name, opts in (("ring", dict(ring=1, chunk_cull=1)), ("ldg_list", dict(ring=0, chunk_cull=1)), ("ldg_all", dict(ring=0, chunk_cull=0)),
+                       ("ring_all", dict(ring=2, chunk_cull=0))):
+        for k, v in opts.items():
+            pc.set_option(k, v)
+        out = []
+        for E in poses:
+            color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+            assert pc.computeFilteredRGBD(calib, E, color, depth) == 1
+            out.append(scenes.sha(color) + scenes.sha(depth) + scenes.sha(pc.read("tensor", np.uint16, P * 5)))
+        digests[name] = out
+    fr, vis, nch = 0, 0, 0
+    pc.set_option("ring", 1)
+    pc.set_option("chunk_cull", 1)
+    pc.cull_stats(reset=True)
+    # the same two poses through the asynchronous trajectory call (frames alternate between two streams)
+    color = np.zeros((4, P * 3), np.uint8)
+    depth = np.zeros((4, P), np.float32)
+    traj = np.ascontiguousarray(np.stack([poses[0], poses[1], poses[0], poses[1]]).reshape(-1, 16))
+    pc._check(pc._lib.rtr_render_trajectory(pc._h, gpu.STAGE_FILTERED, traj.ctypes.data_as(gpu._dp), 4, color.ctypes.data, depth.ctypes.data))
+    fr, vis, nch = pc.cull_stats(reset=True)
+    pc.close()
+    assert fr == 4 and vis / fr > 0.3 * nch          # the corner view really sees a large part of the cloud
+    for name in ("ldg_list", "ldg_all", "ring_all"):
+        assert digests[name] == digests["ring"], name
+    for i in range(4):
+        assert scenes.sha(color[i]) + scenes.sha(depth[i]) == digests["ring"][i % 2][:128], f"trajectory frame {i}"
+
+
 def test_error_behaviour(gpu):
     pc = gpu.ProjectCloud()
     calib = gpu.CameraCalibration()
