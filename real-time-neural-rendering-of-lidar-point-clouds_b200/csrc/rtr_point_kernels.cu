@@ -1,8 +1,12 @@
-// Point-level kernels of the hot path, hand-written for sm_100a.
+// Point-level kernels of the hot path, hand-written for sm_100a: the per-thread LDG.128 forms.
 //
 //   clear_kernel   <- fillBuffer (render.cu:16-31) + cudaMemset (project_cloud.cu:316-317)
 //   zmin_kernel    <- minDepthPass   (render.cu:53-83)
 //   blend_kernel   <- accumulatePass (render.cu:85-130)
+//
+// These stream EVERY point of the cloud (frames rendered with chunk_cull = 0 — the configuration north_star's
+// "16 B/point against the HBM roofline" describes: 6.4 TB/s) and, as zmin_list_kernel / blend_list_kernel, the
+// visible-chunk list when option ring = 0.  Culled frames default to the TMA-fed kernels of rtr_point_ring.cu.
 //
 // Both point passes stream the packed 16-byte {x,y,z,bgra} record with one 128-bit no-allocate
 // load per point, UNROLL independent loads in flight per thread, project in registers with the
