@@ -57,6 +57,12 @@ struct rtr_renderer {
     int zmin_variant = 5, zmin_unroll = 4, blend_variant = 4, blend_unroll = 4;
     int force_generic = 0, keep_masks = 0, timing = 0, key64 = 0, chunk_cull = 1, sort_on_upload = 1;
     int fused_up = 1;  // the four up-pass levels in one launch (needs W % 16 == 0 and keep_masks = 0)
+    // Views in which a pixel collects more than 65 793 points make every frame pay for the exact re-run of the colour
+    // sums.  The re-run leaves a note in a mapped host word; the next `int_sum_frames` frames then use integer sums from
+    // the start (results identical either way), after which float sums are tried again.
+    uint32_t* overflow_note = nullptr;      // pinned, mapped host word
+    uint32_t* overflow_note_dev = nullptr;  // its device alias
+    int int_sum_frames = 0;
     int pipeline = 1;  // asynchronous frame sequences (rtr_render_device, rtr_render_trajectory) alternate between the two frame
                        // sets AND two streams, so frame i+1's point passes overlap frame i's image passes (off with peers / NCCL / timing)
     int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)

@@ -143,7 +143,7 @@ cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRec
 // that returns at once when minmax[2] == 0).  cull/vis_list null = all tiles.
 cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf, uint32_t* accum,
-                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax);
+                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note);
 cudaError_t launch_clear_accum_gated(cudaStream_t s, int sm_count, uint32_t* accum, uint64_t n_px, const uint32_t* gate);
 cudaError_t launch_project_dump(cudaStream_t s, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                 int32_t* pix_out, uint32_t* zbits_out);

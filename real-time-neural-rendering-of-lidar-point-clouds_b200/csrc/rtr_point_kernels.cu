@@ -274,10 +274,14 @@ __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRec
                                                                   const uint32_t* __restrict__ zbuf,
                                                                   uint4* __restrict__ accum, uint64_t n_px,
                                                                   uint8_t* __restrict__ image, uint64_t cov,
-                                                                  uint32_t* __restrict__ minmax) {
+                                                                  uint32_t* __restrict__ minmax,
+                                                                  uint32_t* __restrict__ host_note) {
     pdl_prologue();
     if (minmax[2] == 0u) return;
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, stride = uint64_t(gridDim.x) * blockDim.x;
+    // tell the host (mapped pinned word, read without any synchronisation) that float sums overflowed in this view:
+    // it renders the next frames with integer sums straight away instead of paying for this re-run every frame
+    if (tid == 0 && host_note) *reinterpret_cast<volatile uint32_t*>(host_note) = 1u;
     for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
     grid_barrier(minmax + 3, gridDim.x);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
@@ -368,14 +372,14 @@ cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const P
 
 cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf, uint32_t* accum,
-                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax) {
+                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note) {
     if (n == 0) return cudaSuccess;
     const dim3 grid(unsigned(sm_count) * 2u), block(kPointBlock);
     uint4* a4 = reinterpret_cast<uint4*>(accum);
-    if (cull && pp.distort) launch_pdl_cooperative((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
-    else if (cull) launch_pdl_cooperative((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
-    else if (pp.distort) launch_pdl_cooperative((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
-    else launch_pdl_cooperative((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax);
+    if (cull && pp.distort) launch_pdl_cooperative((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
+    else if (cull) launch_pdl_cooperative((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
+    else if (pp.distort) launch_pdl_cooperative((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
+    else launch_pdl_cooperative((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
     return cudaGetLastError();
 }
 

@@ -376,7 +376,13 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         }
         if (r->timing) cudaEventRecord(ev[2], s);
         // float accumulators (one 16-byte RED per point) unless the sums must be all-reduced as integers
-        const int bv = (r->comm || peer) ? (r->blend_variant & ~4) : r->blend_variant;
+        if (r->overflow_note && *reinterpret_cast<volatile uint32_t*>(r->overflow_note)) {  // an earlier frame's float sums overflowed
+            *reinterpret_cast<volatile uint32_t*>(r->overflow_note) = 0u;
+            r->int_sum_frames = 64;
+        }
+        const bool int_sums = r->comm || peer || r->int_sum_frames > 0;
+        if (r->int_sum_frames > 0) r->int_sum_frames -= 1;
+        const int bv = int_sums ? (r->blend_variant & ~4) : r->blend_variant;
         const bool f32acc = (bv & 4) != 0;
         fs.f32acc = f32acc;
         if (use_ring) RTR_CUDA(r, launch_blend_ring(s, r->sm_count, bv, r->points, r->n_points, pp, sched, cull, fb.zbuf, fb.accum));
@@ -397,7 +403,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
             // raised minmax[2] for it.  This launch returns at once unless that happened, in which
             // case it redoes the colour sums of the frame with the integer REDs and resolve again.
             RTR_CUDA(r, launch_exact_fixup(s, r->sm_count, r->points, r->n_points, pp, cull ? fs.cull_state : nullptr,
-                                           cull ? fs.vis_list : nullptr, fb.zbuf, fb.accum, P, fb.image, cov, fb.minmax));
+                                           cull ? fs.vis_list : nullptr, fb.zbuf, fb.accum, P, fb.image, cov, fb.minmax, r->overflow_note_dev));
             r->launches += 1;
         }
     }
@@ -509,6 +515,13 @@ int rtr_create(int device, rtr_renderer** out) {
         cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
     }
     for (auto& ev : r->ev) cudaEventCreate(&ev);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&r->overflow_note), 64, cudaHostAllocMapped) == cudaSuccess) {
+        *r->overflow_note = 0u;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&r->overflow_note_dev), r->overflow_note, 0) != cudaSuccess) r->overflow_note_dev = nullptr;
+    } else {
+        (void)cudaGetLastError();
+        r->overflow_note = nullptr;  // only the adaptive switch is lost
+    }
     *out = r;
     return RTR_OK;
 }
@@ -522,6 +535,7 @@ void rtr_destroy(rtr_renderer* r) {
     rtr_peer_detach(r);
     cudaFree(r->peer.flags);
     cudaFree(r->post_scratch);
+    if (r->overflow_note) cudaFreeHost(r->overflow_note);
     free_frame_sets(r);
     if (r->owns_points) cudaFree(r->points);
     free_cull_storage(r);
@@ -939,6 +953,7 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
     if (!r || !key) return RTR_ERR_ARG;
     if (!std::strcmp(key, "index_base")) return int64_t(r->index_base);
     if (!std::strcmp(key, "sm_count")) return r->sm_count;
+    if (!std::strcmp(key, "int_sum_frames")) return r->int_sum_frames;  // frames left that start with integer colour sums
     if (!std::strcmp(key, "peer_error")) {  // 1 when a cross-GPU wait of the peer merge timed out
         uint32_t v = 0;
         if (r->peer.flags) { cudaSetDevice(r->device); sync_compute(const_cast<rtr_renderer*>(r)); cudaMemcpy(&v, r->peer.flags + 65, 4, cudaMemcpyDeviceToHost); }

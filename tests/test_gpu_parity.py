@@ -493,6 +493,38 @@ def test_distortion_matches_opencv_model(gpu, cpu_oracle):
 
 
 # ------------------------------------------------------------------ chunk-level frustum culling
+def test_views_that_overflow_float_sums_switch_to_integer_sums(gpu, cpu_oracle):
+    """A view in which a pixel collects > 65 793 points pays for the exact re-run once: the re-run leaves a note for the
+    host, the following frames start with integer colour sums (no overflow flag, no re-run) and every frame is identical."""
+    W, H, heavy = 64, 48, 70_000
+    m = np.array([32, 0, 31.5, 0, 0, 32, 23.5, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
+    rng = np.random.default_rng(9)
+    n = heavy + 5000
+    xyz = rng.uniform(-1.0, 1.0, (n, 3)).astype(np.float32)
+    xyz[:, 2] = rng.uniform(1.5, 3.0, n).astype(np.float32)
+    xyz[:heavy] = np.array([0.013, 0.009, 1.0], np.float32)
+    bgr = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    pc = gpu.ProjectCloud.from_packed(gpu.pack_records(xyz, bgr))
+    c = gpu.CameraCalibration()
+    c.setWidth(W)
+    c.setHeight(H)
+    pc.set_camera(c)
+    pc.set_cam_proj_raw(m)
+    frames, flags, left = [], [], []
+    for _ in range(4):
+        color, depth = np.zeros(W * H * 3, np.uint8), np.zeros(W * H, np.float32)
+        pc._check(pc._lib.rtr_render_filtered(pc._h, color.ctypes.data, depth.ctypes.data))
+        frames.append((color, depth.view(np.uint32).copy(), pc.read("tensor", np.uint16, W * H * 5)))
+        flags.append(int(pc.read("minmax", np.uint32, 3)[2]))
+        left.append(pc.get_option("int_sum_frames"))
+    tap, resident = pc.project_points(), pc.download_cloud()
+    pc.close()
+    assert flags == [1, 0, 0, 0] and left[0] == 0 and left[1] == 63 and left[3] == 61
+    gold = cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(resident), W, H, filtered=True)
+    for color, depth, tensor in frames:
+        assert np.array_equal(color, gold["image"]) and np.array_equal(depth, gold["zbuf"]) and np.array_equal(tensor, gold["tensor"])
+
+
 def test_chunk_culling_never_changes_a_frame(gpu, cpu_oracle):
     """Culling on (default) vs off over many random cameras, including cameras outside the cloud, grazing
     views, huge focal lengths and chunks that hold NaN / inf / huge points: every buffer identical."""
