@@ -157,6 +157,10 @@ int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int 
  * the chunk-level culling tests against.  K9 row-major 3x3, dist5 = k1, k2, p1, p2, k3. */
 int rtr_host_distortion_bounds(int width, int height, const double* K9, const double* dist5, double* r2_max, double* rstar);
 
+/* Host-only helper: the multiplier m of the order in which a stream-all pass of the ring kernels (option ring = 2)
+ * visits the cloud's 1024-point chunks, tile t -> chunk (t * m) mod n_chunks; coprime with n_chunks, i.e. a permutation. */
+uint32_t rtr_host_ring_stride(uint64_t n_points);
+
 /* Device self-test of the ring kernels' perspective divide: for n_pairs random bit patterns (a, b) (every class of
  * float: NaN, inf, denormal, huge) checks on the GPU that whenever !(|b| < 2^-126) the directly issued
  * MUFU.RCP + FMUL gives the same bits as __fdividef(a, b) (what the reference compiles, render.cu:65-66), and the same

@@ -443,6 +443,8 @@ int render_to_host(rtr_renderer* r, int stage, uint8_t* bgr, float* depth) {
 
 }  // namespace
 
+extern "C" uint32_t rtr_host_ring_stride(uint64_t n_points) { return make_ring_schedule(n_points, nullptr, nullptr).perm_mul; }
+
 extern "C" int rtr_host_distortion_bounds(int W, int H, const double* K9, const double* dist5, double* r2_max, double* rstar) {
     if (!K9 || !dist5 || !r2_max || !rstar || W < 1 || H < 1) return RTR_ERR_ARG;
     const double* K = K9;

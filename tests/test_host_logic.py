@@ -86,3 +86,20 @@ def test_distortion_cull_radius_bounds_every_visible_point(pkg):
         assert rstar.value == 0 or far <= rstar.value, (it, far, rstar.value)
         effective += 0 < rstar.value < 0.8 * rmax
     assert effective >= 30      # the bound is tight enough to cull for most cameras
+
+
+def test_ring_stream_all_order_is_a_permutation(pkg):
+    """Tile t of a stream-all ring pass reads chunk (t * m) mod n_chunks (rtr_point_ring.cu): m must be coprime with
+    n_chunks for every cloud size, and spread consecutive tiles over the cloud."""
+    import math
+    lib = pkg.load_library()
+    for n_points in [1, 1023, 1024, 1025, 2048, 3 * 1024, 5000, 100_000, 1_000_003, 20_000_000, 100_000_000, 2 ** 32 - 1]:
+        n_chunks = (n_points + 1023) // 1024
+        m = lib.rtr_host_ring_stride(n_points)
+        if n_chunks == 1:
+            continue
+        assert 0 < m < n_chunks and math.gcd(m, n_chunks) == 1, (n_points, n_chunks, m)
+        if n_chunks <= 4096:
+            assert sorted((t * m) % n_chunks for t in range(n_chunks)) == list(range(n_chunks))
+        if n_chunks >= 1000:   # golden-ratio stride: any 64 consecutive tiles land in at least 32 different 64ths of the cloud
+            assert len({((t * m) % n_chunks) * 64 // n_chunks for t in range(64)}) >= 32
