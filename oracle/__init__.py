@@ -58,6 +58,7 @@ class CpuOracle:
         L.rtro_f16_to_f32.argtypes = [C.c_uint16]
         L.rtro_cam_proj.argtypes = [_vp, _vp, _vp]
         L.rtro_project.argtypes = [_vp, _i, _u64, _vp, _i, _i, _vp, _vp]
+        L.rtro_project_distorted.argtypes = [_vp, _i, _u64, _vp, _vp, _vp, C.c_float, _i, _i, _vp, _vp]
         L.rtro_clear.argtypes = [_vp, _vp, _i, _i]
         L.rtro_zmin.argtypes = [_vp, _vp, _u64, _vp]
         L.rtro_accumulate.argtypes = [_vp, _vp, _vp, _u64, _vp, _vp]
@@ -91,6 +92,17 @@ class CpuOracle:
         pix = np.empty(len(rec), dtype=np.int32)
         zb = np.empty(len(rec), dtype=np.uint32)
         self.lib.rtro_project(_p(rec), 4, len(rec), _p(m), W, H, _p(pix), _p(zb))
+        return pix, zb
+
+    def project_distorted(self, records: np.ndarray, E, K, dist, r2_max: float, W, H):
+        """CPU restatement of the NEW lens-distortion projection (csrc/rtr_common.cuh project_distorted), bit-exact."""
+        rec = np.ascontiguousarray(records, dtype=np.float32).reshape(-1, 4)
+        E, K = np.asarray(E, np.float64), np.asarray(K, np.float64).reshape(3, 3)
+        e12 = np.ascontiguousarray(E.reshape(4, 4)[:3].astype(np.float32).reshape(12))
+        intr = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[0, 1]], np.float32)
+        d = np.ascontiguousarray(np.asarray(dist, np.float64).astype(np.float32))
+        pix, zb = np.empty(len(rec), np.int32), np.empty(len(rec), np.uint32)
+        self.lib.rtro_project_distorted(_p(rec), 4, len(rec), _p(e12), _p(intr), _p(d), float(r2_max), W, H, _p(pix), _p(zb))
         return pix, zb
 
     def new_buffers(self, W, H):

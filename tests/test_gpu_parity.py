@@ -492,6 +492,29 @@ def test_distortion_matches_opencv_model(gpu, cpu_oracle):
     assert np.allclose(z, cam[front][both, 2], rtol=1e-5)
 
 
+def test_distorted_projection_equals_its_cpu_restatement(gpu, cpu_oracle):
+    """The distorted projection uses IEEE-rounded operations only, so — unlike the pinhole path's MUFU.RCP — it is
+    reproducible on a CPU: the GPU's per-point (pixel, depth bits) must equal oracle.project_distorted bit for bit."""
+    import ctypes as C
+    case = scenes.CASES["c2_1280x720"]
+    rec = cloud_of(cpu_oracle, case)[:600_000]
+    for dist in ([-0.05, 0.01, 0.0005, -0.0005, 0.0], [0.2, 0.05, 0.0, 0.0, 0.01], [-0.3, 0.1, 0.004, -0.003, -0.01]):
+        pc = gpu.ProjectCloud.from_packed(rec, apply_distortion=True)
+        calib = calib_of(gpu, case)
+        calib.setDistortionParameters(dist)
+        for E in (case.poses[0], gpu.look_at_w2c((1.0, 1.0, 1.0), (1.0, 0.7, 0.1))):
+            pc.set_camera(calib, E)
+            pix, zb = pc.project_points()
+            r2max, rstar = C.c_double(0), C.c_double(0)
+            K9 = np.ascontiguousarray(case.K.reshape(9))
+            d5 = np.asarray(dist, np.float64)
+            assert gpu.load_library().rtr_host_distortion_bounds(case.W, case.H, K9.ctypes.data_as(gpu._dp), d5.ctypes.data_as(gpu._dp), C.byref(r2max), C.byref(rstar)) == 1
+            want_pix, want_zb = cpu_oracle.project_distorted(pc.download_cloud(), E, case.K, dist, r2max.value, case.W, case.H)
+            assert (want_pix >= 0).sum() > 1_000
+            assert np.array_equal(pix, want_pix) and np.array_equal(zb, want_zb)
+        pc.close()
+
+
 # ------------------------------------------------------------------ chunk-level frustum culling
 def test_views_that_overflow_float_sums_switch_to_integer_sums(gpu, cpu_oracle):
     """A view in which a pixel collects > 65 793 points pays for the exact re-run once: the re-run leaves a note for the
