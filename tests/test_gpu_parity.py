@@ -512,6 +512,13 @@ def test_distorted_projection_equals_its_cpu_restatement(gpu, cpu_oracle):
             want_pix, want_zb = cpu_oracle.project_distorted(pc.download_cloud(), E, case.K, dist, r2max.value, case.W, case.H)
             assert (want_pix >= 0).sum() > 1_000
             assert np.array_equal(pix, want_pix) and np.array_equal(zb, want_zb)
+            # ... and with it the whole distorted frame is reproducible on the CPU without any GPU tap
+            P = case.W * case.H
+            color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+            assert pc.computeFilteredRGBD(calib, E, color, depth) == 1
+            gold = cpu_oracle.render(want_pix, want_zb, scenes.bgra_of(pc.download_cloud()), case.W, case.H, filtered=True)
+            assert np.array_equal(color, gold["image"]) and np.array_equal(depth.view(np.uint32), gold["zbuf"])
+            assert np.array_equal(pc.read("tensor", np.uint16, P * 5), gold["tensor"])
         pc.close()
 
 
