@@ -125,7 +125,12 @@ __device__ __forceinline__ bool chunk_visible(const ChunkBounds& b, const CullPa
 // One launch per frame: fillBuffer + cudaMemset (render.cu:16-31, project_cloud.cu:316-317) and the chunk
 // classification.  The visible-chunk counter is double-buffered by frame parity so that the reset of one counter
 // and the atomic appends to the other need no ordering inside the launch.
-__global__ void __launch_bounds__(256) clear_classify_kernel(uint32_t* __restrict__ zbuf, uint64_t cov,
+//
+// MIN_BLOCKS = 4 caps the kernel at 64 registers (the interval arithmetic in double wants 80): with two frames in
+// flight this kernel should start while the OTHER frame's ring kernel still holds its 2 x 512 threads x 48 registers
+// per SM, which leaves room for exactly 256 threads x 64 registers.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) clear_classify_kernel(uint32_t* __restrict__ zbuf, uint64_t cov,
                                                              uint4* __restrict__ accum, uint64_t n_px,
                                                              uint32_t* __restrict__ minmax,
                                                              const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
@@ -146,6 +151,8 @@ __global__ void __launch_bounds__(256) clear_classify_kernel(uint32_t* __restric
         cull->parity = parity;
         cull->armed = 1u;
     }
+    // the ring kernels' tile-claim counters: every earlier frame of this set has completed (PDL waits are transitive)
+    if (tid < uint64_t(2 * kMaxTileQueues)) tile_counters(cull, 0)[tid * kTileQueueStride] = 0u;
     // ---- classification first (its appends are what the next kernel waits for), whole warps at a time
     const uint32_t n_round = (n_chunks + 31u) & ~31u;
     for (uint64_t c = tid; c < n_round; c += stride) {
@@ -176,9 +183,13 @@ cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t
 
 cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum,
                                   uint64_t n_px, uint32_t* minmax, const ChunkBounds* bounds, uint32_t n_chunks,
-                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity) {
-    launch_pdl(clear_classify_kernel, dim3(sm_count * 8), dim3(256), s, zbuf, cov, reinterpret_cast<uint4*>(accum), n_px, minmax,
-               bounds, n_chunks, cp, vis_list, cull, parity);
+                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity, bool lean) {
+    if (lean)
+        launch_pdl(clear_classify_kernel<4>, dim3(sm_count * 8), dim3(256), s, zbuf, cov, reinterpret_cast<uint4*>(accum), n_px,
+                   minmax, bounds, n_chunks, cp, vis_list, cull, parity);
+    else
+        launch_pdl(clear_classify_kernel<3>, dim3(sm_count * 8), dim3(256), s, zbuf, cov, reinterpret_cast<uint4*>(accum), n_px,
+                   minmax, bounds, n_chunks, cp, vis_list, cull, parity);
     return cudaGetLastError();
 }
 

@@ -66,6 +66,8 @@ struct rtr_renderer {
     int pipeline = 1;  // asynchronous frame sequences (rtr_render_device, rtr_render_trajectory) alternate between the two frame
                        // sets AND two streams, so frame i+1's point passes overlap frame i's image passes (off with peers / NCCL / timing)
     int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)
+    int ring_dynamic = 8;  // list passes of the ring kernels: tiles beyond a CTA's first ring-full are claimed from this many counters (0: round-robin)
+    int clear_lean = 1;  // clear + classify compiled for <= 64 registers, so that it fits beside the other frame's ring kernel (0: 80 registers)
     int ring_perm = 1;  // stream-all ring passes visit the chunks in a low-discrepancy order (0: storage order)
     int ring = 1;  // point passes through the TMA-fed persistent kernels: 1 = for culled frames, 2 = always, 0 = never
     cudaEvent_t ev[6] = {nullptr};

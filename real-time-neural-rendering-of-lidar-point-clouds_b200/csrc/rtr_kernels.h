@@ -28,6 +28,15 @@ struct CullState {
     uint32_t pad;
     unsigned long long total_visible;
 };
+// The allocation that holds a CullState continues with the ring kernels' tile-claim counters of the frame in flight:
+// kMaxTileQueues counters per point pass ([0] z-min, [1] blend), one per 128-byte line (same-address atomics
+// serialise in L2), zeroed by clear_classify_kernel.
+constexpr int kMaxTileQueues = 64;
+constexpr int kTileQueueStride = 32;  // uint32 words between two counters
+constexpr size_t kCullStateAlloc = 256 + size_t(2) * kMaxTileQueues * kTileQueueStride * sizeof(uint32_t);
+__host__ __device__ inline uint32_t* tile_counters(CullState* c, int pass) {
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c) + 256) + size_t(pass) * kMaxTileQueues * kTileQueueStride;
+}
 __host__ __device__ inline uint32_t cull_count(const CullState* c) { return c->n_visible[c->parity & 1u]; }
 // The frame's camera for the chunk test, in double (exact images of the float camProj rows).
 struct CullParams {
@@ -121,6 +130,9 @@ struct RingSchedule {
     uint32_t n_chunks;
     uint32_t perm_mul;
     uint32_t early;  // blend pass over the list: request the first chunks before the PDL wait (0: measurement only)
+    uint32_t* tile_counter;  // list passes: consumer groups claim their tiles beyond the CTA's first ring-full from
+                             // n_queues counters (tile_counters()), so that faster SMs take more tiles; null = round-robin
+    uint32_t n_queues;       // 1 ... kMaxTileQueues
 };
 RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const uint32_t* vis_list);
 cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
@@ -134,7 +146,7 @@ cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t
 // clear (zbuf coverage, accum, minmax) + per-frame chunk classification in ONE launch; parity alternates per frame.
 cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum,
                                   uint64_t n_px, uint32_t* minmax, const ChunkBounds* bounds, uint32_t n_chunks,
-                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity);
+                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity, bool lean = true);
 cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                         uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,

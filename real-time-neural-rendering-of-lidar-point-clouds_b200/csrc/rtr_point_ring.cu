@@ -83,6 +83,16 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint3
         : "memory");
 }
 
+// Claim the next tile of a launch.  atom.inc with a bound below 2^32 - 1, not atom.add: ptxas warp-aggregates an add
+// (and an inc that can be rewritten as one) to a uniform address — vote + ATOMG by one lane + SHFL of the result — and
+// that shuffle waits for the atomic's round trip on the spot, whereas this result is first read one ring iteration
+// later.  SASS: ATOMG.E.INC, no SHFL.
+__device__ __forceinline__ uint32_t claim_tile(uint32_t* counter) {
+    uint32_t v;
+    asm volatile("atom.relaxed.gpu.global.inc.u32 %0, [%1], 0x7FFFFFFF;" : "=r"(v) : "l"(counter) : "memory");
+    return v;
+}
+
 // Which chunk tile number t of this launch is.  l2 = true: read the list through L2 (used before the PDL wait, when
 // this SM's L1 may still hold last frame's list).
 template <bool LIST>
@@ -94,14 +104,26 @@ __device__ __forceinline__ uint32_t tile_chunk(const RingSchedule& sc, uint32_t 
 // Producer / consumer skeleton shared by both passes.  consume(p, chunk, first, rot, valid): p[s] is record
 // chunk * kChunkPoints + first + (s ^ rot) of the cloud and exists iff (s ^ rot) < valid.
 //
-// Tile k of a CTA is tile blockIdx.x + k * gridDim.x of the launch and lands in stage k % kRingStages.  (Handing
-// tiles out through an atomic counter instead was measured slower — the counter's round trip sits on the refilling
-// thread's path — and leaving the z-min pass's last chunks in L2 for a backwards blend pass was slower too: the
-// streamed lines displace the z-buffer / accumulator lines the REDs need.  profiles/r01h_exp_ring_dynamic.json)
+// The k-th tile a CTA takes lands in stage k % kRingStages.  Its first kRingStages tiles are tiles blockIdx.x +
+// k * gridDim.x of the launch.  What it takes after those is
+//   * round-robin (tile blockIdx.x + k * gridDim.x) when sc.tile_counter is null — stream-all passes;
+//   * the next unclaimed tile of the launch otherwise (list passes, default): the group's refilling thread claims it
+//     from sc.tile_counter ONE ITERATION BEFORE the refill that streams it, so the counter's round trip is covered by a
+//     whole tile of arithmetic.  (Claiming at the moment of the refill was measured slower than round-robin in round 1h:
+//     the round trip then sits on the refilling thread's path.)  ncu of the round-robin kernels showed why tiles
+//     should go to whoever is free: an SM is busy for 74 K ... 102 K of the 110 K cycles of a z-min pass although
+//     every CTA gets an even sample of the list — the SMs do not run equally fast (profiles/r01i_ncu_full_frame_kernels.csv).
+// A stage that gets no tile because the launch has run out of them is marked kNoTile and its `full` barrier completed
+// by a plain arrive; a group stops at the first such stage (claims are handed out in increasing order, so every
+// tile streamed for the group lies before it in the ring).
+// (Leaving the z-min pass's last chunks in L2 for a backwards blend pass was measured slower: the streamed lines
+// displace the z-buffer / accumulator lines the REDs need.  profiles/r01h_exp_ring_dynamic.json)
 //
 // early: the tile list is older than the previous grid (the blend pass: the list was built before the z-min pass),
 // so the first kRingStages chunks of the CTA are requested BEFORE the PDL wait and land while the previous grid drains.
 // Either way this function executes the PDL prologue exactly once for every thread.
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+
 template <bool LIST, typename Consume>
 __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, uint64_t n, const RingSchedule& sc,
                                           RingSmem& sm, const bool early, Consume&& consume) {
@@ -113,12 +135,12 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
     }
     const uint32_t G = gridDim.x;
     // Group g takes k = g, g + kRingGroups, ...; its thread 0 is also the producer of those tiles: once every warp of
-    // the group has copied a tile's records into registers (the stage's `empty` barrier) it streams the tile
-    // kRingStages further on into the freed stage, so each group always has kRingStages / kRingGroups chunks in
-    // flight or landed.
+    // the group has copied a tile's records into registers (the stage's `empty` barrier) it streams another tile
+    // into the freed stage, so each group always has kRingStages / kRingGroups chunks in flight or landed.
     const uint32_t group = threadIdx.x / kRingConsumers, tid = threadIdx.x % kRingConsumers;
     const uint32_t lane = threadIdx.x & 31u, rot = (lane >> 1) & 3u;
     const bool leader = tid == 0;
+    const bool claim_tiles = LIST && sc.tile_counter != nullptr;
     uint64_t policy = 0;
     auto issue = [&](uint32_t stage, uint32_t chunk) {
         sm.chunk[stage] = chunk;
@@ -128,15 +150,29 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
         mbar_arrive_expect_tx(&sm.full[stage], bytes);
         bulk_load(&sm.rec[stage][0], pts + first, bytes, &sm.full[stage], policy);
     };
+    auto end_mark = [&](uint32_t stage) {
+        sm.chunk[stage] = kNoTile;
+        mbar_arrive(&sm.full[stage]);
+    };
     if (leader) {
         policy = l2_policy_evict_first();
 #pragma unroll
         for (uint32_t k = group; k < uint32_t(kRingStages); k += kRingGroups) {
             const uint32_t t = blockIdx.x + k * G;
             if (t < n_tiles) issue(k, tile_chunk<LIST>(sc, t, early));
+            else end_mark(k);
         }
     }
     if (early) pdl_prologue();
+    // The tiles beyond the CTAs' first ring-fulls are dealt round-robin into n_queues queues, each with its own counter
+    // (a different 128-byte line each: atomics on one address serialise in L2, and 12 K claims per pass through one
+    // counter held the refills up); a group claims from queue (2 * blockIdx.x + group) mod n_queues only, so a queue
+    // is shared by groups of 592 / n_queues different CTAs spread over the chip.
+    // claim = how many tiles of its queue had been claimed before this group's next one.
+    const uint32_t Q = sc.n_queues, queue = (blockIdx.x * kRingGroups + group) % Q;
+    uint32_t* const counter = sc.tile_counter + queue * kTileQueueStride;
+    uint32_t claim = 0u;
+    if (claim_tiles && leader) claim = claim_tile(counter);
     // Thread i of a group owns records 4i..4i+3 of the chunk.  A 128-bit LDS is served 8 lanes at a time; lane l reads
     // its record s ^ ((l >> 1) & 3) at step s, so that the 8 lanes of a phase touch 8 different 16-byte bank groups
     // (address/16 mod 8 = 4(l&1) + (s ^ (l>>1 & 3))): conflict-free without padding, one XOR per load.
@@ -145,13 +181,26 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
     // how many of this thread's four records exist in the LAST chunk of the cloud (stale bytes follow them in the stage)
     const uint64_t tail_first = uint64_t(last_chunk) * kChunkPoints + tid * kRingPerThread;
     const uint32_t tail_valid = tail_first + kRingPerThread <= n ? uint32_t(kRingPerThread) : (tail_first < n ? uint32_t(n - tail_first) : 0u);
-    for (uint32_t k = group, t = blockIdx.x + group * G; t < n_tiles; k += kRingGroups, t += kRingGroups * G) {
+    for (uint32_t k = group;; k += kRingGroups) {
         const uint32_t stage = k % kRingStages, parity = (k / kRingStages) & 1u;
-        const uint32_t t_refill = t + kRingStages * G;
-        uint32_t refill_chunk = 0u;
-        if (leader && t_refill < n_tiles) refill_chunk = tile_chunk<LIST>(sc, t_refill);  // in flight during the wait below
+        uint32_t t_refill = kNoTile, refill_chunk = 0u;
+        if (leader) {
+            if (claim_tiles) {
+                if (claim < n_tiles) t_refill = uint32_t(kRingStages) * G + claim * Q + queue;
+            } else {
+                t_refill = blockIdx.x + (k + uint32_t(kRingStages)) * G;
+            }
+            if (t_refill < n_tiles) {
+                refill_chunk = tile_chunk<LIST>(sc, t_refill);               // in flight during the wait below
+                if (claim_tiles) claim = claim_tile(counter);    // for the refill after this one: back by then
+            } else {
+                t_refill = kNoTile;  // and nothing more to claim: every later refill of this group is an end mark too
+                claim = kNoTile;
+            }
+        }
         mbar_wait(&sm.full[stage], parity);
         const uint32_t chunk = sm.chunk[stage];
+        if (chunk == kNoTile) break;  // the whole group reads the same word
         const uint32_t a = lds0 + stage * uint32_t(kChunkPoints * sizeof(PointRecord));
         PointRecord p[kRingPerThread];
 #pragma unroll
@@ -162,9 +211,10 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[stage]);
-        if (leader && t_refill < n_tiles) {
+        if (leader) {
             mbar_wait(&sm.empty[stage], parity);  // the group's other warps are a few instructions behind at most
-            issue(stage, refill_chunk);
+            if (t_refill != kNoTile) issue(stage, refill_chunk);
+            else end_mark(stage);
         }
         consume(p, chunk, tid * kRingPerThread, rot, chunk == last_chunk ? tail_valid : uint32_t(kRingPerThread));
     }
@@ -325,6 +375,8 @@ RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const 
     sc.cull = cull;
     sc.vis_list = vis_list;
     sc.early = 1;
+    sc.tile_counter = nullptr;
+    sc.n_queues = 1;
     sc.n_chunks = uint32_t((n_points + kChunkPoints - 1) / kChunkPoints);
     // golden-ratio stride, made coprime with n_chunks: t -> (t * mul) mod n_chunks is a permutation whose every
     // window of consecutive t is spread evenly over the cloud

@@ -322,6 +322,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
     if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
     sched.early = r->ring_early ? 1u : 0u;
+    sched.n_queues = uint32_t(r->ring_dynamic < 1 ? 1 : (r->ring_dynamic > kMaxTileQueues ? kMaxTileQueues : r->ring_dynamic));
     sched.cull = cull ? fs.cull_state : nullptr;
     sched.vis_list = cull ? fs.vis_list : nullptr;
 
@@ -330,13 +331,14 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         fs.f32acc = false;
         if (cull) {
             fs.cull_parity ^= 1u;
-            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity));
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity, r->clear_lean != 0));
         } else {
             RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, nullptr));
         }
         RTR_CUDA(r, launch_clear_key64(s, r->sm_count, fb.zkey, cov));
         r->launches += 2;
         if (r->timing) cudaEventRecord(ev[1], s);
+        sched.tile_counter = (cull && r->ring_dynamic > 0) ? tile_counters(fs.cull_state, 0) : nullptr;
         if (use_ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, fb.zkey));
         else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, fs.cull_state, fs.vis_list, fb.zbuf, fb.zkey));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
@@ -358,12 +360,13 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     } else {
         if (cull) {
             fs.cull_parity ^= 1u;
-            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity));
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity, r->clear_lean != 0));
         } else {
             RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, nullptr));
         }
         r->launches += 1;
         if (r->timing) cudaEventRecord(ev[1], s);
+        sched.tile_counter = (cull && r->ring_dynamic > 0) ? tile_counters(fs.cull_state, 0) : nullptr;
         if (use_ring) RTR_CUDA(r, launch_zmin_ring(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, sched, cull, fb.zbuf, nullptr));
         else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant, r->points, r->n_points, r->index_base, pp, fs.cull_state, fs.vis_list, fb.zbuf, nullptr));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
@@ -385,6 +388,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         const int bv = int_sums ? (r->blend_variant & ~4) : r->blend_variant;
         const bool f32acc = (bv & 4) != 0;
         fs.f32acc = f32acc;
+        sched.tile_counter = (cull && r->ring_dynamic > 0) ? tile_counters(fs.cull_state, 1) : nullptr;
         if (use_ring) RTR_CUDA(r, launch_blend_ring(s, r->sm_count, bv, r->points, r->n_points, pp, sched, cull, fb.zbuf, fb.accum));
         else if (cull) RTR_CUDA(r, launch_blend_list(s, r->sm_count, bv, r->points, r->n_points, pp, fs.cull_state, fs.vis_list, fb.zbuf, fb.accum, nullptr));
         else RTR_CUDA(r, launch_blend(s, bv, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, nullptr));
@@ -577,8 +581,8 @@ int build_chunk_bounds(rtr_renderer* r) {
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->bounds), size_t(r->n_chunks) * sizeof(ChunkBounds)));
     for (auto& fs : r->set) {
         RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.vis_list), size_t(r->n_chunks) * sizeof(uint32_t)));
-        RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.cull_state), sizeof(CullState)));
-        RTR_CUDA(r, cudaMemsetAsync(fs.cull_state, 0, sizeof(CullState), r->stream));
+        RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.cull_state), kCullStateAlloc));  // + the tile-claim counters
+        RTR_CUDA(r, cudaMemsetAsync(fs.cull_state, 0, kCullStateAlloc, r->stream));
         fs.cull_parity = 0;
     }
     RTR_CUDA(r, launch_chunk_bounds(r->stream, r->points, r->n_points, r->bounds));
@@ -932,6 +936,8 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "fused_up")) return &r->fused_up;
     if (!std::strcmp(key, "ring_perm")) return &r->ring_perm;
     if (!std::strcmp(key, "ring_early")) return &r->ring_early;
+    if (!std::strcmp(key, "ring_dynamic")) return &r->ring_dynamic;
+    if (!std::strcmp(key, "clear_lean")) return &r->clear_lean;
     if (!std::strcmp(key, "pipeline")) return &r->pipeline;
     return nullptr;
 }

@@ -30,6 +30,9 @@ def main():
     out = {"workload": wl, "points": n, "frames": len(poses), "runs": {}}
     combos = [
         ("default", dict()),
+        ("round_robin", dict(ring_dynamic=0)),
+        ("default_again", dict()),
+        ("round_robin_again", dict(ring_dynamic=0)),
         ("nomerge", dict(zmin_variant=37, blend_variant=36)),
         ("up_per_level", dict(fused_up=0)),
         ("no_early", dict(ring_early=0)),
@@ -42,7 +45,7 @@ def main():
         ("all_ring_nored", dict(chunk_cull=0, ring=2, zmin_variant=13)),
         ("all_ldg_red", dict(ring=0, chunk_cull=0)),
     ]
-    defaults = dict(ring=1, zmin_variant=5, blend_variant=4, chunk_cull=1, fused_up=1, ring_perm=1, ring_early=1)
+    defaults = dict(ring=1, zmin_variant=5, blend_variant=4, chunk_cull=1, fused_up=1, ring_perm=1, ring_early=1, ring_dynamic=1)
     stage_times(pc, pkg, poses, len(poses))  # warm-up
     for name, opts in combos:
         for k, v in {**defaults, **opts}.items():
