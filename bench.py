@@ -481,7 +481,7 @@ def run_b200(args, wl):
                                     ("point-sharded, ncclAllReduce min/sum" if args.nccl else "point-sharded, two-shot min/sum all-reduce kernels over NVLink peer memory")),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
                        "distortion": bool(args.distort),
-                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "fused_up", "pipeline", "zmin_variant", "blend_variant", "key64")}},
+                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "ring_dynamic", "clear_lean", "fused_up", "pipeline", "zmin_variant", "blend_variant", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

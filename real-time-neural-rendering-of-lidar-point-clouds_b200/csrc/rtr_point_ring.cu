@@ -106,13 +106,17 @@ __device__ __forceinline__ uint32_t tile_chunk(const RingSchedule& sc, uint32_t 
 //
 // The k-th tile a CTA takes lands in stage k % kRingStages.  Its first kRingStages tiles are tiles blockIdx.x +
 // k * gridDim.x of the launch.  What it takes after those is
-//   * round-robin (tile blockIdx.x + k * gridDim.x) when sc.tile_counter is null — stream-all passes;
-//   * the next unclaimed tile of the launch otherwise (list passes, default): the group's refilling thread claims it
-//     from sc.tile_counter ONE ITERATION BEFORE the refill that streams it, so the counter's round trip is covered by a
-//     whole tile of arithmetic.  (Claiming at the moment of the refill was measured slower than round-robin in round 1h:
-//     the round trip then sits on the refilling thread's path.)  ncu of the round-robin kernels showed why tiles
-//     should go to whoever is free: an SM is busy for 74 K ... 102 K of the 110 K cycles of a z-min pass although
-//     every CTA gets an even sample of the list — the SMs do not run equally fast (profiles/r01i_ncu_full_frame_kernels.csv).
+//   * round-robin (tile blockIdx.x + k * gridDim.x) when sc.tile_counter is null — stream-all passes, ring_dynamic = 0;
+//   * claimed (list passes, default): ncu of the round-robin kernels showed an SM busy for 74 K ... 102 K of the 110 K
+//     cycles of a z-min pass although every CTA gets an even sample of the list — the SMs do not run equally fast — so
+//     tiles should go to whoever is free.  The remaining tiles are dealt into sc.n_queues queues (tile 6G + c * Q + q is
+//     entry c of queue q), each with its own counter on its own 128-byte line; a consumer group belongs to queue
+//     (2 * blockIdx.x + group) mod Q and its refilling thread claims entry c ONE ITERATION BEFORE the refill that
+//     streams it, so the counter's round trip is covered by a whole tile of arithmetic.  Two things made earlier
+//     attempts slower than round-robin (profiles/r01j_exp_ring_dynamic.json): ptxas warp-aggregates atomicAdd on a
+//     uniform address (vote + ATOMG + SHFL of the result: the shuffle waits for the round trip on the spot), and
+//     12.5 K claims per pass on ONE address serialise in L2 until the refills run late (44 % of the blend pass's stall
+//     samples on the wait for the tile's bytes).  With 4-16 queues: z-min 57 -> 54 us, blend 59 -> 56 us on C3.
 // A stage that gets no tile because the launch has run out of them is marked kNoTile and its `full` barrier completed
 // by a plain arrive; a group stops at the first such stage (claims are handed out in increasing order, so every
 // tile streamed for the group lies before it in the ring).

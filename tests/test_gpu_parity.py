@@ -166,6 +166,8 @@ VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u,
                                   (0, 4, 2, 1, 0), (1, 4, 0, 1, 0), (3, 4, 0, 1, 0), (7, 4, 2, 1, 0), (5, 4, 4, 1, 0), (5, 4, 6, 0, 0),
                                   (5, 2, 4, 0, 0), (21, 4, 4, 1, 0),
                                   (0, 4, 0, 0, 2), (1, 4, 4, 0, 2), (5, 4, 4, 0, 2), (0, 4, 4, 1, 1), (1, 4, 0, 1, 1), (5, 4, 0, 1, 2)]]
+# ring_dynamic: how the list passes of the ring kernels hand out tiles — 0 round-robin, q > 0 claimed from q counters
+VARIANTS += [dict(ring=1, chunk_cull=1, ring_dynamic=q) for q in (0, 1, 3, 64)] + [dict(ring=1, chunk_cull=1, clear_lean=0)]
 
 
 @pytest.mark.parametrize("opts", VARIANTS)
@@ -365,7 +367,8 @@ def test_cloud_sizes_around_chunk_and_ring_boundaries(gpu, cpu_oracle, n):
     calib, E = calib_of(gpu, case), case.poses[0]
     outs = {}
     for name, opts in (("ring_list", dict(ring=1)), ("ring_all", dict(ring=2, chunk_cull=0)), ("ldg_list", dict(ring=0)),
-                       ("ldg_all", dict(ring=0, chunk_cull=0)), ("ring_key64", dict(ring=2, key64=1)), ("ldg_key64", dict(ring=0, key64=1))):
+                       ("ldg_all", dict(ring=0, chunk_cull=0)), ("ring_key64", dict(ring=2, key64=1)), ("ldg_key64", dict(ring=0, key64=1)),
+                       ("ring_list_rr", dict(ring=1, ring_dynamic=0)), ("ring_list_q1", dict(ring=1, ring_dynamic=1))):
         pc = gpu.ProjectCloud.from_packed(rec, sort=False)
         for k, v in opts.items():
             pc.set_option(k, v)
@@ -376,7 +379,7 @@ def test_cloud_sizes_around_chunk_and_ring_boundaries(gpu, cpu_oracle, n):
             tap = pc.project_points()
         pc.close()
     gold = cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(rec), W, H, filtered=True)
-    for name in ("ring_list", "ring_all", "ldg_list", "ldg_all"):
+    for name in ("ring_list", "ring_all", "ldg_list", "ldg_all", "ring_list_rr", "ring_list_q1"):
         assert np.array_equal(outs[name][0], gold["image"]) and np.array_equal(outs[name][1], gold["zbuf"]), name
         assert np.array_equal(outs[name][2], gold["tensor"]), name
     for a, b in zip(outs["ring_key64"], outs["ldg_key64"]):
@@ -395,8 +398,11 @@ def test_large_cloud_ring_equals_per_thread_kernels(gpu):
     poses = [gpu.look_at_w2c((0.3, 0.3, 2.7), (1.0, 0.8, -0.2)), gpu.look_at_w2c((6.0, 5.0, 1.5), (1.0, 0.3, 0.0))]
     pc = gpu.ProjectCloud.synthetic(seed=4242, n_total=n, hall=scenes.HALL_LARGE, n_boxes=12)
     digests = {}
-    for name, opts in (("ring", dict(ring=1, chunk_cull=1)), ("ldg_list", dict(ring=0, chunk_cull=1)), ("ldg_all", dict(ring=0, chunk_cull=0)),
-                       ("ring_all", dict(ring=2, chunk_cull=0))):
+    dyn = pc.get_option("ring_dynamic")
+    assert dyn > 0   # the default claims tiles from counters
+    for name, opts in (("ring", dict(ring=1, chunk_cull=1)), ("ring_rr", dict(ring_dynamic=0)), ("ring_q1", dict(ring_dynamic=1)),
+                       ("ring_q64", dict(ring_dynamic=64)), ("ldg_list", dict(ring=0, chunk_cull=1, ring_dynamic=dyn)),
+                       ("ldg_all", dict(ring=0, chunk_cull=0)), ("ring_all", dict(ring=2, chunk_cull=0))):
         for k, v in opts.items():
             pc.set_option(k, v)
         out = []
@@ -417,7 +423,7 @@ def test_large_cloud_ring_equals_per_thread_kernels(gpu):
     fr, vis, nch = pc.cull_stats(reset=True)
     pc.close()
     assert fr == 4 and vis / fr > 0.3 * nch          # the corner view really sees a large part of the cloud
-    for name in ("ldg_list", "ldg_all", "ring_all"):
+    for name in ("ring_rr", "ring_q1", "ring_q64", "ldg_list", "ldg_all", "ring_all"):
         assert digests[name] == digests["ring"], name
     for i in range(4):
         assert scenes.sha(color[i]) + scenes.sha(depth[i]) == digests["ring"][i % 2][:128], f"trajectory frame {i}"
