@@ -65,7 +65,7 @@ def main():
     out["identical_frames"] = sums[0] == sums[8]
     print("identical frames:", out["identical_frames"], flush=True)
     frame_rate(pc, pkg, poses, 200)  # warm-up
-    combos = [dict(ring_dynamic=d) for d in (0, 4, 8)]
+    combos = [dict(ring_dynamic=d) for d in (0, 4, 8, 16)]
     for combo in combos + combos:
         for k, v in combo.items():
             pc.set_option(k, v)
