@@ -5,6 +5,9 @@ frame at a time) and the frame rate of `frames` back-to-back asynchronous frames
 that the two settings give byte-identical frames.  Writes gpurun_out/exp_ring_dynamic_<workload>.json.
 
     python tools/experiments/ring_dynamic_ab.py [workload=c3] [frames=1000] [key=value ...]   (extra renderer options)
+    python tools/experiments/ring_dynamic_ab.py c3 1000 combos zmin_variant=13 zmin_variant=8,ring_dynamic=0 ...
+        (after the word "combos": one comma-separated option set per argument, measured in turn, twice, against the
+         defaults; variants with bit 3 set are timing-only — they issue no REDs and their frames are wrong)
 """
 import json
 import os
@@ -48,7 +51,13 @@ def checksums(pc, pkg, poses, W, H):
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-    extra = dict((k, int(v)) for k, v in (a.split("=") for a in sys.argv[3:]))
+    rest = sys.argv[3:]
+    custom = None
+    if "combos" in rest:
+        i = rest.index("combos")
+        custom = [dict((k, int(v)) for k, v in (kv.split("=") for kv in a.split(","))) for a in rest[i + 1:]]
+        rest = rest[:i]
+    extra = dict((k, int(v)) for k, v in (a.split("=") for a in rest))
     pkg = entry.load_package()
     n, W, H, f, cx, cy, hall, boxes, seed, n_poses = bench.WORKLOADS[wl]
     pc = pkg.ProjectCloud.synthetic(seed=seed, n_total=n, hall=hall, n_boxes=boxes)
@@ -66,8 +75,11 @@ def main():
     print("identical frames:", out["identical_frames"], flush=True)
     frame_rate(pc, pkg, poses, 200)  # warm-up
     combos = [dict(ring_dynamic=d) for d in (0, 4, 8, 16)]
+    if custom is not None:
+        combos = [dict()] + custom
+    defaults = {k: pc.get_option(k) for c in combos for k in c}
     for combo in combos + combos:
-        for k, v in combo.items():
+        for k, v in {**defaults, **combo}.items():
             pc.set_option(k, v)
         stage_times(pc, pkg, sub, 4)
         st = dict(zip(NAMES, stage_times(pc, pkg, sub, len(sub))))
