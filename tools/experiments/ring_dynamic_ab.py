@@ -68,9 +68,11 @@ def main():
     sub = np.ascontiguousarray(poses[:: max(1, len(poses) // 40)][:40])
     out = {"workload": wl, "points": n, "frames": frames, "options": extra, "runs": []}
     sums = {}
+    default_queues = pc.get_option("ring_dynamic")
     for dyn in (8, 0):
         pc.set_option("ring_dynamic", dyn)
         sums[dyn] = checksums(pc, pkg, sub, W, H)   # the float colour sums are exact integers: they compare byte for byte too
+    pc.set_option("ring_dynamic", default_queues)
     out["identical_frames"] = sums[0] == sums[8]
     print("identical frames:", out["identical_frames"], flush=True)
     frame_rate(pc, pkg, poses, 200)  # warm-up
