@@ -133,6 +133,7 @@ struct RingSchedule {
     uint32_t* tile_counter;  // list passes: consumer groups claim their tiles beyond the CTA's first ring-full from
                              // n_queues counters (tile_counters()), so that faster SMs take more tiles; null = round-robin
     uint32_t n_queues;       // 1 ... kMaxTileQueues
+    uint32_t ctas_per_sm;    // host side: CTAs launched per SM (2 fill an SM's shared memory; 1 leaves room for another frame's ring kernel)
 };
 RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const uint32_t* vis_list);
 cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,

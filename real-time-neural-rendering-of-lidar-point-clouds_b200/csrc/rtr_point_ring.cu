@@ -381,6 +381,7 @@ RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const 
     sc.early = 1;
     sc.tile_counter = nullptr;
     sc.n_queues = 1;
+    sc.ctas_per_sm = kRingCtasPerSm;
     sc.n_chunks = uint32_t((n_points + kChunkPoints - 1) / kChunkPoints);
     // golden-ratio stride, made coprime with n_chunks: t -> (t * mul) mod n_chunks is a permutation whose every
     // window of consecutive t is spread evenly over the cloud
@@ -404,7 +405,7 @@ static cudaError_t ring_attr(K kernel, bool* done) {
     return e;
 }
 static unsigned ring_grid(int sm_count, const RingSchedule& sc, bool list) {
-    unsigned grid = unsigned(sm_count) * unsigned(kRingCtasPerSm);
+    unsigned grid = unsigned(sm_count) * (sc.ctas_per_sm >= 1u && sc.ctas_per_sm <= unsigned(kRingCtasPerSm) ? sc.ctas_per_sm : unsigned(kRingCtasPerSm));
     if (!list && sc.n_chunks < grid) grid = sc.n_chunks ? sc.n_chunks : 1u;
     return grid;
 }

@@ -322,6 +322,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
     if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
     sched.early = r->ring_early ? 1u : 0u;
+    sched.ctas_per_sm = uint32_t(r->ring_ctas);
     sched.n_queues = uint32_t(r->ring_dynamic < 1 ? 1 : (r->ring_dynamic > kMaxTileQueues ? kMaxTileQueues : r->ring_dynamic));
     sched.cull = cull ? fs.cull_state : nullptr;
     sched.vis_list = cull ? fs.vis_list : nullptr;
@@ -938,6 +939,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "ring_early")) return &r->ring_early;
     if (!std::strcmp(key, "ring_dynamic")) return &r->ring_dynamic;
     if (!std::strcmp(key, "clear_lean")) return &r->clear_lean;
+    if (!std::strcmp(key, "ring_ctas")) return &r->ring_ctas;
     if (!std::strcmp(key, "pipeline")) return &r->pipeline;
     return nullptr;
 }
