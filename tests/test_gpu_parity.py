@@ -168,6 +168,8 @@ VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u,
                                   (0, 4, 0, 0, 2), (1, 4, 4, 0, 2), (5, 4, 4, 0, 2), (0, 4, 4, 1, 1), (1, 4, 0, 1, 1), (5, 4, 0, 1, 2)]]
 # ring_dynamic: how the list passes of the ring kernels hand out tiles — 0 round-robin, q > 0 claimed from q counters
 VARIANTS += [dict(ring=1, chunk_cull=1, ring_dynamic=q) for q in (0, 1, 3, 64)] + [dict(ring=1, chunk_cull=1, clear_lean=0)]
+# ring_ctas = 1: one ring-kernel CTA per SM (half the grid)
+VARIANTS += [dict(ring=1, chunk_cull=1, ring_ctas=1), dict(ring=2, chunk_cull=0, ring_ctas=1), dict(ring=1, chunk_cull=1, ring_ctas=1, ring_dynamic=0)]
 
 
 @pytest.mark.parametrize("opts", VARIANTS)
@@ -401,7 +403,8 @@ def test_large_cloud_ring_equals_per_thread_kernels(gpu):
     dyn = pc.get_option("ring_dynamic")
     assert dyn > 0   # the default claims tiles from counters
     for name, opts in (("ring", dict(ring=1, chunk_cull=1)), ("ring_rr", dict(ring_dynamic=0)), ("ring_q1", dict(ring_dynamic=1)),
-                       ("ring_q64", dict(ring_dynamic=64)), ("ldg_list", dict(ring=0, chunk_cull=1, ring_dynamic=dyn)),
+                       ("ring_q64", dict(ring_dynamic=64)), ("ring_1cta", dict(ring_dynamic=dyn, ring_ctas=1)),
+                       ("ldg_list", dict(ring=0, chunk_cull=1, ring_ctas=2)),
                        ("ldg_all", dict(ring=0, chunk_cull=0)), ("ring_all", dict(ring=2, chunk_cull=0))):
         for k, v in opts.items():
             pc.set_option(k, v)
@@ -423,7 +426,7 @@ def test_large_cloud_ring_equals_per_thread_kernels(gpu):
     fr, vis, nch = pc.cull_stats(reset=True)
     pc.close()
     assert fr == 4 and vis / fr > 0.3 * nch          # the corner view really sees a large part of the cloud
-    for name in ("ring_rr", "ring_q1", "ring_q64", "ldg_list", "ldg_all", "ring_all"):
+    for name in ("ring_rr", "ring_q1", "ring_q64", "ring_1cta", "ldg_list", "ldg_all", "ring_all"):
         assert digests[name] == digests["ring"], name
     for i in range(4):
         assert scenes.sha(color[i]) + scenes.sha(depth[i]) == digests["ring"][i % 2][:128], f"trajectory frame {i}"
