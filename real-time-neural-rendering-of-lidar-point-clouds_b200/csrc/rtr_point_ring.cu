@@ -34,6 +34,10 @@ constexpr int kRingGroups = 2;                        // consumer groups per CTA
 constexpr int kRingConsumers = kPointBlock;           // a group: 256 threads x 4 consecutive records = one chunk
 constexpr int kRingThreads = kRingGroups * kRingConsumers;  // 512: no dedicated producer warp, thread 0 of a group refills its stages
 constexpr int kRingCtasPerSm = 2;                     // 2 x (96 KB ring + barriers) per SM: 32 warps, up to 64 registers
+// What __launch_bounds__ is told.  3 (shared memory admits 2 anyway) would cap the kernels at 40 registers without a
+// spill and leave 24 K instead of 16 K registers per SM to the other frame's image kernels: measured 3 % SLOWER with two
+// frames in flight (profiles/r01j_exp_ring_dynamic.json, section 7), so the kernels keep their 48.
+constexpr int kRingMinCtas = 2;
 constexpr int kRingPerThread = kChunkPoints / kRingConsumers;
 static_assert(kRingStages % kRingGroups == 0, "every group must own a fixed subset of the stages");
 static_assert(kRingPerThread == 4, "the bank-conflict-free XOR swizzle below assumes 4 records per thread");
@@ -243,7 +247,7 @@ __device__ __forceinline__ RingSmem& ring_setup() {
 // VARIANT bit 0: early depth test, bit 2: through L1 (ld.ca), bit 3: measurement only — no RED issued,
 // bit 5: measurement only — no in-register merge of same-pixel neighbours.
 template <int VARIANT, bool DISTORT, int KEY64, bool LIST>
-__global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) zmin_ring_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+__global__ void __launch_bounds__(kRingThreads, kRingMinCtas) zmin_ring_kernel(const PointRecord* __restrict__ pts, uint64_t n,
                                                                  uint64_t index_base,
                                                                  const __grid_constant__ ProjParams pp,
                                                                  const __grid_constant__ RingSchedule sc,
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) zmin_ring_kernel
 // VARIANT bit 2: float accumulators, one RED.ADD.F32x4 per (thread, pixel); else two RED.ADD.64 on the
 // reference's 4 x u32 layout.
 template <int VARIANT, bool DISTORT, bool LIST>
-__global__ void __launch_bounds__(kRingThreads, kRingCtasPerSm) blend_ring_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+__global__ void __launch_bounds__(kRingThreads, kRingMinCtas) blend_ring_kernel(const PointRecord* __restrict__ pts, uint64_t n,
                                                                   const __grid_constant__ ProjParams pp,
                                                                   const __grid_constant__ RingSchedule sc,
                                                                   const uint32_t* __restrict__ zbuf,
