@@ -164,6 +164,15 @@ int rtr_host_distortion_bounds(int width, int height, const double* K9, const do
  * visits the cloud's 1024-point chunks, tile t -> chunk (t * m) mod n_chunks; coprime with n_chunks, i.e. a permutation. */
 uint32_t rtr_host_ring_stride(uint64_t n_points);
 
+/* Host-only helper: how the ring kernels' list passes hand out tiles (option ring_dynamic = n_queues > 0).  A launch of
+ * `grid` CTAs, each with *groups_per_cta consumer groups and a ring of *stages stages: the CTA's first *stages tiles are
+ * tiles block + k * grid; every tile from *stages * grid on is entry `claim` of one of n_queues queues, and consumer
+ * group `group` of CTA `block` claims from *queue only (one atomic counter per queue; n_queues is first clamped to the
+ * number of groups, grid * *groups_per_cta, so that no queue is left without a group).  Returns the queue of that group
+ * and the tile its claim number `claim` stands for. */
+int rtr_host_ring_claim(uint32_t grid, uint32_t n_queues, uint32_t block, uint32_t group, uint32_t claim, uint32_t* queue,
+                        uint32_t* tile, uint32_t* stages, uint32_t* groups_per_cta);
+
 /* Device self-test of the ring kernels' perspective divide: for n_pairs random bit patterns (a, b) (every class of
  * float: NaN, inf, denormal, huge) checks on the GPU that whenever !(|b| < 2^-126) the directly issued
  * MUFU.RCP + FMUL gives the same bits as __fdividef(a, b) (what the reference compiles, render.cu:65-66), and the same

@@ -68,6 +68,8 @@ API = {
     "rtr_selftest_fast_divide": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),
     "rtr_host_distortion_bounds": (_i, [_i, _i, _dp, _dp, _dp, _dp]),
     "rtr_host_ring_stride": (C.c_uint32, [_u64]),
+    "rtr_host_ring_claim": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rtr_comm_unique_id": (_i, [_vp]),
     "rtr_comm_init": (_i, [_vp, _vp, _i, _i]),
     "rtr_comm_destroy": (_i, [_vp]),

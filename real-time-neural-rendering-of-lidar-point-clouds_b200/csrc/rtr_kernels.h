@@ -135,7 +135,25 @@ struct RingSchedule {
     uint32_t n_queues;       // 1 ... kMaxTileQueues
     uint32_t ctas_per_sm;    // host side: CTAs launched per SM (2 fill an SM's shared memory; 1 leaves room for another frame's ring kernel)
 };
+// Claimed tiles (list passes): a CTA's first `stages` tiles are tiles blockIdx.x + k * grid of the launch; the tiles from
+// stages * grid on are dealt round-robin into n_queues queues, entry c of queue q being this tile.  Every tile index
+// >= stages * grid is entry (t - stages * grid) / n_queues of queue (t - stages * grid) % n_queues: a bijection.
+__host__ __device__ inline uint32_t ring_claimed_tile(uint32_t grid, uint32_t stages, uint32_t n_queues, uint32_t queue, uint32_t claim) {
+    return stages * grid + claim * n_queues + queue;
+}
+// Every queue needs a group that claims from it: with fewer consumer groups than queues the tiles dealt to the
+// orphaned queues would never be streamed.  The launchers (and rtr_host_ring_claim) clamp the queue count with this.
+__host__ __device__ inline uint32_t ring_effective_queues(uint32_t grid, uint32_t groups_per_cta, uint32_t n_queues) {
+    const uint32_t groups = grid * groups_per_cta;
+    const uint32_t q = n_queues < groups ? n_queues : groups;
+    return q < 1u ? 1u : q;
+}
+// The queue a consumer group claims from.
+__host__ __device__ inline uint32_t ring_queue_of(uint32_t block, uint32_t group, uint32_t groups_per_cta, uint32_t n_queues) {
+    return (block * groups_per_cta + group) % n_queues;
+}
 RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const uint32_t* vis_list);
+void ring_geometry(uint32_t* stages, uint32_t* groups_per_cta, uint32_t* ctas_per_sm);  // the ring kernels' compile-time shape
 cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
                              uint64_t index_base, const ProjParams& pp, const RingSchedule& sc, bool list, uint32_t* zbuf,
                              unsigned long long* zkey);

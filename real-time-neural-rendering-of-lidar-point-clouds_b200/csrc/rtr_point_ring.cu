@@ -177,7 +177,7 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
     // counter held the refills up); a group claims from queue (2 * blockIdx.x + group) mod n_queues only, so a queue
     // is shared by groups of 592 / n_queues different CTAs spread over the chip.
     // claim = how many tiles of its queue had been claimed before this group's next one.
-    const uint32_t Q = sc.n_queues, queue = (blockIdx.x * kRingGroups + group) % Q;
+    const uint32_t Q = sc.n_queues, queue = ring_queue_of(blockIdx.x, group, kRingGroups, Q);
     uint32_t* const counter = sc.tile_counter + queue * kTileQueueStride;
     uint32_t claim = 0u;
     if (claim_tiles && leader) claim = claim_tile(counter);
@@ -194,7 +194,7 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
         uint32_t t_refill = kNoTile, refill_chunk = 0u;
         if (leader) {
             if (claim_tiles) {
-                if (claim < n_tiles) t_refill = uint32_t(kRingStages) * G + claim * Q + queue;
+                if (claim < n_tiles) t_refill = ring_claimed_tile(G, kRingStages, Q, queue, claim);
             } else {
                 t_refill = blockIdx.x + (k + uint32_t(kRingStages)) * G;
             }
@@ -442,11 +442,19 @@ static cudaError_t launch_zmin_ring_v(cudaStream_t s, unsigned grid, const Point
     return cudaGetLastError();
 }
 
+void ring_geometry(uint32_t* stages, uint32_t* groups_per_cta, uint32_t* ctas_per_sm) {
+    *stages = kRingStages;
+    *groups_per_cta = kRingGroups;
+    *ctas_per_sm = kRingCtasPerSm;
+}
+
 cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
-                             uint64_t index_base, const ProjParams& pp, const RingSchedule& sc, bool list, uint32_t* zbuf,
+                             uint64_t index_base, const ProjParams& pp, const RingSchedule& sc_in, bool list, uint32_t* zbuf,
                              unsigned long long* zkey) {
     if (n == 0) return cudaSuccess;
-    const unsigned grid = ring_grid(sm_count, sc, list);
+    const unsigned grid = ring_grid(sm_count, sc_in, list);
+    RingSchedule sc = sc_in;
+    sc.n_queues = ring_effective_queues(grid, kRingGroups, sc.n_queues);
     switch (variant & 45) {  // bit 1 (warp aggregation) has no ring form: the in-register merge replaces it
         case 37: return launch_zmin_ring_v<37>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
         case 0: return launch_zmin_ring_v<0>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
@@ -460,9 +468,11 @@ cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const Po
 }
 
 cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
-                              const ProjParams& pp, const RingSchedule& sc, bool list, const uint32_t* zbuf, uint32_t* accum) {
+                              const ProjParams& pp, const RingSchedule& sc_in, bool list, const uint32_t* zbuf, uint32_t* accum) {
     if (n == 0) return cudaSuccess;
-    const unsigned grid = ring_grid(sm_count, sc, list);
+    const unsigned grid = ring_grid(sm_count, sc_in, list);
+    RingSchedule sc = sc_in;
+    sc.n_queues = ring_effective_queues(grid, kRingGroups, sc.n_queues);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     const bool f32 = (variant & 4) != 0;
     if (list && !pp.distort && f32 && (variant & 32)) {  // measurement: no in-register merge

@@ -448,6 +448,18 @@ int render_to_host(rtr_renderer* r, int stage, uint8_t* bgr, float* depth) {
 
 }  // namespace
 
+extern "C" int rtr_host_ring_claim(uint32_t grid, uint32_t n_queues, uint32_t block, uint32_t group, uint32_t claim, uint32_t* queue,
+                                   uint32_t* tile, uint32_t* stages, uint32_t* groups_per_cta) {
+    uint32_t st = 0, gr = 0, cps = 0;
+    ring_geometry(&st, &gr, &cps);
+    if (n_queues < 1 || n_queues > uint32_t(kMaxTileQueues) || group >= gr || !queue || !tile) return RTR_ERR_ARG;
+    n_queues = ring_effective_queues(grid, gr, n_queues);   // what the launchers do: no queue without a group
+    *queue = ring_queue_of(block, group, gr, n_queues);
+    *tile = ring_claimed_tile(grid, st, n_queues, *queue, claim);
+    if (stages) *stages = st;
+    if (groups_per_cta) *groups_per_cta = gr;
+    return RTR_OK;
+}
 extern "C" uint32_t rtr_host_ring_stride(uint64_t n_points) { return make_ring_schedule(n_points, nullptr, nullptr).perm_mul; }
 
 extern "C" int rtr_host_distortion_bounds(int W, int H, const double* K9, const double* dist5, double* r2_max, double* rstar) {

@@ -103,3 +103,68 @@ def test_ring_stream_all_order_is_a_permutation(pkg):
             assert sorted((t * m) % n_chunks for t in range(n_chunks)) == list(range(n_chunks))
         if n_chunks >= 1000:   # golden-ratio stride: any 64 consecutive tiles land in at least 32 different 64ths of the cloud
             assert len({((t * m) % n_chunks) * 64 // n_chunks for t in range(64)}) >= 32
+
+
+def test_ring_tile_claims_cover_every_tile_once(pkg):
+    """rtr_host_ring_claim is the arithmetic the ring kernels' list passes use to hand out tiles (csrc/rtr_kernels.h:
+    ring_queue_of / ring_claimed_tile).  Replay the protocol of csrc/rtr_point_ring.cu:ring_walk on the CPU with consumer
+    groups advancing in random order: a CTA's first `stages` tiles are fixed; every refill streams the tile claimed from
+    the group's queue one iteration earlier; a group stops at the first stage that got no tile.  Every tile of the launch
+    must be consumed exactly once and every group must stop, for any grid / queue count / tile count."""
+    import ctypes as C
+    import random
+    lib = pkg.load_library()
+    u32 = C.c_uint32
+
+    def claim_of(grid, nq, block, group, claim):
+        q, t, st, gr = u32(), u32(), u32(), u32()
+        assert lib.rtr_host_ring_claim(grid, nq, block, group, claim, C.byref(q), C.byref(t), C.byref(st), C.byref(gr)) == 1
+        return q.value, t.value, st.value, gr.value
+
+    _, _, stages, groups = claim_of(1, 1, 0, 0, 0)
+    assert stages % groups == 0
+    assert lib.rtr_host_ring_claim(4, 0, 0, 0, 0, C.byref(u32()), C.byref(u32()), None, None) < 0        # no queue
+    assert lib.rtr_host_ring_claim(4, 1, 0, groups, 0, C.byref(u32()), C.byref(u32()), None, None) < 0   # no such group
+    rng = random.Random(5)
+    for grid, nq, n_tiles in [(4, 1, 0), (4, 1, 3), (4, 3, 24), (4, 3, 25), (6, 8, 500), (296, 8, 12535), (296, 64, 1777), (148, 5, 4000), (3, 64, 200)]:
+        counters = [0] * nq
+        seen = [0] * n_tiles
+        NO = None
+        state = []   # per group: ring (stage -> tile or NO), pending claim, next k
+        for block in range(grid):
+            for g in range(groups):
+                ring = {}
+                for k in range(g, stages, groups):          # the fixed first ring-full
+                    t = block + k * grid
+                    ring[k % stages] = t if t < n_tiles else NO
+                q = claim_of(grid, nq, block, g, 0)[0]
+                c = counters[q]; counters[q] += 1            # the claim made before the loop
+                state.append(dict(block=block, g=g, q=q, ring=ring, claim=c, k=g, done=False))
+        live = list(range(len(state)))
+        steps = 0
+        while live:
+            i = rng.choice(live)
+            s = state[i]
+            stage = s["k"] % stages
+            # the refill this iteration will issue: the tile claimed one iteration ago
+            t_refill = NO
+            if s["claim"] is not NO and s["claim"] < n_tiles:
+                t = claim_of(grid, nq, s["block"], s["g"], s["claim"])[1]
+                if t < n_tiles:
+                    t_refill = t
+            if t_refill is not NO:
+                s["claim"] = counters[s["q"]]; counters[s["q"]] += 1
+            else:
+                s["claim"] = NO
+            tile = s["ring"][stage]
+            if tile is NO:                                   # end mark: the group stops
+                s["done"] = True
+                live.remove(i)
+                continue
+            seen[tile] += 1
+            s["ring"][stage] = t_refill
+            s["k"] += groups
+            steps += 1
+            assert steps <= n_tiles + 1
+        assert all(v == 1 for v in seen), (grid, nq, n_tiles, [j for j, v in enumerate(seen) if v != 1][:5])
+        assert all(s["done"] for s in state)
