@@ -127,7 +127,8 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
 /* ---- options / introspection.  Known keys: "zmin_variant" (bit0 early test, bit1 warp
  * aggregation, bit2 L1-cached test), "zmin_unroll", "blend_variant", "blend_unroll",
  * "force_generic", "keep_masks", "timing", "key64", "chunk_cull", "ring", "ring_dynamic" (default 8: the ring kernels'
- * list passes claim their tiles from this many counters; 0 = round-robin), "ring_ctas" (ring-kernel CTAs per SM, 2 or 1),
+ * list passes claim their tiles from this many counters; 0 = round-robin), "ring_claim_min" (default 12: passes with no more tiles per CTA than this stay
+ * round-robin), "ring_ctas" (ring-kernel CTAs per SM, 2 or 1),
  * "clear_lean", "fused_up", "pipeline",
  * "sort_on_upload" (default 1: every upload
  * re-orders the cloud along a Morton curve on the GPU — no output depends on point order; set 0 BEFORE uploading

@@ -133,6 +133,7 @@ struct RingSchedule {
     uint32_t* tile_counter;  // list passes: consumer groups claim their tiles beyond the CTA's first ring-full from
                              // n_queues counters (tile_counters()), so that faster SMs take more tiles; null = round-robin
     uint32_t n_queues;       // 1 ... kMaxTileQueues
+    uint32_t claim_min_tiles_per_cta;  // list passes with no more tiles per CTA than this stay round-robin (default 12)
     uint32_t ctas_per_sm;    // host side: CTAs launched per SM (2 fill an SM's shared memory; 1 leaves room for another frame's ring kernel)
 };
 // Claimed tiles (list passes): a CTA's first `stages` tiles are tiles blockIdx.x + k * grid of the launch; the tiles from

@@ -148,7 +148,10 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
     const uint32_t group = threadIdx.x / kRingConsumers, tid = threadIdx.x % kRingConsumers;
     const uint32_t lane = threadIdx.x & 31u, rot = (lane >> 1) & 3u;
     const bool leader = tid == 0;
-    const bool claim_tiles = LIST && sc.tile_counter != nullptr;
+    // Claiming pays once a CTA has many tiles to even out; with a dozen or fewer (C2: 20 M points, 1280x720) the claims'
+    // atomics cost 0.5 us per pass and buy nothing (profiles/r01j_exp_ring_dynamic.json, section 9).  n_tiles is the same
+    // word for every CTA of the launch, so they all decide alike.
+    const bool claim_tiles = LIST && sc.tile_counter != nullptr && n_tiles > sc.claim_min_tiles_per_cta * G;
     uint64_t policy = 0;
     auto issue = [&](uint32_t stage, uint32_t chunk) {
         sm.chunk[stage] = chunk;
@@ -386,6 +389,7 @@ RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const 
     sc.tile_counter = nullptr;
     sc.n_queues = 1;
     sc.ctas_per_sm = kRingCtasPerSm;
+    sc.claim_min_tiles_per_cta = 12;
     sc.n_chunks = uint32_t((n_points + kChunkPoints - 1) / kChunkPoints);
     // golden-ratio stride, made coprime with n_chunks: t -> (t * mul) mod n_chunks is a permutation whose every
     // window of consecutive t is spread evenly over the cloud

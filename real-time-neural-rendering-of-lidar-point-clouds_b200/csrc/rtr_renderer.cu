@@ -323,6 +323,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
     sched.early = r->ring_early ? 1u : 0u;
     sched.ctas_per_sm = uint32_t(r->ring_ctas);
+    sched.claim_min_tiles_per_cta = uint32_t(r->ring_claim_min < 0 ? 0 : r->ring_claim_min);
     sched.n_queues = uint32_t(r->ring_dynamic < 1 ? 1 : (r->ring_dynamic > kMaxTileQueues ? kMaxTileQueues : r->ring_dynamic));
     sched.cull = cull ? fs.cull_state : nullptr;
     sched.vis_list = cull ? fs.vis_list : nullptr;
@@ -952,6 +953,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "ring_dynamic")) return &r->ring_dynamic;
     if (!std::strcmp(key, "clear_lean")) return &r->clear_lean;
     if (!std::strcmp(key, "ring_ctas")) return &r->ring_ctas;
+    if (!std::strcmp(key, "ring_claim_min")) return &r->ring_claim_min;
     if (!std::strcmp(key, "pipeline")) return &r->pipeline;
     return nullptr;
 }

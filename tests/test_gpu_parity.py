@@ -167,9 +167,9 @@ VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u,
                                   (5, 2, 4, 0, 0), (21, 4, 4, 1, 0),
                                   (0, 4, 0, 0, 2), (1, 4, 4, 0, 2), (5, 4, 4, 0, 2), (0, 4, 4, 1, 1), (1, 4, 0, 1, 1), (5, 4, 0, 1, 2)]]
 # ring_dynamic: how the list passes of the ring kernels hand out tiles — 0 round-robin, q > 0 claimed from q counters
-VARIANTS += [dict(ring=1, chunk_cull=1, ring_dynamic=q) for q in (0, 1, 3, 64)] + [dict(ring=1, chunk_cull=1, clear_lean=0)]
+VARIANTS += [dict(ring=1, chunk_cull=1, ring_dynamic=q, ring_claim_min=0) for q in (0, 1, 3, 8, 64)] + [dict(ring=1, chunk_cull=1, clear_lean=0)]
 # ring_ctas = 1: one ring-kernel CTA per SM (half the grid)
-VARIANTS += [dict(ring=1, chunk_cull=1, ring_ctas=1), dict(ring=2, chunk_cull=0, ring_ctas=1), dict(ring=1, chunk_cull=1, ring_ctas=1, ring_dynamic=0)]
+VARIANTS += [dict(ring=1, chunk_cull=1, ring_ctas=1, ring_claim_min=0), dict(ring=2, chunk_cull=0, ring_ctas=1), dict(ring=1, chunk_cull=1, ring_ctas=1, ring_dynamic=0)]
 
 
 @pytest.mark.parametrize("opts", VARIANTS)
@@ -370,7 +370,8 @@ def test_cloud_sizes_around_chunk_and_ring_boundaries(gpu, cpu_oracle, n):
     outs = {}
     for name, opts in (("ring_list", dict(ring=1)), ("ring_all", dict(ring=2, chunk_cull=0)), ("ldg_list", dict(ring=0)),
                        ("ldg_all", dict(ring=0, chunk_cull=0)), ("ring_key64", dict(ring=2, key64=1)), ("ldg_key64", dict(ring=0, key64=1)),
-                       ("ring_list_rr", dict(ring=1, ring_dynamic=0)), ("ring_list_q1", dict(ring=1, ring_dynamic=1))):
+                       ("ring_list_rr", dict(ring=1, ring_dynamic=0)), ("ring_list_q1", dict(ring=1, ring_dynamic=1, ring_claim_min=0)),
+                       ("ring_list_q8", dict(ring=1, ring_claim_min=0))):
         pc = gpu.ProjectCloud.from_packed(rec, sort=False)
         for k, v in opts.items():
             pc.set_option(k, v)
@@ -381,7 +382,7 @@ def test_cloud_sizes_around_chunk_and_ring_boundaries(gpu, cpu_oracle, n):
             tap = pc.project_points()
         pc.close()
     gold = cpu_oracle.render(tap[0], tap[1], scenes.bgra_of(rec), W, H, filtered=True)
-    for name in ("ring_list", "ring_all", "ldg_list", "ldg_all", "ring_list_rr", "ring_list_q1"):
+    for name in ("ring_list", "ring_all", "ldg_list", "ldg_all", "ring_list_rr", "ring_list_q1", "ring_list_q8"):
         assert np.array_equal(outs[name][0], gold["image"]) and np.array_equal(outs[name][1], gold["zbuf"]), name
         assert np.array_equal(outs[name][2], gold["tensor"]), name
     for a, b in zip(outs["ring_key64"], outs["ldg_key64"]):
