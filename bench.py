@@ -56,7 +56,10 @@ def parse_args():
     ap.add_argument("--mode", default="frames", choices=["frames", "points"])
     ap.add_argument("--stage", default="filtered", choices=["filtered", "rgbd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-points", type=int, default=20_000_000)
+    ap.add_argument("--cpu-sample-points", type=int, default=100_000_000, help="points of the CPU port's sample (default: the full c3 cloud)")
+    ap.add_argument("--no-unet", action="store_true", help="skip the config-5 leg (projection + prefilter feeding the reference U-Net)")
+    ap.add_argument("--no-points-mode", action="store_true", help="N > 1: skip the point-sharded (config 4) record")
+    ap.add_argument("--points-mode-points", type=int, default=125_000_000, help="points per GPU of the point-sharded record")
     ap.add_argument("--distort", action="store_true", help="apply config 2's k1,k2,p1,p2,k3 = (-0.05, 0.01, 0.0005, -0.0005, 0) (new feature, no reference parity)")
     ap.add_argument("--nccl", action="store_true", help="--mode points: merge with ncclAllReduce instead of the peer-memory kernels")
     ap.add_argument("--opt", action="append", default=[], help="renderer option key=value (repeatable)")
@@ -247,6 +250,260 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------
+def pose_schedule(n_steps, n_poses, world, rank, segments=4):
+    """Which trajectory pose each of this rank's frames renders.  Frame f of the trajectory goes to rank f mod N
+    (SURVEY.md §8 e), so a rank's consecutive frames are N poses apart.  A run shorter than the loop is cut into
+    `segments` arcs of consecutive frames spread evenly over the loop: any step count samples the easy and the hard
+    parts of the trajectory alike, and within an arc the frame-to-frame motion is the real trajectory's (which is what
+    the fused sequences' shared chunk stream depends on).  At 1000 steps the arcs tile the whole loop."""
+    seg_len = -(-n_steps // segments)
+    out = []
+    for i in range(n_steps):
+        seg, off = divmod(i, seg_len)
+        out.append((seg * n_poses // segments + off * world + rank) % n_poses)
+    return out
+
+
+def d2h_ceiling(torch, dist, world, P, iters=60):
+    """What the box can move device->host: every rank copies a frame's worth of output (depth 4 B/px + BGR 3 B/px) from
+    device memory into pinned host memory `iters` times, all ranks at once, nothing else running.  Returns aggregate GB/s."""
+    src_d, src_c = torch.empty(P, dtype=torch.float32, device="cuda"), torch.empty(P * 3, dtype=torch.uint8, device="cuda")
+    n_buf = 4
+    dst_d = torch.empty((n_buf, P), dtype=torch.float32, pin_memory=True)
+    dst_c = torch.empty((n_buf, P * 3), dtype=torch.uint8, pin_memory=True)
+    st = torch.cuda.Stream()
+
+    def loop(n):
+        with torch.cuda.stream(st):
+            for i in range(n):
+                dst_d[i % n_buf].copy_(src_d, non_blocking=True)
+                dst_c[i % n_buf].copy_(src_c, non_blocking=True)
+        st.synchronize()
+    loop(5)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loop(iters)
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return world * iters * P * 7 / dt / 1e9
+
+
+def attach_merge(pkg, torch, dist, pc, kind, rank, world):
+    """kind 'peer': our two-shot all-reduce kernels over NVLink peer memory; 'nccl': ncclAllReduce inside the library."""
+    if kind == "nccl":
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.ProjectCloud.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        pc.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    else:
+        blob = torch.frombuffer(bytearray(pc.peer_export()), dtype=torch.uint8).cuda()
+        blobs = [torch.zeros(512, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(blobs, blob)
+        pc.peer_attach(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs), rank, world)
+
+
+def detach_merge(pc, dist, kind):
+    dist.barrier()
+    if kind == "nccl":
+        pc._check(pc._lib.rtr_comm_destroy(pc._h))
+    else:
+        pc.peer_detach()
+
+
+def points_mode_record(args, pkg, torch, dist, wl, rank, world, local, n_per_gpu, steps):
+    """BASELINE config 4 for the driver's record: points sharded over the ranks (n_per_gpu each, 1 B at 8 x 125 M), every
+    rank renders the same poses, per-GPU z-buffers / colour sums merged (a) by our peer-memory kernels, (b) by
+    ncclAllReduce, and in north_star's 64-bit-key mode — ncclMin on uint64 keys and the same min in the peer kernel.
+    Each variant is first checked on a down-sampled cloud: every rank's merged frame must equal, bit for bit, the frame
+    one GPU renders from the union of the shards."""
+    import hashlib
+    n, W, H, f, cx, cy, hall, boxes, seed, n_poses = wl
+    P = W * H
+    calib = make_calib(pkg, W, H, f, cx, cy)
+    poses = trajectory(pkg, hall, n_poses)
+    variants = [("peer", 0), ("nccl", 0), ("nccl", 1), ("peer", 1)]   # (merge, key64)
+    out = {"points_per_gpu": n_per_gpu, "points_total": n_per_gpu * world, "resolution": f"{W}x{H}", "steps": steps, "variants": {}}
+
+    def digest_of(pc, E):
+        color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        assert pc.computeFilteredRGBD(calib, E, color, depth) == 1
+        return hashlib.sha256(color.tobytes() + depth.tobytes() + pc.read("tensor", np.uint16, P * 5).tobytes()).digest()
+
+    # ---- parity on a down-sampled cloud (2 M points per rank), all variants
+    n_small = 2_000_000
+    check_poses = [poses[0], poses[n_poses // 3], poses[(2 * n_poses) // 3]]
+    small = pkg.ProjectCloud.synthetic(seed=seed + rank, n_total=n_small, hall=hall, n_boxes=boxes, device=local, sort=False)
+    host = torch.empty((n_small, 4), dtype=torch.float32, device="cuda")
+    host.copy_(torch.from_numpy(small.download_cloud()))
+    gathered = [torch.empty_like(host) for _ in range(world)]
+    dist.all_gather(gathered, host)
+    union = pkg.ProjectCloud.from_packed(torch.cat(gathered).cpu().numpy(), device=local, sort=False) if rank == 0 else None
+    del gathered, host
+    small.set_option("index_base", n_small * rank)
+    small.set_camera(calib)
+    for merge, key64 in variants:
+        small.set_option("key64", key64)
+        attach_merge(pkg, torch, dist, small, merge, rank, world)
+        equal = True
+        for E in check_poses:
+            mine = digest_of(small, E)
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
+            if rank == 0:
+                union.set_option("key64", key64)
+                t = torch.frombuffer(bytearray(digest_of(union, E)), dtype=torch.uint8).cuda()
+            dist.broadcast(t, 0)
+            equal &= bytes(t.cpu().numpy().tobytes()) == mine
+        flag = torch.tensor([1 if equal else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        detach_merge(small, dist, merge)
+        out["variants"][f"{merge}{'_key64' if key64 else ''}"] = {"digest_equal": bool(int(flag.item()) == 1),
+                                                                "digest_check": f"{world} x {n_small} points, {len(check_poses)} poses: every rank's merged frame (colour, depth, tensor) "
+                                                                                "== the frame one GPU renders from the union of the shards"}
+    small.close()
+    if union is not None:
+        union.close()
+
+    # ---- timing at full size: every rank holds an independent n_per_gpu-point scan of the whole hall (seed + rank), so the
+    # shards cover the scene uniformly and the ranks' per-frame work is balanced
+    pc = pkg.ProjectCloud.synthetic(seed=seed + rank, n_total=n_per_gpu, hall=hall, n_boxes=boxes, device=local)
+    pc.set_camera(calib)
+    pc.set_option("index_base", 0 if n_per_gpu * world > (1 << 32) else n_per_gpu * rank)
+    idx = pose_schedule(steps + 3, n_poses, 1, 0)
+    my = np.ascontiguousarray(np.stack([poses[i] for i in idx]).reshape(-1, 16))
+    stage = pkg.STAGE_FILTERED
+
+    def loop(timing):
+        pc.set_option("timing", timing)
+        for i in range(3):
+            pc._check(pc._lib.rtr_set_pose_w2c(pc._h, my[i].ctypes.data_as(pkg._dp)))
+            pc.render_device(stage)
+        pc.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if timing:
+            pc.stage_ms_sum(reset=True)
+        stream = torch.cuda.ExternalStream(pc.device_buffers().stream, device=torch.device("cuda", local))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            pc._check(pc._lib.rtr_set_pose_w2c(pc._h, my[3 + i].ctypes.data_as(pkg._dp)))
+            pc.render_device(stage)
+        pc.device_buffers()
+        e1.record(stream)
+        pc.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stages = None
+        if timing:
+            sums, nfr = pc.stage_ms_sum(reset=True)
+            stages = (sums / max(nfr, 1)).tolist()
+        pc.set_option("timing", 0)
+        return float(t.item()) / steps, stages
+
+    # the local passes alone (no merge attached; two passes per frame, integer sums as in the merged frames)
+    pc.set_option("fuse", 0)
+    pc.set_option("pipeline", 0)
+    pc.set_option("blend_variant", 0)
+    _, local_stages = loop(2)
+    for merge, key64 in variants:
+        pc.set_option("key64", key64)
+        if key64:
+            _, base_stages = loop(2)
+        else:
+            base_stages = local_stages
+        attach_merge(pkg, torch, dist, pc, merge, rank, world)
+        ms, _ = loop(0)
+        _, st = loop(2)
+        detach_merge(pc, dist, merge)
+        rec = out["variants"][f"{merge}{'_key64' if key64 else ''}"]
+        merge_ms = (st[1] - base_stages[1]) + (st[2] - base_stages[2]) if not key64 else (st[1] - base_stages[1]) + (st[3] - base_stages[3])
+        rec.update({"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "gpoints_per_s": n_per_gpu * world / (ms * 1e-3) / 1e9,
+                    "merge_ms": merge_ms,
+                    "merge": ("two-shot all-reduce kernels over NVLink peer memory (csrc/rtr_peer.cu)" if merge == "peer" else "ncclAllReduce") +
+                             (": min of uint64 (depth bits << 32 | point index) keys + sum of the image bytes" if key64 else ": min of u32 depth bits + sum of u32 colour sums"),
+                    "stage_ms_with_merge": dict(zip(["clear_classify", "zmin+merge", "blend+merge", "resolve", "up_pass", "frame"], st)),
+                    "stage_ms_local_only": dict(zip(["clear_classify", "zmin", "blend", "resolve", "up_pass", "frame"], base_stages))})
+    pc.close()
+    return out
+
+
+def unet_leg(pkg, torch, wl, local, frames=30):
+    """BASELINE config 5 at 1080p for the driver's record: projection + prefilter feeding the REFERENCE's U-Net
+    (TorchScript export of the reference's own model.py with seeded random weights, oracle/_ref/unet_<W>x<H>.pt — the real
+    weights are a Git-LFS pointer), output converted on the GPU, image + depth to pinned host memory, per frame."""
+    n, W, H, f, cx, cy, hall, boxes, seed, n_poses = wl
+    model_file = os.path.join(ROOT, "oracle", "_ref", f"unet_{W}x{H}.pt")
+    if not os.path.exists(model_file):
+        return {"unavailable": f"{os.path.relpath(model_file, ROOT)} is not on this box (tools/export_unet.py writes it where /root/reference exists)"}
+    P = W * H
+    try:
+        model = torch.jit.load(model_file).cuda().eval()
+    except Exception as e:   # measurement support: never fail the bench line for it
+        return {"unavailable": f"torch.jit.load failed: {e}"}
+
+    class DevPtr:
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    calib = make_calib(pkg, W, H, f, cx, cy)
+    poses = trajectory(pkg, hall, n_poses)
+    idx = pose_schedule(frames + 3, n_poses, 1, 0)
+    pc = pkg.ProjectCloud.synthetic(seed=seed, n_total=n, hall=hall, n_boxes=boxes, device=local)
+    color = torch.empty(P * 3, dtype=torch.uint8, pin_memory=True)
+    depth = torch.empty(P, dtype=torch.float32, pin_memory=True)
+    pc.set_camera(calib, poses[0])
+    pc.render_device(pkg.STAGE_FILTERED)
+    stream = torch.cuda.ExternalStream(pc.device_buffers().stream, device=torch.device("cuda", local))
+
+    def one(E):
+        pc.set_camera(calib, E)
+        pc.render_device(pkg.STAGE_FILTERED)
+        bufs = pc.device_buffers()                       # completes the frame; `stream` waits for it
+        tin = torch.as_tensor(DevPtr(bufs.tensor, (1, 5, H, W), "<f2"), device="cuda")   # what torch::from_blob does, project_cloud.cu:471
+        with torch.no_grad(), torch.cuda.stream(stream):
+            y = model(tin)[0].contiguous()
+        pc._check(pc._lib.rtr_postprocess_unet_output(pc._h, y.data_ptr(), W, H, color.data_ptr(), None))
+        pc._check(pc._lib.rtr_read_buffer(pc._h, 0, depth.data_ptr(), P * 4))
+
+    for i in idx[:3]:
+        one(poses[i])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in idx[3:]:
+        one(poses[i])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # split: the projection + prefilter alone, and the network alone
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bufs = pc.device_buffers()
+    tin = torch.as_tensor(DevPtr(bufs.tensor, (1, 5, H, W), "<f2"), device="cuda")
+    with torch.no_grad(), torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(5):
+            model(tin)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    unet_ms = e0.elapsed_time(e1) / 5
+    pc.close()
+    return {"frames_per_s": frames / dt, "ms_per_frame": dt / frames * 1e3, "unet_ms": unet_ms, "frames": frames,
+            "model": os.path.basename(model_file), "resolution": f"{W}x{H}", "points": n,
+            "d2h_bytes_per_frame": P * 7,
+            "note": "per frame: rtr_render_device -> tensor wrapped zero-copy as fp16 {1,5,H,W} -> TorchScript U-Net of the reference on the renderer's "
+                    "stream -> rtr_postprocess_unet_output (fp16 CHW -> uint8 HWC on the GPU) -> image + depth in pinned host memory; the network "
+                    "dominates the frame"}
+
+
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
@@ -295,24 +552,12 @@ def run_b200(args, wl):
         pc.apply_distortion = True
     pc.set_camera(calib)
     if args.mode == "points":
-        pc.set_option("index_base", n * rank)
-        if world > 1 and args.nccl:
-            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                uid.copy_(torch.frombuffer(bytearray(pkg.ProjectCloud.comm_unique_id()), dtype=torch.uint8))
-            dist.broadcast(uid, 0)
-            pc.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
-        elif world > 1:   # our own two-shot all-reduce over NVLink peer memory
-            blob = torch.frombuffer(bytearray(pc.peer_export()), dtype=torch.uint8).cuda()
-            blobs = [torch.zeros(512, dtype=torch.uint8, device="cuda") for _ in range(world)]
-            dist.all_gather(blobs, blob)
-            pc.peer_attach(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs), rank, world)
+        pc.set_option("index_base", 0 if n * world > (1 << 32) else n * rank)
+        if world > 1:
+            attach_merge(pkg, torch, dist, pc, "nccl" if args.nccl else "peer", rank, world)
     poses = trajectory(pkg, hall, n_poses)
-    if args.mode == "frames":   # frame f of the (looping) trajectory goes to rank f mod N (SURVEY.md §8 e)
-        my = [poses[(i * world + rank) % len(poses)] for i in range(K_steps + Wm)]
-    else:
-        my = [poses[i % len(poses)] for i in range(K_steps + Wm)]
-    my = np.ascontiguousarray(np.stack(my).reshape(-1, 16))
+    idx = pose_schedule(K_steps + Wm, n_poses, world if args.mode == "frames" else 1, rank if args.mode == "frames" else 0)
+    my = np.ascontiguousarray(np.stack([poses[i] for i in idx]).reshape(-1, 16))
 
     def set_pose(i):
         pc._check(pc._lib.rtr_set_pose_w2c(pc._h, my[i].ctypes.data_as(pkg._dp)))
@@ -339,7 +584,7 @@ def run_b200(args, wl):
         for i in range(K_steps):
             set_pose(Wm + i)
             pc.render_device(stage)
-        pc.device_buffers()   # consecutive frames alternate between two streams: make `stream` wait for both before the end event
+        pc.device_buffers()   # completes the last frame (a fused sequence's last blend) and makes `stream` wait for every stream of the sequence
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1), pc.launch_count - l0
@@ -359,51 +604,93 @@ def run_b200(args, wl):
     points_per_frame = n if args.mode == "frames" else n * world
     value = points_per_frame * frames_total / (ms * 1e-3) / 1e9
 
-    # ---- leg 2: same loop with per-stage CUDA events (roofline of the dominant kernel)
+    # ---- leg 2: the same loop with per-stage CUDA events (roofline of the dominant kernel)
     peak, peak_src = peaks()
-    names = ["clear_classify", "zmin", "blend", "resolve_pyramid_minmax", "up_pass_tensor", "frame"]
+    culling = bool(pc.get_option("chunk_cull"))
+    fused = bool(pc.get_option("fuse")) and bool(pc.get_option("pipeline")) and culling and pc.get_option("ring") >= 1 and \
+        not pc.get_option("key64") and args.mode == "frames"
 
-    def staged_loop():
-        pc.set_option("timing", 2)
+    def staged_loop(timing):
+        pc.set_option("timing", timing)
         pc.stage_ms_sum(reset=True)
         pc.cull_stats(reset=True)
         ms_t, _ = timed_device_loop()
         sums, nfr = pc.stage_ms_sum(reset=True)
+        passes, streamed = pc.stream_stats(reset=False)
         cf, cvis, nch = pc.cull_stats(reset=True)
         pc.set_option("timing", 0)
-        return (sums / max(nfr, 1)).tolist(), ms_t / K_steps, (cvis / cf if cf else None), nch   # warm-up frames included (same work)
-
-    culling = bool(pc.get_option("chunk_cull"))
-    stage_ms, frame_ms_ev, vis_chunks, n_chunks = staged_loop()
-    streamed = count if not (culling and vis_chunks is not None) else min(count, vis_chunks * 1024.0)
+        return {"stage_ms": (sums / max(nfr, 1)).tolist(), "frame_ms": ms_t / K_steps, "visible_chunks_per_frame": (cvis / cf if cf else None),
+                "chunks_per_pass": (streamed / passes if passes else None), "passes_per_frame": (passes / cf if cf else None), "n_chunks": nch,
+                "timed_passes": nfr}   # warm-up frames included (same work)
 
     def kernel_line(ms, pts):
         a = 16.0 * pts / (ms * 1e-3) / 1e9
         return {"launch_ms": ms, "achieved": a, "frac": a / peak, "frac_of_nominal_8TBps": a / 8000.0}
-    dom = "zmin" if stage_ms[1] >= stage_ms[2] else "blend"
-    dom_ms = max(stage_ms[1], stage_ms[2])
-    kl = kernel_line(dom_ms, streamed)
-    roofline = {"bound": "hbm",
-                "kernel": (f"{dom}_{'ring' if pc.get_option('ring') else 'list'}_kernel (walks the frame's visible 1024-point chunks: 16 B/point "
-                           f"read for the {streamed / count * 100:.1f}% of the cloud inside or near the frustum)") if culling
-                else f"{dom}_{'ring_' if pc.get_option('ring') == 2 else ''}kernel (every point streamed, 16 B/point read)",
-                "achieved": kl["achieved"], "peak": peak, "unit": "GB/s", "frac": kl["frac"],
-                "frac_of_nominal_8TBps": kl["frac_of_nominal_8TBps"], "peak_source": peak_src, "traffic": None,
-                "launch_ms": dom_ms, "algorithmic_bytes_per_launch": 16.0 * streamed,
-                "points_streamed_per_launch": streamed, "points_in_cloud": count,
-                "zmin": kernel_line(stage_ms[1], streamed), "blend": kernel_line(stage_ms[2], streamed),
-                "stage_ms": dict(zip(names, stage_ms)), "frame_ms_with_stage_events": frame_ms_ev}
-    if culling:
+
+    names2 = ["clear_classify", "zmin", "blend", "resolve_pyramid_minmax", "up_pass_tensor", "frame"]
+    if fused:
+        # the default path: ONE point pass per frame (blend of frame k-1 + z-min of frame k over the union of the two frames'
+        # visible chunks), timed on the point stream while the previous frame's image passes run on the image stream
+        st = staged_loop(3)
+        streamed = min(count, st["chunks_per_pass"] * 1024.0)
+        names3 = ["clear_classify_pair (clear stream)", "wait", "fused_blend_zmin (point stream)", "wait_for_image_stream",
+                  "resolve_pyramid_minmax_fixup_gate_up_pass (image stream)", "first_to_last_event"]
+        fused_ms = st["stage_ms"][2]
+        kl = kernel_line(fused_ms, streamed)
+        roofline = {"bound": "hbm",
+                    "kernel": (f"fused_ring_kernel: blend of frame k-1 + z-min of frame k over ONE stream of chunks (the union of the two frames' visible "
+                               f"1024-point chunks, {streamed / count * 100:.1f}% of the cloud; 16 B/point read once, projected for both cameras)"),
+                    "achieved": kl["achieved"], "peak": peak, "unit": "GB/s", "frac": kl["frac"],
+                    "frac_of_nominal_8TBps": kl["frac_of_nominal_8TBps"], "peak_source": peak_src, "traffic": None,
+                    "launch_ms": fused_ms, "algorithmic_bytes_per_launch": 16.0 * streamed,
+                    "points_streamed_per_launch": streamed, "points_in_cloud": count,
+                    "visible_chunks_per_frame": st["visible_chunks_per_frame"], "chunks_streamed_per_pass": st["chunks_per_pass"],
+                    "chunks_in_cloud": st["n_chunks"], "stage_ms": dict(zip(names3, st["stage_ms"])), "timed_passes": st["timed_passes"],
+                    "frame_ms_with_stage_events": st["frame_ms"],
+                    "note": "the pass does the arithmetic, gathers and reductions of BOTH of the reference's point passes on every record it reads; "
+                            "`two_pass` is the same trajectory with fuse=0 (each frame streams its own list twice)"}
+        # the same frames as two passes per frame (option fuse = 0): what each pass costs on its own
+        pc.set_option("fuse", 0)
+        ms2, _ = timed_device_loop()
+        st2 = staged_loop(2)
+        pc.set_option("fuse", 1)
+        vis2 = min(count, st2["visible_chunks_per_frame"] * 1024.0)
+        roofline["two_pass"] = {"note": "fuse=0: zmin_ring_kernel and blend_ring_kernel each walk the frame's own visible list",
+                                "zmin": kernel_line(st2["stage_ms"][1], vis2), "blend": kernel_line(st2["stage_ms"][2], vis2),
+                                "stage_ms": dict(zip(names2, st2["stage_ms"])), "points_streamed_per_pass": vis2,
+                                "ms_per_step": max_over_ranks(ms2) / K_steps,
+                                "value_gpoints_per_s": points_per_frame * frames_total / (max_over_ranks(ms2) * 1e-3) / 1e9}
+        dom = "fused"
+        stage_ms = st2["stage_ms"]
+    else:
+        st = staged_loop(2)
+        stage_ms = st["stage_ms"]
+        streamed = count if not (culling and st["visible_chunks_per_frame"] is not None) else min(count, st["visible_chunks_per_frame"] * 1024.0)
+        dom = "zmin" if stage_ms[1] >= stage_ms[2] else "blend"
+        dom_ms = max(stage_ms[1], stage_ms[2])
+        kl = kernel_line(dom_ms, streamed)
+        roofline = {"bound": "hbm",
+                    "kernel": (f"{dom}_{'ring' if pc.get_option('ring') else 'list'}_kernel (walks the frame's visible 1024-point chunks: 16 B/point "
+                               f"read for the {streamed / count * 100:.1f}% of the cloud inside or near the frustum)") if culling
+                    else f"{dom}_{'ring_' if pc.get_option('ring') == 2 else ''}kernel (every point streamed, 16 B/point read)",
+                    "achieved": kl["achieved"], "peak": peak, "unit": "GB/s", "frac": kl["frac"],
+                    "frac_of_nominal_8TBps": kl["frac_of_nominal_8TBps"], "peak_source": peak_src, "traffic": None,
+                    "launch_ms": dom_ms, "algorithmic_bytes_per_launch": 16.0 * streamed,
+                    "points_streamed_per_launch": streamed, "points_in_cloud": count,
+                    "zmin": kernel_line(stage_ms[1], streamed), "blend": kernel_line(stage_ms[2], streamed),
+                    "stage_ms": dict(zip(names2, stage_ms)), "frame_ms_with_stage_events": st["frame_ms"]}
+        if culling:
+            roofline["visible_chunks_per_frame"], roofline["chunks_in_cloud"] = st["visible_chunks_per_frame"], st["n_chunks"]
+    if culling and args.mode == "frames":
         # the same trajectory with chunk culling off: every record of the cloud is streamed by both passes
         # (the configuration north_star's "16 B/point against the HBM roofline" is quoted on)
-        roofline["visible_chunks_per_frame"], roofline["chunks_in_cloud"] = vis_chunks, n_chunks
         pc.set_option("chunk_cull", 0)
-        sm_all, fm_all, _, _ = staged_loop()
+        sa = staged_loop(2)
         ms_all, _ = timed_device_loop()
         pc.set_option("chunk_cull", 1)
         roofline["stream_all"] = {"note": "chunk_cull=0: zmin_kernel / blend_kernel stream all points, 16 B/point/pass",
-                                  "zmin": kernel_line(sm_all[1], count), "blend": kernel_line(sm_all[2], count),
-                                  "stage_ms": dict(zip(names, sm_all)), "ms_per_step": max_over_ranks(ms_all) / K_steps,
+                                  "zmin": kernel_line(sa["stage_ms"][1], count), "blend": kernel_line(sa["stage_ms"][2], count),
+                                  "stage_ms": dict(zip(names2, sa["stage_ms"])), "ms_per_step": max_over_ranks(ms_all) / K_steps,
                                   "value_gpoints_per_s": points_per_frame * frames_total / (max_over_ranks(ms_all) * 1e-3) / 1e9}
     if world == 1:
         # second bound named by north_star: L2 atomic (RED) throughput into a frame-sized buffer
@@ -415,21 +702,23 @@ def run_b200(args, wl):
                                   "zmin_upper_bound_red_Gops": live / stage_ms[1] / 1e6,
                                   "zmin_frac_of_measured_red_peak": live / stage_ms[1] / 1e6 / red_peak,
                                   "blend_upper_bound_red64_Gops": 2 * live / stage_ms[2] / 1e6,
-                                  "note": "upper bounds: one RED per in-frustum point (z-min, before the early depth test) / two 64-bit REDs per in-frustum point (blend)"}
+                                  "note": "upper bounds from the two-pass stage times: one RED per in-frustum point (z-min, before the early depth test) / two 64-bit REDs per in-frustum point (blend)"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tr):
         try:
             tj = json.load(open(tr))
             roofline["traffic"] = tj.get(f"{dom}_{args.workload}")
+            roofline["traffic_source"] = (f"profiles/traffic.json ({tj.get('source', 'committed ncu --set full capture')}): dram__bytes_read.sum + dram__bytes_write.sum per "
+                                          "launch of that capture's poses — not measured in this run")
             ncu_at = tj.get(f"ncu_atomics_{args.workload}")
             if ncu_at and "l2_atomics" in roofline and culling and pc.get_option("ring"):
                 # REDs really issued (ncu counters of the committed capture) against the measured random-address RED rate
                 # (one 32-byte sector per lane there): what fraction of the pass the reduction path alone accounts for
-                for name, st in (("zmin", stage_ms[1]), ("blend", stage_ms[2])):
+                for name, stt in (("zmin", stage_ms[1]), ("blend", stage_ms[2])):
                     c = ncu_at.get(f"{name}_ring_kernel")
                     if c:
                         roofline["l2_atomics"][f"{name}_ncu"] = dict(c, red_sector_time_ms_at_measured_peak=c["red_sectors"] / (red_peak * 1e6),
-                                                                    frac_of_launch=c["red_sectors"] / (red_peak * 1e6) / st)
+                                                                    frac_of_launch=c["red_sectors"] / (red_peak * 1e6) / stt)
         except Exception:
             pass
 
@@ -463,14 +752,23 @@ def run_b200(args, wl):
                 torch.empty((CHUNK, P), dtype=torch.float32, pin_memory=True))
     ms_traj = max_over_ranks(e2e_loop(False))
     checksum = int(e2e_bufs[0][-1].to(torch.int64).sum().item())   # the D2H result is really read
+    del e2e_bufs
     e2e_val = points_per_frame * frames_total / (ms_traj * 1e-3) / 1e9
     e2e = {"value": e2e_val, "unit": "Gpoints/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": P * 7,
            "api": f"rtr_render_trajectory in calls of {CHUNK} poses (poses from host, BGR + depth images to pinned host memory every frame)",
            "frames_per_s": frames_total / (ms_traj * 1e-3),
+           "d2h_gbs": frames_total * P * 7 / (ms_traj * 1e-3) / 1e9,
            "per_call_sync": {"api": "rtr_render_filtered per pose (== computeFilteredRGBD, blocking)",
                              "value": points_per_frame * frames_total / (ms_call * 1e-3) / 1e9,
                              "frames_per_s": frames_total / (ms_call * 1e-3)},
            "cloud_upload_s": upload_s, "last_frame_checksum": checksum}
+    if args.mode == "frames":
+        # what the box can copy device -> host with nothing else running: all ranks at once, the same bytes per frame
+        ceil = d2h_ceiling(torch, dist, world, P)
+        e2e["d2h_ceiling_gbs"] = ceil
+        e2e["frac_of_d2h_ceiling"] = e2e["d2h_gbs"] / ceil
+        e2e["d2h_ceiling_note"] = (f"{world} rank(s) copying {P * 7} B per frame (depth + BGR) from device to pinned host memory concurrently, no rendering; "
+                                   "the end-to-end frame rate is bounded by this, not by the kernels")
 
     line = {"metric": "Gpoints/s (points x frames / s, whole frame: projection + z-buffer + blend + resolve + prefilter)",
             "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": K_steps, "warmup": Wm,
@@ -480,17 +778,30 @@ def run_b200(args, wl):
                        "sharding": ("frame-sharded, cloud replicated" if args.mode == "frames" else
                                     ("point-sharded, ncclAllReduce min/sum" if args.nccl else "point-sharded, two-shot min/sum all-reduce kernels over NVLink peer memory")),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
+                       "poses": f"{K_steps} timed frames per rank in 4 arcs of consecutive trajectory frames spread over the {n_poses}-pose loop (frame f -> rank f mod N)",
                        "distortion": bool(args.distort),
-                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "ring_dynamic", "clear_lean", "fused_up", "pipeline", "zmin_variant", "blend_variant", "key64")}},
+                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "ring_dynamic", "clear_lean", "fused_up", "pipeline", "fuse", "zmin_variant", "blend_variant", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_port_baseline(args, (n,) + wl[1:], args.cpu_sample_points)
     if args.mode == "points" and world > 1 and not args.nccl:
         line["peer_error"] = pc.get_option("peer_error")
         dist.barrier()
         pc.peer_detach()
     pc.close()
+    del pc
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_unet and args.workload in ("c3", "c5_4k") and not args.points and not args.distort:
+        line["unet_e2e"] = unet_leg(pkg, torch, wl, local)
+    if world > 1 and args.mode == "frames" and not args.no_points_mode:
+        # config 4 (point-sharded) in the same run, so that the driver's scaling record carries it
+        try:
+            line["points_mode"] = points_mode_record(args, pkg, torch, dist, wl, rank, world, local, args.points_mode_points,
+                                                     min(K_steps, 100))
+        except Exception as e:
+            line["points_mode"] = {"error": repr(e)}
+            raise
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_port_baseline(args, (n,) + wl[1:], args.cpu_sample_points)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -40,7 +40,7 @@ enum {
     RTR_ERR_CUDA = -2,     /* CUDA runtime / launch failure; see rtr_last_error() */
     RTR_ERR_STATE = -3,    /* no cloud uploaded / no camera set */
     RTR_ERR_UNSUPPORTED = -4,
-    RTR_ERR_COMM = -5      /* NCCL failure */
+    RTR_ERR_COMM = -5      /* NCCL failure, or a peer of the point-sharded merge did not answer (the frame is invalid) */
 };
 
 /* render stages for rtr_render_device() */
@@ -89,10 +89,15 @@ int rtr_render_filtered(rtr_renderer* r, uint8_t* bgr, float* depth);  /* comput
  * 1x5xHxW fp16 U-Net input (torch::from_blob it, project_cloud.cu:471).  Stream-synchronised. */
 int rtr_render_tensor(rtr_renderer* r, void** device_fp16);
 
-/* ---- device-resident / asynchronous variants (no host copies, no sync).  Back-to-back frames alternate between the
- * renderer's two frame-buffer sets and two streams (option "pipeline", default 1), so that one frame's point passes
- * overlap the previous frame's image passes; rtr_get_device_buffers / rtr_read_buffer always refer to the frame
- * enqueued last, and rtr_get_device_buffers makes `stream` wait for the frames in flight on either stream. */
+/* ---- device-resident / asynchronous variants (no host copies, no sync).  Back-to-back frames form a SEQUENCE
+ * (options "pipeline" and "fuse", default 1): frame k's blend shares one stream of chunks with frame k+1's z-min
+ * (consecutive poses see nearly the same part of the cloud, so every chunk is read from HBM once per frame instead of
+ * twice), the image passes run on a second stream and the clears on a third, over three frame-buffer sets.  A frame's
+ * blend and image passes are therefore enqueued with the NEXT rtr_render_device call — or by rtr_sync,
+ * rtr_get_device_buffers, rtr_read_buffer, rtr_set_option and every blocking render call, all of which complete the
+ * outstanding frame first.  Frames are byte-identical to the blocking calls'.  rtr_get_device_buffers /
+ * rtr_read_buffer refer to the frame enqueued last; rtr_get_device_buffers makes `stream` wait for every frame in
+ * flight.  "fuse" = 0: two point passes per frame, frames alternating between two sets and two streams. */
 int rtr_render_device(rtr_renderer* r, int stage);
 int rtr_sync(rtr_renderer* r);
 /* Render n_frames poses (n_frames x 16 doubles, world->camera) back to back.  bgr/depth, when not
@@ -124,12 +129,14 @@ int rtr_read_buffer(rtr_renderer* r, int what, void* dst, size_t bytes);
 /* Per-point projection tap: pix (int32, -1 = culled) and depth bits for every point (tests). */
 int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host);
 
-/* ---- options / introspection.  Known keys: "zmin_variant" (bit0 early test, bit1 warp
- * aggregation, bit2 L1-cached test), "zmin_unroll", "blend_variant", "blend_unroll",
+/* ---- options / introspection.  An option applies to the frames enqueued after the call.  Known keys: "zmin_variant"
+ * (bit0 early test, bit1 warp aggregation, bit2 L1-cached test, bit6 = 64: shared-memory tile pre-reduction in the
+ * z-min ring pass of two-pass frames; the measurement-only bits 8/16/32, whose frames are
+ * wrong by design, are rejected unless the library was built with -DRTR_EXPERIMENTS), "zmin_unroll", "blend_variant", "blend_unroll",
  * "force_generic", "keep_masks", "timing", "key64", "chunk_cull", "ring", "ring_dynamic" (default 8: the ring kernels'
  * list passes claim their tiles from this many counters; 0 = round-robin), "ring_claim_min" (default 12: passes with no more tiles per CTA than this stay
  * round-robin), "ring_ctas" (ring-kernel CTAs per SM, 2 or 1),
- * "clear_lean", "fused_up", "pipeline",
+ * "clear_lean", "fused_up", "pipeline", "fuse",
  * "sort_on_upload" (default 1: every upload
  * re-orders the cloud along a Morton curve on the GPU — no output depends on point order; set 0 BEFORE uploading
  * to keep the input order, e.g. when the point index of the 64-bit key must be the caller's index). */
@@ -139,12 +146,25 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key);
  * {clear, zmin, blend, resolve+pyramid, up-pass, total}. */
 int rtr_get_stage_ms(rtr_renderer* r, float* ms6);
 /* With option timing=2 every frame records its own six events (pooled); this returns the per-stage
- * SUMS in ms over all frames rendered since the last reset, and how many frames that was. */
+ * SUMS in ms over all frames rendered since the last reset, and how many frames that was.
+ * timing=3 does the same for fused sequences, per point pass that carries both halves:
+ * {clear + chunk classification for two cameras (clear stream), wait, fused pass: blend k-1 + z-min k (point stream),
+ *  wait, resolve + fix-up gate + up-pass of frame k-1 (image stream), first to last event} — the three streams
+ * overlap one another across frames.  (timing 1 / 2 render whole frames one after the other.) */
 int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, int reset);
 /* Chunk-level frustum culling statistics since the last reset: frames rendered with culling, the sum
- * over those frames of the chunks (1024 consecutive points) that were streamed, and the cloud's
+ * over those frames of the frame's visible chunks (1024 consecutive points), and the cloud's
  * chunk count.  Option "chunk_cull" (default 1) switches the culling; results are identical. */
 int rtr_get_cull_stats(rtr_renderer* r, uint64_t* frames, uint64_t* visible_chunks_total, uint64_t* n_chunks, int reset);
+/* What the point passes really read from HBM since the last reset: the number of passes over a visible-chunk list
+ * and the chunks they streamed (16 KB each).  A frame rendered on its own walks its list twice (z-min, blend); a
+ * fused sequence walks the union of two consecutive frames' lists once per frame.  Resets the same counters as
+ * rtr_get_cull_stats. */
+int rtr_get_stream_stats(rtr_renderer* r, uint64_t* passes, uint64_t* chunks_streamed, int reset);
+/* Statistics of the shared-memory tile pre-reduction (option zmin_variant bit 6 = 64, two-pass frames) since the last
+ * reset of the culling statistics: {tiles whose pixels fitted the 32 x 32 shared-memory window, tiles that went
+ * straight to global memory, window pixels flushed (one RED candidate each), records that entered a window}. */
+int rtr_get_smem_tile_stats(rtr_renderer* r, uint64_t* stats4);
 /* Number of kernel launches issued by this renderer since creation. */
 uint64_t rtr_launch_count(const rtr_renderer* r);
 

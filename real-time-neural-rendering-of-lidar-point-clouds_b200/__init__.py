@@ -25,7 +25,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtr_b200.so")
+LIB_PATH = os.environ.get("RTR_B200_LIB") or os.path.join(_HERE, "librtr_b200.so")   # RTR_B200_LIB: an experiment build (tools/experiments)
 
 RTR_OK = 1
 RTR_ERR_ARG, RTR_ERR_CUDA, RTR_ERR_STATE, RTR_ERR_UNSUPPORTED, RTR_ERR_COMM = -1, -2, -3, -4, -5
@@ -63,6 +63,8 @@ API = {
     "rtr_get_stage_ms": (_i, [_vp, _fp]),
     "rtr_get_stage_ms_sum": (_i, [_vp, _dp, C.POINTER(_u64), _i]),
     "rtr_get_cull_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _i]),
+    "rtr_get_stream_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), _i]),
+    "rtr_get_smem_tile_stats": (_i, [_vp, C.POINTER(_u64)]),
     "rtr_launch_count": (_u64, [_vp]),
     "rtr_bench_red_min": (_i, [_vp, _i, _u64, _i, _i, _fp, C.POINTER(_u64)]),
     "rtr_selftest_fast_divide": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),
@@ -327,6 +329,18 @@ class ProjectCloud:
         f, v, n = _u64(0), _u64(0), _u64(0)
         self._check(self._lib.rtr_get_cull_stats(self._h, C.byref(f), C.byref(v), C.byref(n), int(reset)))
         return int(f.value), int(v.value), int(n.value)
+
+    def stream_stats(self, reset: bool = True):
+        """(point passes over a visible-chunk list, chunks they streamed from HBM) since the last reset."""
+        p, c = _u64(0), _u64(0)
+        self._check(self._lib.rtr_get_stream_stats(self._h, C.byref(p), C.byref(c), int(reset)))
+        return int(p.value), int(c.value)
+
+    def smem_tile_stats(self):
+        """(tiles through the shared-memory window, tiles direct, window pixels flushed, records entered) — zmin_variant bit 6."""
+        v = (_u64 * 4)()
+        self._check(self._lib.rtr_get_smem_tile_stats(self._h, v))
+        return tuple(int(x) for x in v)
 
     def bench_red_min(self, mode: int, n_ops: int = 0, key64: bool = False, iters: int = 5):
         """(ms per launch, REDs issued per launch) of the L2 atomic micro-benchmark."""

@@ -11,7 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "librtr_b200.so")
+# RTR_LIB_SUFFIX / RTR_NVCC_FLAGS / RTR_EXPERIMENTS=1: experiment builds next to the shipped library (tools/experiments)
+LIB = os.path.join(HERE, "librtr_b200" + os.environ.get("RTR_LIB_SUFFIX", "") + ".so")
 SOURCES = ["rtr_point_kernels.cu", "rtr_point_ring.cu", "rtr_image_kernels.cu", "rtr_cull.cu", "rtr_peer.cu", "rtr_synth.cu", "rtr_microbench.cu", "rtr_io.cu", "rtr_renderer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -32,7 +33,8 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu into librtr_b200.so; returns the library path."""
     if not force and not _stale():
         return LIB
-    cmd = [NVCC, *FLAGS, "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    extra = os.environ.get("RTR_NVCC_FLAGS", "").split() + (["-DRTR_EXPERIMENTS"] if os.environ.get("RTR_EXPERIMENTS") == "1" else [])
+    cmd = [NVCC, *FLAGS, *extra, "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

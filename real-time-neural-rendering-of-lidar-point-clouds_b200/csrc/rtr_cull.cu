@@ -146,9 +146,11 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) clear_classify_kernel(uint32_
         minmax[2] = 0u;  // float-accumulator overflow flag of this frame
         minmax[3] = 0u;  // grid-barrier counter of exact_fixup_kernel
         // fold the previous culled frame into the running totals, hand its counter over to the next frame
-        if (cull->armed) { cull->total_visible += cull->n_visible[parity ^ 1u]; cull->frames += 1u; }
+        if (cull->armed) cull_fold(cull, parity ^ 1u);
         cull->n_visible[parity ^ 1u] = 0u;
+        cull->n_blend[0] = cull->n_blend[1] = cull->n_zmin[0] = cull->n_zmin[1] = 0u;  // (two-camera lists only)
         cull->parity = parity;
+        cull->kind = kListWhole;
         cull->armed = 1u;
     }
     // the ring kernels' tile-claim counters: every earlier frame of this set has completed (PDL waits are transitive)
@@ -173,6 +175,69 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) clear_classify_kernel(uint32_
     for (uint64_t i = tid; i < cov4; i += stride)
         z4[i] = make_uint4(kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits);
     for (uint64_t i = (cov4 << 2) + tid; i < cov; i += stride) zbuf[i] = kEmptyDepthBits;
+}
+
+// Classification for TWO cameras, no clear (the fused point pass, rtr_point_ring.cu): consecutive trajectory poses
+// see nearly the same chunks, so frame k-1's blend and frame k's z-min walk ONE list — the union of the two frames'
+// visible chunks — and every chunk is streamed from HBM once per frame instead of twice.  An entry carries which of
+// the two passes the chunk can contribute to (kTileBlend: camera cp_blend of the previous frame, kTileZmin: camera
+// cp_zmin of this frame); each flag is the same conservative test as above, so each pass still sees a superset of
+// the chunks the reference's per-point test would keep and the per-point tests inside the pass stay exact.
+// 128 threads x <= 64 registers = 8 K registers: what two resident CTAs of the fused point pass (2 x 512 x 56) leave free
+// on an SM, so the classification for the NEXT pass runs beside the current one (it is enqueued on the clear stream).
+__global__ void __launch_bounds__(128, 8) classify_pair_kernel(const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
+                                                               const __grid_constant__ CullParams cp_blend,
+                                                               const __grid_constant__ CullParams cp_zmin, uint32_t have,
+                                                               uint32_t* __restrict__ vis_list, CullState* __restrict__ cull,
+                                                               uint32_t parity) {
+    pdl_prologue();
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    if (tid == 0) {
+        if (cull->armed) cull_fold(cull, parity ^ 1u);
+        cull->n_visible[parity ^ 1u] = 0u;
+        cull->n_blend[parity ^ 1u] = 0u;
+        cull->n_zmin[parity ^ 1u] = 0u;
+        cull->parity = parity;
+        cull->kind = have;  // kListHasBlend | kListHasZmin
+        cull->armed = 1u;
+    }
+    if (tid < uint64_t(2 * kMaxTileQueues)) tile_counters(cull, 0)[tid * kTileQueueStride] = 0u;
+    const uint32_t n_round = (n_chunks + 31u) & ~31u;
+    for (uint64_t c = tid; c < n_round; c += stride) {
+        uint32_t flags = 0u;
+        if (c < n_chunks) {
+            const ChunkBounds b = bounds[c];
+            if ((have & 1u) && chunk_visible(b, cp_blend)) flags |= kTileBlend;
+            if ((have & 2u) && chunk_visible(b, cp_zmin)) flags |= kTileZmin;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, flags != 0u);
+        if (m) {
+            const unsigned mb = __ballot_sync(0xFFFFFFFFu, (flags & kTileBlend) != 0u), mz = __ballot_sync(0xFFFFFFFFu, (flags & kTileZmin) != 0u);
+            const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if (lane == leader) {
+                base = atomicAdd(&cull->n_visible[parity], uint32_t(__popc(m)));
+                if (mb) atomicAdd(&cull->n_blend[parity], uint32_t(__popc(mb)));
+                if (mz) atomicAdd(&cull->n_zmin[parity], uint32_t(__popc(mz)));
+            }
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (flags) vis_list[base + __popc(m & ((1u << lane) - 1u))] = uint32_t(c) | flags;
+        }
+    }
+}
+
+cudaError_t launch_classify_pair(cudaStream_t s, int sm_count, const ChunkBounds* bounds, uint32_t n_chunks,
+                                 const CullParams& cp_blend, bool have_blend, const CullParams& cp_zmin, bool have_zmin,
+                                 uint32_t* vis_list, CullState* cull, uint32_t parity) {
+    const uint32_t have = (have_blend ? 1u : 0u) | (have_zmin ? 2u : 0u);
+    // one thread per chunk, at most 8 CTAs per SM (the list is short: a few microseconds, latency-bound)
+    unsigned grid = (n_chunks + 127u) / 128u;
+    const unsigned cap = unsigned(sm_count) * 8u;
+    if (grid > cap) grid = cap;
+    if (grid < 1u) grid = 1u;
+    launch_pdl(classify_pair_kernel, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds) {

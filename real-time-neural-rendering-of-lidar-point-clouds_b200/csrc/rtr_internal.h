@@ -12,10 +12,17 @@
 typedef struct ncclComm* ncclComm_t;
 
 namespace rtr {
+constexpr int kFrameSets = 3;  // a fused frame sequence has three frames in flight: z-min of k, blend of k-1, image passes / D2H of k-2
 struct FrameSet {
     FrameBuffers fb{};
+    // accum | zbuf | image live in ONE allocation (one CUDA IPC handle per set for the point-sharded merge)
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0, zbuf_off = 0, image_off = 0;
     bool f32acc = false;  // the last frame rendered into this set accumulated colour sums as floats
     cudaEvent_t rendered = nullptr, copied = nullptr;
+    // fused frame sequences: `points_done` = the point pass that z-min'ed this set's frame has finished; `cleared` =
+    // the clear stream has cleared the set and classified the chunks for the pass that z-mins into it
+    cudaEvent_t points_done = nullptr, cleared = nullptr;
     // chunk-level frustum culling state of the frame rendered into this set (rtr_cull.cu); per set so that two frames
     // can be in flight on two streams
     uint32_t* vis_list = nullptr;
@@ -23,13 +30,30 @@ struct FrameSet {
     uint32_t cull_parity = 0;  // alternates per culled frame (CullState::n_visible double buffer)
 };
 
+// What a frame needs besides its buffers: fixed when the frame is enqueued (the pose may change before its blend runs).
+struct FramePlan {
+    ProjParams pp;
+    CullParams cp;
+    bool cull = false;      // chunk-level frustum culling applies
+    bool use_ring = false;  // the point passes run through the TMA-fed kernels
+};
+// A frame of a fused sequence whose z-min pass has been enqueued and whose blend / image passes have not: they are
+// enqueued together with the NEXT frame's z-min (one stream of chunks for both) or by flush_pending().
+struct PendingFrame {
+    bool active = false;
+    int si = 0, stage = 0;
+    FramePlan plan;
+    uint8_t* bgr = nullptr;  // host destinations of the frame's D2H copies (trajectory call), or null
+    float* depth = nullptr;
+};
 }  // namespace rtr
 
 struct rtr_renderer {
     int device = 0;
     int sm_count = 148;
     // `stream`: everything; `stream2`: every other frame of an asynchronous frame sequence (option "pipeline")
-    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
+    // fused sequences: point passes on `stream`, image passes on `stream2`, clears of the set after next on `clear_stream`
+    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr, clear_stream = nullptr;
     // cloud
     rtr::PointRecord* points = nullptr;
     uint64_t n_points = 0;
@@ -48,8 +72,10 @@ struct rtr_renderer {
     float cam_proj[16] = {0};
     double cull_rstar = 0;  // distortion: normalised radius beyond which nothing reaches the image (make_params)
     // frame buffers (two sets, see header)
-    rtr::FrameSet set[2];
+    rtr::FrameSet set[rtr::kFrameSets];
     int cur = 0;
+    rtr::PendingFrame pending;
+    int fuse = 1;  // asynchronous frame sequences stream each chunk once per frame: blend of frame k-1 + z-min of frame k in one pass (0: two passes per frame)
     int alloc_W = 0, alloc_H = 0;
     rtr::PyramidDims dims{};
     bool masks_allocated = false, key64_allocated = false;
@@ -82,14 +108,18 @@ struct rtr_renderer {
     // point-sharded merge over peer memory (rtr_peer.cu): device pointers of every rank's buffers
     struct Peer {
         bool attached = false;
+        bool exported = false;               // a fresh rtr_peer_export (flags zeroed, epochs reset) has not been attached yet
         int rank = 0, n = 1;
-        uint32_t* flags = nullptr;           // local flag array + [64] local barrier counter + [65] error word
+        uint32_t* flags = nullptr;           // local flag array + [64] local barrier counter
         uint32_t* peer_flags[rtr::kMaxPeers] = {nullptr};
-        uint32_t* peer_zbuf[2][rtr::kMaxPeers] = {{nullptr}};
-        uint32_t* peer_accum[2][rtr::kMaxPeers] = {{nullptr}};
+        // every rank's buffers of frame sets 0 / 1: [what][set][rank], what = 0 z-buffer, 1 colour sums, 2 64-bit keys, 3 image
+        void* peer_buf[4][2][rtr::kMaxPeers] = {{{nullptr}}};
         std::vector<void*> opened;           // cudaIpcOpenMemHandle results to close
         uint32_t epoch = 1, local_base = 0;
         int W = 0, H = 0;
+        uint32_t* err_host = nullptr;        // mapped pinned word a timed-out wait raises (checked after every synchronisation)
+        uint32_t* err_dev = nullptr;
+        int timeout_ms = 10000;              // option "peer_timeout_ms"
     } peer;
     // persistent scratch of rtr_postprocess_unet_output (no per-call cudaMalloc/cudaFree)
     uint8_t* post_scratch = nullptr;
@@ -104,8 +134,10 @@ namespace rtr {
 int renderer_fail(rtr_renderer* r, int code, const std::string& msg);
 // Frees the chunk bounds and both frame sets' visible-list storage.
 void free_cull_storage(rtr_renderer* r);
-// Waits until both compute streams are idle.
+// Waits until the compute streams are idle (does not enqueue anything: see flush_pending).
 cudaError_t sync_compute(rtr_renderer* r);
+// Enqueues the blend and image passes of a fused sequence's last frame, if one is outstanding.
+int flush_pending(rtr_renderer* r);
 // Frees the current cloud and allocates room for n records (r->points, owned).
 int replace_cloud(rtr_renderer* r, uint64_t n);
 // (Re)builds the chunk bounds for the cloud in r->points; every upload path ends with it.

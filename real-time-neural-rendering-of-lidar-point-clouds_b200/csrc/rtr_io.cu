@@ -178,11 +178,45 @@ inline uint32_t pack_bgr(uint8_t b, uint8_t g, uint8_t rr) {
 
 }  // namespace
 
+namespace {
+// Bytes between the stream's read position and its end (0 when the stream cannot seek).
+uint64_t bytes_left(std::ifstream& f) {
+    const std::streampos here = f.tellg();
+    if (here < 0) return 0;
+    f.seekg(0, std::ios::end);
+    const std::streampos end = f.tellg();
+    f.seekg(here);
+    return end > here ? uint64_t(end - here) : 0;
+}
+// No exception may cross the C ABI (std::terminate in the host application): header fields of a corrupt or
+// truncated file are bounded by the file size before anything is allocated, and whatever still throws
+// (bad_alloc, length_error) becomes RTR_ERR_ARG.
+template <typename F>
+int io_guard(rtr_renderer* r, F&& body) {
+    try {
+        return body();
+    } catch (const std::exception& e) {
+        return renderer_fail(r, RTR_ERR_ARG, std::string("I/O failed: ") + e.what());
+    } catch (...) {
+        return renderer_fail(r, RTR_ERR_ARG, "I/O failed");
+    }
+}
+int load_ply_impl(rtr_renderer* r, const char* path, int bin_cells);
+int read_oct_impl(const char* path, float** xyz, uint8_t** bgr, uint64_t* n, int* header4, int** keys, uint64_t** counts);
+int write_oct_impl(const char* path, const float* xyz, const uint8_t* bgr, uint64_t n);
+}  // namespace
+
 extern "C" {
 
 // =============================================================== f1: PLY
 int rtr_load_ply(rtr_renderer* r, const char* path, int bin_cells) {
     if (!r || !path) return RTR_ERR_ARG;
+    return io_guard(r, [&] { return load_ply_impl(r, path, bin_cells); });
+}
+}  // extern "C"
+
+namespace {
+int load_ply_impl(rtr_renderer* r, const char* path, int bin_cells) {
     std::ifstream f(path, std::ios::binary);
     if (!f.is_open()) return renderer_fail(r, RTR_ERR_ARG, std::string("cannot open ") + path);
     std::string line, fmt;
@@ -227,6 +261,11 @@ int rtr_load_ply(rtr_renderer* r, const char* path, int bin_cells) {
         if (!props[idx[w]].is_float) return renderer_fail(r, RTR_ERR_UNSUPPORTED, "PLY x/y/z must be float or double");
     const bool has_rgb = off[3] >= 0 && off[4] >= 0 && off[5] >= 0 && sz[3] == 1 && sz[4] == 1 && sz[5] == 1;
     if (n_vertex > 0xFFFFFFFFull) return renderer_fail(r, RTR_ERR_UNSUPPORTED, "more than 2^32 points");
+    {   // the header's vertex count against what the file can hold (binary: stride bytes, ascii: >= 2 bytes per value)
+        const uint64_t left = bytes_left(f);
+        const uint64_t need = fmt == "ascii" ? n_vertex * 2 * props.size() : n_vertex * uint64_t(stride);
+        if (n_vertex && (stride == 0 || need > left)) return renderer_fail(r, RTR_ERR_ARG, "PLY truncated: the header promises more vertices than the file holds");
+    }
     std::vector<PointRecord> rec(n_vertex);
     if (fmt == "binary_little_endian") {
         std::vector<char> buf(size_t(stride) * std::min<uint64_t>(n_vertex, 1u << 20));
@@ -268,6 +307,9 @@ int rtr_load_ply(rtr_renderer* r, const char* path, int bin_cells) {
     if (rc != RTR_OK || !bin_cells) return rc;
     return rtr_bin_cells(r, nullptr);
 }
+}  // namespace
+
+extern "C" {
 
 int rtr_io_write_ply(const char* path, const float* xyz, const uint8_t* bgr, uint64_t n) {
     if (!path || (n && (!xyz || !bgr))) return RTR_ERR_ARG;
@@ -364,11 +406,25 @@ int rtr_io_read_oct(const char* path, float** xyz, uint8_t** bgr, uint64_t* n, i
     *xyz = nullptr; *bgr = nullptr; *n = 0;
     if (keys) *keys = nullptr;
     if (counts) *counts = nullptr;
+    const int rc = io_guard(nullptr, [&] { return read_oct_impl(path, xyz, bgr, n, header4, keys, counts); });
+    if (rc != RTR_OK) {  // nothing half-filled leaves the call
+        std::free(*xyz); std::free(*bgr);
+        *xyz = nullptr; *bgr = nullptr; *n = 0;
+        if (keys) { std::free(*keys); *keys = nullptr; }
+        if (counts) { std::free(*counts); *counts = nullptr; }
+    }
+    return rc;
+}
+}  // extern "C"
+namespace {
+int read_oct_impl(const char* path, float** xyz, uint8_t** bgr, uint64_t* n, int* header4, int** keys, uint64_t** counts) {
     std::ifstream f(path, std::ios::binary);
     if (!f.is_open()) return renderer_fail(nullptr, RTR_ERR_ARG, std::string("cannot open ") + path);
     int32_t hdr[4];
     f.read(reinterpret_cast<char*>(hdr), 16);
     if (f.gcount() != 16 || hdr[3] < 0) return renderer_fail(nullptr, RTR_ERR_ARG, "bad .oct header");
+    // every block costs at least its 36-byte frame (key, count, bounds): bound the block count by the file size
+    if (uint64_t(hdr[3]) * 36u > bytes_left(f)) return renderer_fail(nullptr, RTR_ERR_ARG, "bad .oct header: more blocks than the file can hold");
     if (header4) std::memcpy(header4, hdr, 16);
     std::vector<float> P;
     std::vector<uint8_t> Cc;
@@ -379,7 +435,7 @@ int rtr_io_read_oct(const char* path, float** xyz, uint8_t** bgr, uint64_t* n, i
         uint64_t cnt;  // size_t in the reference (Octreegrid.h:71): 8 bytes on every platform it builds for
         f.read(reinterpret_cast<char*>(&key), 4);
         f.read(reinterpret_cast<char*>(&cnt), 8);
-        if (!f.good() || cnt > (1ull << 40)) return renderer_fail(nullptr, RTR_ERR_ARG, "bad .oct block header");
+        if (!f.good() || cnt > (1ull << 40) || cnt * 15u + 24u > bytes_left(f)) return renderer_fail(nullptr, RTR_ERR_ARG, "bad .oct block header or truncated file");
         const size_t p0 = P.size(), c0 = Cc.size();
         P.resize(p0 + cnt * 3);
         Cc.resize(c0 + cnt * 3);
@@ -397,14 +453,29 @@ int rtr_io_read_oct(const char* path, float** xyz, uint8_t** bgr, uint64_t* n, i
     if (!*xyz || !*bgr) return renderer_fail(nullptr, RTR_ERR_ARG, "out of memory");
     std::memcpy(*xyz, P.data(), P.size() * 4);
     std::memcpy(*bgr, Cc.data(), Cc.size());
-    if (keys) { *keys = static_cast<int*>(std::malloc(K.size() * 4 + 16)); std::memcpy(*keys, K.data(), K.size() * 4); }
-    if (counts) { *counts = static_cast<uint64_t*>(std::malloc(Cn.size() * 8 + 16)); std::memcpy(*counts, Cn.data(), Cn.size() * 8); }
+    if (keys) {
+        *keys = static_cast<int*>(std::malloc(K.size() * 4 + 16));
+        if (!*keys) return renderer_fail(nullptr, RTR_ERR_ARG, "out of memory");
+        std::memcpy(*keys, K.data(), K.size() * 4);
+    }
+    if (counts) {
+        *counts = static_cast<uint64_t*>(std::malloc(Cn.size() * 8 + 16));
+        if (!*counts) return renderer_fail(nullptr, RTR_ERR_ARG, "out of memory");
+        std::memcpy(*counts, Cn.data(), Cn.size() * 8);
+    }
     return RTR_OK;
 }
+}  // namespace
+extern "C" {
 void rtr_io_free(void* p) { std::free(p); }
 
 int rtr_io_write_oct(const char* path, const float* xyz, const uint8_t* bgr, uint64_t n) {
     if (!path || (n && (!xyz || !bgr))) return RTR_ERR_ARG;
+    return io_guard(nullptr, [&] { return write_oct_impl(path, xyz, bgr, n); });
+}
+}  // extern "C"
+namespace {
+int write_oct_impl(const char* path, const float* xyz, const uint8_t* bgr, uint64_t n) {
     // computeGrid (cloudreader.cpp:10-60)
     float lo[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
     float hi[3] = {std::numeric_limits<float>::min(), std::numeric_limits<float>::min(), std::numeric_limits<float>::min()};
@@ -453,6 +524,8 @@ int rtr_io_write_oct(const char* path, const float* xyz, const uint8_t* bgr, uin
     }
     return f.good() ? RTR_OK : renderer_fail(nullptr, RTR_ERR_ARG, "write failed");
 }
+}  // namespace
+extern "C" {
 
 int rtr_load_oct(rtr_renderer* r, const char* path) {
     if (!r || !path) return RTR_ERR_ARG;

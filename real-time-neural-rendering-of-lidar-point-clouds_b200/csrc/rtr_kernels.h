@@ -25,17 +25,47 @@ struct CullState {
     uint32_t parity;               // which counter the frame in flight uses (written by clear_classify_kernel)
     uint32_t armed;                // a classified frame has not been folded into the totals yet
     uint32_t frames;               // frames folded into total_visible
-    uint32_t pad;
-    unsigned long long total_visible;
+    uint32_t kind;                 // what the list in flight is: kListPair | have flags (classify_pair_kernel) or kListWhole
+    unsigned long long total_visible;  // sum over the folded frames of the frame's visible chunks
+    // two-camera lists (classify_pair_kernel): how many entries of the list in flight carry each flag
+    uint32_t n_blend[2], n_zmin[2];
+    unsigned long long total_streamed;  // chunk reads from HBM: entries of every pair list, 2 x entries of every whole-frame list
+    uint32_t passes, pad;               // point passes folded into total_streamed
 };
+constexpr uint32_t kListHasBlend = 1u, kListHasZmin = 2u, kListWhole = 4u;
+// Fold the list in flight (counter `old`) into the totals — device (next classification) and host (statistics read-out).
+__host__ __device__ inline void cull_fold(CullState* c, uint32_t old) {
+    if (c->kind & kListWhole) {  // one camera, walked by the z-min pass and again by the blend pass
+        c->total_visible += c->n_visible[old];
+        c->frames += 1u;
+        c->total_streamed += 2ull * c->n_visible[old];
+        c->passes += 2u;
+    } else {
+        if (c->kind & kListHasZmin) { c->total_visible += c->n_zmin[old]; c->frames += 1u; }
+        c->total_streamed += c->n_visible[old];
+        c->passes += 1u;
+    }
+}
+// A visible-list entry is a chunk id (< 2^30) plus, in lists built for TWO cameras (the fused point pass: frame k-1's
+// blend and frame k's z-min over one stream of chunks), which of the two passes the chunk takes part in.  Lists built
+// for one camera carry no flags; every consumer masks the id.
+constexpr uint32_t kTileBlend = 1u << 30;   // the chunk can hold a point of the PREVIOUS frame's frustum: blend it
+constexpr uint32_t kTileZmin = 1u << 31;    // the chunk can hold a point of THIS frame's frustum: z-min it
+constexpr uint32_t kTileIdMask = kTileBlend - 1u;
 // The allocation that holds a CullState continues with the ring kernels' tile-claim counters of the frame in flight:
 // kMaxTileQueues counters per point pass ([0] z-min, [1] blend), one per 128-byte line (same-address atomics
 // serialise in L2), zeroed by clear_classify_kernel.
 constexpr int kMaxTileQueues = 64;
 constexpr int kTileQueueStride = 32;  // uint32 words between two counters
-constexpr size_t kCullStateAlloc = 256 + size_t(2) * kMaxTileQueues * kTileQueueStride * sizeof(uint32_t);
+constexpr size_t kCullStateAlloc = 256 + size_t(2) * kMaxTileQueues * kTileQueueStride * sizeof(uint32_t) + 64;
 __host__ __device__ inline uint32_t* tile_counters(CullState* c, int pass) {
     return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c) + 256) + size_t(pass) * kMaxTileQueues * kTileQueueStride;
+}
+// ... and ends with the statistics of the shared-memory tile pre-reduction (zmin_variant bit 6): [0] tiles whose pixels
+// fitted the shared-memory window, [1] tiles that went straight to global memory, [2] pixels flushed from windows,
+// [3] records that entered a window.  Never reset by the frame's kernels.
+__host__ __device__ inline unsigned long long* smem_tile_stats(CullState* c) {
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c) + 256 + size_t(2) * kMaxTileQueues * kTileQueueStride * sizeof(uint32_t));
 }
 __host__ __device__ inline uint32_t cull_count(const CullState* c) { return c->n_visible[c->parity & 1u]; }
 // The frame's camera for the chunk test, in double (exact images of the float camProj rows).
@@ -80,30 +110,32 @@ inline void launch_pdl_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-// For kernels with a grid-wide spin barrier (exact_fixup_kernel): the cooperative attribute makes the driver guarantee
-// that all CTAs are co-resident — or run the grid after whatever occupies the SMs — also when another renderer shares
-// the GPU.  Falls back to the plain PDL launch if the driver rejects the combination of attributes.
+// For kernels with a grid-wide spin barrier (exact_fixup_kernel, peer_allreduce_kernel): the cooperative attribute makes
+// the driver guarantee that all CTAs are co-resident — or run the grid after whatever occupies the SMs — also when
+// another renderer shares the GPU.  If the driver rejects the cooperative + PDL pair the launch is retried cooperative
+// only; it is NEVER downgraded to a plain launch (a spin barrier without the co-residency guarantee can deadlock):
+// the error is returned instead.
 template <typename... KArgs, typename... Args>
-inline void launch_pdl_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
-    static bool coop_ok = true;
-    if (coop_ok) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = block;
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        if (cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...) == cudaSuccess) return;
+inline cudaError_t launch_pdl_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess && cfg.numAttrs == 2) {
         (void)cudaGetLastError();
-        coop_ok = false;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
     }
-    launch_pdl_smem(kernel, grid, block, 0, s, static_cast<Args&&>(args)...);
+    return e;
 }
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
@@ -119,7 +151,7 @@ cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const Po
                              uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
                               const ProjParams& pp, const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf,
-                              uint32_t* accum, const uint32_t* gate);
+                              uint32_t* accum, const uint32_t* gate, uint32_t need_flag = 0u);
 
 // ---- the point passes as persistent TMA-fed kernels (rtr_point_ring.cu) — the default (option "ring")
 // Tile t of a launch is chunk vis_list[t] (list = true: the frame's visible chunks, count read on the device from
@@ -160,6 +192,12 @@ cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const Po
                              unsigned long long* zkey);
 cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
                               const ProjParams& pp, const RingSchedule& sc, bool list, const uint32_t* zbuf, uint32_t* accum);
+// One stream of chunks for two frames: tiles flagged kTileBlend are blended for the camera pp_blend against
+// zbuf_blend (complete) into accum_blend, tiles flagged kTileZmin are z-min'ed for the camera pp_zmin into zbuf_zmin.
+// The list (sc.vis_list / sc.cull) comes from launch_classify_pair.  blend_variant bit 2: float colour sums.
+cudaError_t launch_fused_ring(cudaStream_t s, int sm_count, int zmin_variant, int blend_variant, const PointRecord* pts,
+                              uint64_t n, const ProjParams& pp_blend, const ProjParams& pp_zmin, const RingSchedule& sc,
+                              const uint32_t* zbuf_blend, uint32_t* accum_blend, uint32_t* zbuf_zmin);
 
 // ---- chunk-level frustum culling (rtr_cull.cu)
 cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds);
@@ -167,16 +205,26 @@ cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t
 cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum,
                                   uint64_t n_px, uint32_t* minmax, const ChunkBounds* bounds, uint32_t n_chunks,
                                   const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity, bool lean = true);
+// Chunk classification for two cameras at once, no clear: entry = chunk | kTileBlend (visible for cp_blend, if
+// have_blend) | kTileZmin (visible for cp_zmin, if have_zmin); chunks visible for neither are dropped.
+cudaError_t launch_classify_pair(cudaStream_t s, int sm_count, const ChunkBounds* bounds, uint32_t n_chunks,
+                                 const CullParams& cp_blend, bool have_blend, const CullParams& cp_zmin, bool have_zmin,
+                                 uint32_t* vis_list, CullState* cull, uint32_t parity);
 cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                         uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                          const ProjParams& pp, const uint32_t* zbuf, uint32_t* accum, const uint32_t* gate);
 // The in-stream exact re-run after a float-accumulator overflow (clear + integer blend + resolve in one launch
 // that returns at once when minmax[2] == 0).  cull/vis_list null = all tiles.
+// need_flag: 0 for one-camera lists; kTileBlend for two-camera lists (only the entries carrying the flag are redone).
 cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf, uint32_t* accum,
-                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note);
-cudaError_t launch_clear_accum_gated(cudaStream_t s, int sm_count, uint32_t* accum, uint64_t n_px, const uint32_t* gate);
+                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note,
+                               uint32_t need_flag = 0u);
+// The exact re-run as three gated launches without a grid barrier (fused sequences: a cooperative grid on the image
+// stream would have to wait for the point stream's persistent kernel to leave the SMs): clear -> launch_blend_list
+// (integer sums, gate) -> launch_resolve_gated.  Each returns at once unless *gate != 0.
+cudaError_t launch_clear_accum_gated(cudaStream_t s, int sm_count, uint32_t* accum, uint64_t n_px, const uint32_t* gate, uint32_t* host_note);
 cudaError_t launch_project_dump(cudaStream_t s, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                 int32_t* pix_out, uint32_t* zbits_out);
 
@@ -218,9 +266,10 @@ struct PeerMergeParams {
     uint32_t epoch;              // this launch uses epoch, epoch + 1, epoch + 2
     uint32_t* local_bar;         // local grid-barrier counter (grows by 2 * gridDim.x per launch)
     uint32_t local_base;         // its value before this launch
-    uint32_t* err;               // raised when a wait timed out
+    volatile uint32_t* err;      // mapped host word, raised when a wait timed out
+    unsigned long long timeout_ns;
 };
-// op 0: min of u32, op 1: sum of u32.  Grid = 2 CTAs per SM (co-resident, see kernel).
+// op 0: min of u32, op 1: sum of u32, op 2: min of u64.  Grid = 2 CTAs per SM (cooperative launch, see kernel).
 cudaError_t launch_peer_allreduce(cudaStream_t s, int sm_count, int op, const PeerMergeParams& pm);
 
 // ---- synthetic cloud on the device (rtr_synth.cu; bench/test support, same generator as the oracle)

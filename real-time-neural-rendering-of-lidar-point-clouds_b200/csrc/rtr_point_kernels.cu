@@ -51,9 +51,11 @@ __global__ void __launch_bounds__(256) clear_kernel(uint32_t* __restrict__ zbuf,
 }
 
 __global__ void __launch_bounds__(256) clear_accum_gated_kernel(uint4* __restrict__ accum, uint64_t n_px,
-                                                                const uint32_t* __restrict__ gate) {
+                                                                const uint32_t* __restrict__ gate, uint32_t* __restrict__ host_note) {
     pdl_prologue();
     if (*gate == 0u) return;
+    // tell the host (mapped pinned word) that float sums overflowed in this view: the next frames start with integer sums
+    if (blockIdx.x == 0 && threadIdx.x == 0 && host_note) *reinterpret_cast<volatile uint32_t*>(host_note) = 1u;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_px; i += uint64_t(gridDim.x) * blockDim.x)
         accum[i] = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -230,20 +232,23 @@ __global__ void __launch_bounds__(kPointBlock) blend_kernel(const PointRecord* _
         blend_tile<UNROLL, VARIANT, DISTORT>(pts, n, t * (kPointBlock * UNROLL) + threadIdx.x, pp, zbuf, accum2);
 }
 
-template <int VARIANT>
+template <int VARIANT, bool DISTORT = false>
 __global__ void __launch_bounds__(kPointBlock) blend_list_kernel(const PointRecord* __restrict__ pts, uint64_t n,
                                                                  const __grid_constant__ ProjParams pp,
                                                                  const CullState* __restrict__ cull,
                                                                  const uint32_t* __restrict__ vis_list,
                                                                  const uint32_t* __restrict__ zbuf,
                                                                  unsigned long long* __restrict__ accum2,
-                                                                 const uint32_t* __restrict__ gate) {
+                                                                 const uint32_t* __restrict__ gate, uint32_t need_flag) {
     pdl_prologue();
     if (gate && *gate == 0u) return;
     const uint32_t n_vis = cull_count(cull);
-    for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
-        blend_tile<kChunkPoints / kPointBlock, VARIANT, false>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x,
-                                                              pp, zbuf, accum2);
+    for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x) {
+        const uint32_t entry = vis_list[c];  // two-camera lists (need_flag = kTileBlend): only the chunks flagged for this blend
+        if ((entry & need_flag) != need_flag) continue;
+        if (DISTORT) blend_tile<kChunkPoints / kPointBlock, VARIANT, true>(pts, n, uint64_t(entry & kTileIdMask) * kChunkPoints + threadIdx.x, pp, zbuf, accum2);
+        else blend_tile<kChunkPoints / kPointBlock, VARIANT, false>(pts, n, uint64_t(entry & kTileIdMask) * kChunkPoints + threadIdx.x, pp, zbuf, accum2);
+    }
 }
 
 // ---------------------------------------------------------------- exact re-run after a float-accumulator overflow
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRec
                                                                   uint4* __restrict__ accum, uint64_t n_px,
                                                                   uint8_t* __restrict__ image, uint64_t cov,
                                                                   uint32_t* __restrict__ minmax,
-                                                                  uint32_t* __restrict__ host_note) {
+                                                                  uint32_t* __restrict__ host_note, uint32_t need_flag) {
     pdl_prologue();
     if (minmax[2] == 0u) return;
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, stride = uint64_t(gridDim.x) * blockDim.x;
@@ -287,8 +292,11 @@ __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRec
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     if constexpr (LIST) {
         const uint32_t n_vis = cull_count(cull);
-        for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x)
-            blend_tile<kChunkPoints / kPointBlock, 0, DISTORT>(pts, n, uint64_t(vis_list[c]) * kChunkPoints + threadIdx.x, pp, zbuf, a2);
+        for (uint32_t c = blockIdx.x; c < n_vis; c += gridDim.x) {
+            const uint32_t entry = vis_list[c];  // two-camera lists: only the chunks flagged for this frame's blend
+            if ((entry & need_flag) != need_flag) continue;
+            blend_tile<kChunkPoints / kPointBlock, 0, DISTORT>(pts, n, uint64_t(entry & kTileIdMask) * kChunkPoints + threadIdx.x, pp, zbuf, a2);
+        }
     } else {
         const uint64_t n_tiles = (n + kChunkPoints - 1) / kChunkPoints;
         for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
@@ -346,9 +354,11 @@ cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const Po
         case 3: RTR_ZL(3); break;
         case 5: RTR_ZL(5); break;
         case 7: RTR_ZL(7); break;
+#ifdef RTR_EXPERIMENTS  // measurement-only kernels (no RED / ATOMG builtin) exist in experiment builds only
         case 8: RTR_ZL(8); break;
         case 9: RTR_ZL(9); break;
         case 21: RTR_ZL(21); break;
+#endif
         default: return cudaErrorInvalidValue;
     }
 #undef RTR_ZL
@@ -357,34 +367,38 @@ cudaError_t launch_zmin_list(cudaStream_t s, int sm_count, int variant, const Po
 
 cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
                               const ProjParams& pp, const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf,
-                              uint32_t* accum, const uint32_t* gate) {
+                              uint32_t* accum, const uint32_t* gate, uint32_t need_flag) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = unsigned(sm_count) * (gate ? 2u : 8u);  // the gated re-run almost always returns at once
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
+    if (pp.distort) {  // only the gated exact re-run of a fused sequence comes here with a distorted camera: integer sums
+        launch_pdl((blend_list_kernel<0, true>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate, need_flag);
+        return cudaGetLastError();
+    }
     switch (variant & 6) {
-        case 0: launch_pdl((blend_list_kernel<0>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate); break;
-        case 2: launch_pdl((blend_list_kernel<2>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate); break;
-        case 4: launch_pdl((blend_list_kernel<4>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate); break;
-        default: launch_pdl((blend_list_kernel<6>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate); break;
+        case 0: launch_pdl((blend_list_kernel<0>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate, need_flag); break;
+        case 2: launch_pdl((blend_list_kernel<2>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate, need_flag); break;
+        case 4: launch_pdl((blend_list_kernel<4>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate, need_flag); break;
+        default: launch_pdl((blend_list_kernel<6>), dim3(grid), dim3(kPointBlock), s, pts, n, pp, cull, vis_list, zbuf, a2, gate, need_flag); break;
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf, uint32_t* accum,
-                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note) {
+                               uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note,
+                               uint32_t need_flag) {
     if (n == 0) return cudaSuccess;
     const dim3 grid(unsigned(sm_count) * 2u), block(kPointBlock);
     uint4* a4 = reinterpret_cast<uint4*>(accum);
-    if (cull && pp.distort) launch_pdl_cooperative((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
-    else if (cull) launch_pdl_cooperative((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
-    else if (pp.distort) launch_pdl_cooperative((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
-    else launch_pdl_cooperative((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note);
-    return cudaGetLastError();
+    if (cull && pp.distort) return launch_pdl_cooperative((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
+    if (cull) return launch_pdl_cooperative((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
+    if (pp.distort) return launch_pdl_cooperative((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
+    return launch_pdl_cooperative((exact_fixup_kernel<false, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
 }
 
-cudaError_t launch_clear_accum_gated(cudaStream_t s, int sm_count, uint32_t* accum, uint64_t n_px, const uint32_t* gate) {
-    launch_pdl(clear_accum_gated_kernel, dim3(sm_count * 2), dim3(256), s, reinterpret_cast<uint4*>(accum), n_px, gate);
+cudaError_t launch_clear_accum_gated(cudaStream_t s, int sm_count, uint32_t* accum, uint64_t n_px, const uint32_t* gate, uint32_t* host_note) {
+    launch_pdl(clear_accum_gated_kernel, dim3(sm_count * 2), dim3(256), s, reinterpret_cast<uint4*>(accum), n_px, gate, host_note);
     return cudaGetLastError();
 }
 
@@ -406,7 +420,9 @@ template <int UNROLL>
 static cudaError_t launch_zmin_u(cudaStream_t s, int variant, const PointRecord* pts, uint64_t n, uint64_t index_base,
                                  const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey) {
     switch (variant & 15) {
+#ifdef RTR_EXPERIMENTS
         case 8: return launch_zmin_uv<UNROLL, 8>(s, pts, n, index_base, pp, zbuf, zkey);
+#endif
         case 0: return launch_zmin_uv<UNROLL, 0>(s, pts, n, index_base, pp, zbuf, zkey);
         case 1: return launch_zmin_uv<UNROLL, 1>(s, pts, n, index_base, pp, zbuf, zkey);
         case 2: return launch_zmin_uv<UNROLL, 2>(s, pts, n, index_base, pp, zbuf, zkey);

@@ -154,8 +154,8 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
     const bool claim_tiles = LIST && sc.tile_counter != nullptr && n_tiles > sc.claim_min_tiles_per_cta * G;
     uint64_t policy = 0;
     auto issue = [&](uint32_t stage, uint32_t chunk) {
-        sm.chunk[stage] = chunk;
-        const uint64_t first = uint64_t(chunk) * kChunkPoints;
+        sm.chunk[stage] = chunk;  // the list entry as it is: two-camera lists carry their pass flags in the top bits
+        const uint64_t first = uint64_t(chunk & kTileIdMask) * kChunkPoints;
         const uint64_t left = n - first;
         const uint32_t bytes = uint32_t(left < uint64_t(kChunkPoints) ? left : uint64_t(kChunkPoints)) * uint32_t(sizeof(PointRecord));
         mbar_arrive_expect_tx(&sm.full[stage], bytes);
@@ -227,7 +227,7 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
             if (t_refill != kNoTile) issue(stage, refill_chunk);
             else end_mark(stage);
         }
-        consume(p, chunk, tid * kRingPerThread, rot, chunk == last_chunk ? tail_valid : uint32_t(kRingPerThread));
+        consume(p, chunk, tid * kRingPerThread, rot, (chunk & kTileIdMask) == last_chunk ? tail_valid : uint32_t(kRingPerThread));
     }
 }
 
@@ -246,9 +246,138 @@ __device__ __forceinline__ RingSmem& ring_setup() {
     return sm;
 }
 
+// ---------------------------------------------------------------- the two passes' per-thread bodies
+// Each body is split into "project" (arithmetic + in-register merge), "gather" (the z-buffer loads are issued) and
+// "commit" (compare + REDs), so that the fused kernel can have both passes' gathers in flight before either is consumed.
+//
+// z-min.  VARIANT bit 0: early depth test, bit 2: through L1 (ld.ca); RTR_EXPERIMENTS builds only: bit 3: no RED
+// issued (results are wrong), bit 5: no in-register merge of same-pixel neighbours.
+template <int KEY64>
+struct ZminLanes {
+    using Key = std::conditional_t<KEY64 != 0, unsigned long long, uint32_t>;
+    uint32_t pix[kRingPerThread];
+    Key key[kRingPerThread], cur[kRingPerThread];  // KEY64: (depth bits << 32) | global index ; else the depth bits
+    bool live[kRingPerThread];
+    bool any;  // some record of the WARP is in the frustum
+};
+template <int VARIANT, bool DISTORT, int KEY64>
+__device__ __forceinline__ void zmin_project(ZminLanes<KEY64>& z, const PointRecord (&p)[kRingPerThread], const ProjParams& pp,
+                                             uint32_t chunk, uint32_t first, uint32_t rot, uint32_t valid, uint64_t index_base) {
+    const float x[4] = {p[0].x, p[1].x, p[2].x, p[3].x}, y[4] = {p[0].y, p[1].y, p[2].y, p[3].y}, zz[4] = {p[0].z, p[1].z, p[2].z, p[3].z};
+    float depth[4];
+    project4<DISTORT>(pp, x, y, zz, z.pix, depth, z.live);
+#pragma unroll
+    for (int s = 0; s < kRingPerThread; ++s) {
+        const uint32_t slot = uint32_t(s) ^ rot;
+        z.live[s] = z.live[s] & (slot < valid);
+        z.key[s] = __float_as_uint(depth[s]);
+        if constexpr (KEY64)
+            z.key[s] = (z.key[s] << 32) | static_cast<unsigned long long>(uint32_t(index_base + uint64_t(chunk) * kChunkPoints + first + slot));
+    }
+    (void)index_base; (void)chunk; (void)first;
+    // a warp whose 128 records all fell outside the frustum is done (most warps of a stream-all pass, the rim of a culled one)
+    z.any = __any_sync(0xFFFFFFFFu, z.live[0] | z.live[1] | z.live[2] | z.live[3]);
+    if (!z.any) return;
+    // neighbours that landed in the same pixel: keep the smallest key in the first of them
+#pragma unroll
+    for (int j = 1; j < ((VARIANT & 32) ? 0 : kRingPerThread); ++j) {
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+            const bool same = z.live[i] & z.live[j] & (z.pix[i] == z.pix[j]);
+            if (same) z.key[i] = z.key[j] < z.key[i] ? z.key[j] : z.key[i];
+            z.live[j] = z.live[j] & !same;
+        }
+    }
+}
+template <int VARIANT, int KEY64>
+__device__ __forceinline__ void zmin_gather(ZminLanes<KEY64>& z, const uint32_t* __restrict__ zbuf, const unsigned long long* __restrict__ zkey) {
+    if (!z.any) return;
+#pragma unroll
+    for (int s = 0; s < kRingPerThread; ++s) {
+        z.cur[s] = ~typename ZminLanes<KEY64>::Key(0);
+        if constexpr (KEY64) {
+            if ((VARIANT & 1) && z.live[s]) z.cur[s] = (VARIANT & 4) ? __ldca(zkey + z.pix[s]) : __ldcg(zkey + z.pix[s]);
+        } else {
+            if ((VARIANT & 1) && z.live[s]) z.cur[s] = (VARIANT & 4) ? __ldca(zbuf + z.pix[s]) : __ldcg(zbuf + z.pix[s]);
+        }
+    }
+}
+template <int VARIANT, int KEY64>
+__device__ __forceinline__ void zmin_commit(const ZminLanes<KEY64>& z, uint32_t* __restrict__ zbuf, unsigned long long* __restrict__ zkey) {
+    if (!z.any) return;
+#pragma unroll
+    for (int s = 0; s < kRingPerThread; ++s) {
+        if (z.live[s] && z.key[s] < z.cur[s]) {
+            if constexpr (KEY64) {
+                if (!(VARIANT & 8)) red_min_u64(zkey + z.pix[s], z.key[s]);
+            } else if constexpr ((VARIANT & 8) != 0) {  // RTR_EXPERIMENTS only: no RED (results are wrong)
+                if (z.key[s] == 0x12345678u && z.pix[s] == 0xFFFFFFFFu) zbuf[0] = 0u;
+            } else {
+                red_min_u32(zbuf + z.pix[s], z.key[s]);
+            }
+        }
+    }
+}
+
+// blend.  VARIANT bit 2: float accumulators, one RED.ADD.F32x4 per (thread, pixel); else two RED.ADD.64 on the
+// reference's 4 x u32 layout.  RTR_EXPERIMENTS builds only: bit 5: no in-register merge.
+struct BlendLanes {
+    uint32_t pix[kRingPerThread], zmin[kRingPerThread];
+    float depth[kRingPerThread];
+    bool live[kRingPerThread];
+    bool any;
+};
+template <bool DISTORT>
+__device__ __forceinline__ void blend_project(BlendLanes& b, const PointRecord (&p)[kRingPerThread], const ProjParams& pp, uint32_t rot, uint32_t valid) {
+    const float x[4] = {p[0].x, p[1].x, p[2].x, p[3].x}, y[4] = {p[0].y, p[1].y, p[2].y, p[3].y}, z[4] = {p[0].z, p[1].z, p[2].z, p[3].z};
+    project4<DISTORT>(pp, x, y, z, b.pix, b.depth, b.live);
+#pragma unroll
+    for (int s = 0; s < kRingPerThread; ++s) b.live[s] = b.live[s] & ((uint32_t(s) ^ rot) < valid);
+    b.any = __any_sync(0xFFFFFFFFu, b.live[0] | b.live[1] | b.live[2] | b.live[3]);  // false: nothing of this warp is in the frustum
+}
+__device__ __forceinline__ void blend_gather(BlendLanes& b, const uint32_t* __restrict__ zbuf) {
+    if (!b.any) return;
+#pragma unroll
+    for (int s = 0; s < kRingPerThread; ++s) {
+        b.zmin[s] = 0u;
+        if (b.live[s]) b.zmin[s] = __ldg(zbuf + b.pix[s]);
+    }
+}
+template <int VARIANT>
+__device__ __forceinline__ void blend_commit(BlendLanes& l, const PointRecord (&p)[kRingPerThread], unsigned long long* __restrict__ accum2) {
+    if (!l.any) return;
+    uint32_t b[kRingPerThread], g[kRingPerThread], r[kRingPerThread], c[kRingPerThread];
+#pragma unroll
+    for (int s = 0; s < kRingPerThread; ++s) {
+        const float lim = __fadd_rn(__uint_as_float(l.zmin[s]), kDepthWindow);
+        l.live[s] = l.live[s] & !(l.depth[s] > lim);  // render.cu:106 (NaN depth is accepted, as there)
+        b[s] = p[s].bgra & 0xFFu; g[s] = (p[s].bgra >> 8) & 0xFFu; r[s] = (p[s].bgra >> 16) & 0xFFu; c[s] = 1u;
+    }
+    // accepted neighbours of the same pixel: sum their bytes into the first of them (integer, exact)
+#pragma unroll
+    for (int j = 1; j < ((VARIANT & 32) ? 0 : kRingPerThread); ++j) {
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+            const bool same = l.live[i] & l.live[j] & (l.pix[i] == l.pix[j]);
+            if (same) { b[i] += b[j]; g[i] += g[j]; r[i] += r[j]; c[i] += c[j]; }
+            l.live[j] = l.live[j] & !same;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < kRingPerThread; ++s) {
+        if (l.live[s]) {
+            unsigned long long* a = accum2 + uint64_t(l.pix[s]) * 2;
+            if constexpr ((VARIANT & 4) != 0) {
+                red_add_f32x4(a, float(b[s]), float(g[s]), float(r[s]), float(c[s]));
+            } else {
+                red_add_u64(a + 0, static_cast<unsigned long long>(b[s]) | (static_cast<unsigned long long>(g[s]) << 32));
+                red_add_u64(a + 1, static_cast<unsigned long long>(r[s]) | (static_cast<unsigned long long>(c[s]) << 32));
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- z-min
-// VARIANT bit 0: early depth test, bit 2: through L1 (ld.ca), bit 3: measurement only — no RED issued,
-// bit 5: measurement only — no in-register merge of same-pixel neighbours.
 template <int VARIANT, bool DISTORT, int KEY64, bool LIST>
 __global__ void __launch_bounds__(kRingThreads, kRingMinCtas) zmin_ring_kernel(const PointRecord* __restrict__ pts, uint64_t n,
                                                                  uint64_t index_base,
@@ -257,71 +386,124 @@ __global__ void __launch_bounds__(kRingThreads, kRingMinCtas) zmin_ring_kernel(c
                                                                  uint32_t* __restrict__ zbuf,
                                                                  unsigned long long* __restrict__ zkey) {
     RingSmem& sm = ring_setup();  // touches shared memory only: overlaps the previous grid's tail
-    ring_walk<LIST>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t chunk, uint32_t first, uint32_t rot, uint32_t valid) {
-        uint32_t pix[kRingPerThread];
-        using Key = std::conditional_t<KEY64 != 0, unsigned long long, uint32_t>;
-        Key key[kRingPerThread];  // KEY64: (depth bits << 32) | global index ; else the depth bits
-        bool live[kRingPerThread];
-        {
-            const float x[4] = {p[0].x, p[1].x, p[2].x, p[3].x}, y[4] = {p[0].y, p[1].y, p[2].y, p[3].y}, z[4] = {p[0].z, p[1].z, p[2].z, p[3].z};
-            float depth[4];
-            project4<DISTORT>(pp, x, y, z, pix, depth, live);
-#pragma unroll
-            for (int s = 0; s < kRingPerThread; ++s) {
-                const uint32_t slot = uint32_t(s) ^ rot;
-                live[s] = live[s] & (slot < valid);
-                key[s] = __float_as_uint(depth[s]);
-                if constexpr (KEY64)
-                    key[s] = (key[s] << 32) | static_cast<unsigned long long>(uint32_t(index_base + uint64_t(chunk) * kChunkPoints + first + slot));
-            }
-            (void)index_base; (void)chunk; (void)first;
-        }
-        // a warp whose 128 records all fell outside the frustum is done (most warps of a stream-all pass, the rim of a culled one)
-        if (!__any_sync(0xFFFFFFFFu, live[0] | live[1] | live[2] | live[3])) return;
-        // neighbours that landed in the same pixel: keep the smallest key in the first of them
-#pragma unroll
-        for (int j = 1; j < ((VARIANT & 32) ? 0 : kRingPerThread); ++j) {
-#pragma unroll
-            for (int i = 0; i < j; ++i) {
-                const bool same = live[i] & live[j] & (pix[i] == pix[j]);
-                if (same) key[i] = key[j] < key[i] ? key[j] : key[i];
-                live[j] = live[j] & !same;
-            }
-        }
-        if constexpr (KEY64) {
-            unsigned long long cur[kRingPerThread];
-#pragma unroll
-            for (int s = 0; s < kRingPerThread; ++s) {
-                cur[s] = ~0ull;
-                if ((VARIANT & 1) && live[s]) cur[s] = (VARIANT & 4) ? __ldca(zkey + pix[s]) : __ldcg(zkey + pix[s]);
-            }
-#pragma unroll
-            for (int s = 0; s < kRingPerThread; ++s)
-                if (live[s] && key[s] < cur[s] && !(VARIANT & 8)) red_min_u64(zkey + pix[s], key[s]);
-        } else {
-            uint32_t cur[kRingPerThread];
-#pragma unroll
-            for (int s = 0; s < kRingPerThread; ++s) {
-                cur[s] = 0xFFFFFFFFu;
-                if ((VARIANT & 1) && live[s]) cur[s] = (VARIANT & 4) ? __ldca(zbuf + pix[s]) : __ldcg(zbuf + pix[s]);
-            }
-#pragma unroll
-            for (int s = 0; s < kRingPerThread; ++s) {
-                if (live[s] && key[s] < cur[s]) {
-                    if constexpr (VARIANT & 8) {  // measurement only (results are wrong)
-                        if (key[s] == 0x12345678u && pix[s] == 0xFFFFFFFFu) zbuf[0] = 0u;
-                    } else {
-                        red_min_u32(zbuf + pix[s], key[s]);
-                    }
-                }
-            }
-        }
+    ring_walk<LIST>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t entry, uint32_t first, uint32_t rot, uint32_t valid) {
+        ZminLanes<KEY64> z;
+        zmin_project<VARIANT, DISTORT, KEY64>(z, p, pp, entry & kTileIdMask, first, rot, valid, index_base);
+        zmin_gather<VARIANT, KEY64>(z, zbuf, zkey);
+        zmin_commit<VARIANT, KEY64>(z, zbuf, zkey);
     });
 }
 
+// ---------------------------------------------------------------- z-min with shared-memory tile pre-reduction
+// north_star names "shared-memory tile pre-reduction ... to cut L2 contention"; this is that design, as zmin_variant
+// bit 6 (results identical, tests/test_gpu_parity.py VARIANTS).  Per tile (one chunk, one consumer group of 256 threads):
+//   1. project + merge in registers as above; the group's pixel bounding box by redux.min/max per warp and four
+//      shared-memory atomics per warp;
+//   2. bar.sync (group).  If the box fits a 32 x 32 window: atom.shared.min of every surviving record into the
+//      window, else the direct path (early test + RED to global memory) for this tile;
+//   3. bar.sync (group); every thread takes four consecutive window pixels: early depth test against the global
+//      z-buffer and ONE red.global.min per touched pixel — a warp's REDs cover 4 window rows of 128 B.
+// Windows and boxes are double-buffered per group, so a tile costs two group barriers.  What it buys and costs is
+// measured in profiles/r02_exp_smem_tile.json.
+constexpr int kWinDim = 32;
+struct alignas(16) TileWindows {   // (the windows are initialised and flushed with 16-byte accesses)
+    uint32_t win[kRingGroups][2][kWinDim * kWinDim];  // depth bits, 0xFFFFFFFF = untouched
+    uint32_t box[kRingGroups][2][4];                  // u min, v min, u max, v max of the tile's live records
+};
+struct RingSmemTile {
+    RingSmem ring;
+    TileWindows tw;
+};
+__device__ __forceinline__ void group_barrier(uint32_t group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1u + group), "r"(uint32_t(kRingConsumers)) : "memory");
+}
+
+template <int VARIANT, bool LIST>
+__global__ void __launch_bounds__(kRingThreads, kRingMinCtas) zmin_ring_smem_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                                      const __grid_constant__ ProjParams pp,
+                                                                      const __grid_constant__ RingSchedule sc,
+                                                                      uint32_t* __restrict__ zbuf,
+                                                                      unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    RingSmemTile& st = *reinterpret_cast<RingSmemTile*>(ring_raw);
+    RingSmem& sm = ring_setup();  // (the ring is the first member)
+    const uint32_t group = threadIdx.x / kRingConsumers, tid = threadIdx.x % kRingConsumers, lane = threadIdx.x & 31u;
+    const uint32_t W = uint32_t(pp.W);
+    // both windows untouched, both boxes empty
+    for (int b = 0; b < 2; ++b) {
+        reinterpret_cast<uint4*>(st.tw.win[group][b])[tid] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (tid < 4) st.tw.box[group][b][tid] = tid < 2 ? 0xFFFFFFFFu : 0u;
+    }
+    group_barrier(group);
+    uint32_t it = 0;
+    unsigned long long n_fit = 0, n_direct = 0, n_flushed = 0, n_entered = 0;
+    ring_walk<LIST>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t entry, uint32_t first, uint32_t rot, uint32_t valid) {
+        const uint32_t cur_buf = it & 1u, nxt_buf = cur_buf ^ 1u;
+        ++it;
+        uint32_t* win = st.tw.win[group][cur_buf];
+        uint32_t* box = st.tw.box[group][cur_buf];
+        ZminLanes<0> z;
+        zmin_project<VARIANT, false, 0>(z, p, pp, entry & kTileIdMask, first, rot, valid, 0ull);   // (z.any false: nothing of the warp is live)
+        uint32_t u[kRingPerThread], v[kRingPerThread];
+        uint32_t umin = 0xFFFFFFFFu, vmin = 0xFFFFFFFFu, umax = 0u, vmax = 0u;
+#pragma unroll
+        for (int s = 0; s < kRingPerThread; ++s) {
+            z.live[s] = z.live[s] & z.any;
+            v[s] = z.pix[s] / W;
+            u[s] = z.pix[s] - v[s] * W;
+            if (z.live[s]) { umin = min(umin, u[s]); vmin = min(vmin, v[s]); umax = max(umax, u[s]); vmax = max(vmax, v[s]); }
+        }
+        if (z.any) {
+            umin = __reduce_min_sync(0xFFFFFFFFu, umin); vmin = __reduce_min_sync(0xFFFFFFFFu, vmin);
+            umax = __reduce_max_sync(0xFFFFFFFFu, umax); vmax = __reduce_max_sync(0xFFFFFFFFu, vmax);
+            if (lane == 0) { atomicMin(box + 0, umin); atomicMin(box + 1, vmin); atomicMax(box + 2, umax); atomicMax(box + 3, vmax); }
+        }
+        group_barrier(group);
+        const uint32_t u0 = box[0], v0 = box[1], u1 = box[2], v1 = box[3];
+        const bool some = u1 >= u0 && v1 >= v0;                       // the tile has a live record at all
+        const bool fits = some && (u1 - u0) < uint32_t(kWinDim) && (v1 - v0) < uint32_t(kWinDim);
+        if (fits) {
+#pragma unroll
+            for (int s = 0; s < kRingPerThread; ++s)
+                if (z.live[s]) { atomicMin(win + (v[s] - v0) * kWinDim + (u[s] - u0), z.key[s]); ++n_entered; }
+        } else if (some) {
+            zmin_gather<VARIANT, 0>(z, zbuf, nullptr);
+            zmin_commit<VARIANT, 0>(z, zbuf, nullptr);
+        }
+        // the other window / box were last read in the previous tile's flush, which every thread of the group finished
+        // before it arrived at this tile's first barrier: re-arm them for the next tile
+        reinterpret_cast<uint4*>(st.tw.win[group][nxt_buf])[tid] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (tid < 4) st.tw.box[group][nxt_buf][tid] = tid < 2 ? 0xFFFFFFFFu : 0u;
+        group_barrier(group);
+        if (tid == 0) { n_fit += fits ? 1u : 0u; n_direct += (some && !fits) ? 1u : 0u; }
+        if (fits) {
+            // flush: thread t owns window pixels 4t .. 4t+3 (row t / 8, columns 4 (t % 8) ...)
+            const uint4 w4 = reinterpret_cast<const uint4*>(win)[tid];
+            const uint32_t wk[4] = {w4.x, w4.y, w4.z, w4.w};
+            const uint32_t row = v0 + tid / (kWinDim / 4), col = u0 + (tid % (kWinDim / 4)) * 4;
+            uint32_t cur[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                cur[k] = 0xFFFFFFFFu;
+                if ((VARIANT & 1) && wk[k] != 0xFFFFFFFFu) cur[k] = (VARIANT & 4) ? __ldca(zbuf + row * W + col + k) : __ldcg(zbuf + row * W + col + k);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (wk[k] != 0xFFFFFFFFu) {
+                    ++n_flushed;
+                    if (wk[k] < cur[k]) red_min_u32(zbuf + row * W + col + k, wk[k]);
+                }
+        }
+    });
+    if (stats) {   // measurement support: a handful of atomics per CTA
+        n_flushed = __reduce_add_sync(0xFFFFFFFFu, uint32_t(n_flushed));
+        n_entered = __reduce_add_sync(0xFFFFFFFFu, uint32_t(n_entered));
+        if (tid == 0) { atomicAdd(stats + 0, n_fit); atomicAdd(stats + 1, n_direct); }
+        if (lane == 0) { atomicAdd(stats + 2, n_flushed); atomicAdd(stats + 3, n_entered); }
+    }
+}
+
 // ---------------------------------------------------------------- blend
-// VARIANT bit 2: float accumulators, one RED.ADD.F32x4 per (thread, pixel); else two RED.ADD.64 on the
-// reference's 4 x u32 layout.
 template <int VARIANT, bool DISTORT, bool LIST>
 __global__ void __launch_bounds__(kRingThreads, kRingMinCtas) blend_ring_kernel(const PointRecord* __restrict__ pts, uint64_t n,
                                                                   const __grid_constant__ ProjParams pp,
@@ -332,51 +514,56 @@ __global__ void __launch_bounds__(kRingThreads, kRingMinCtas) blend_ring_kernel(
     // early: the visible list this pass walks is older than the grid in front of it (the z-min pass or the merge of
     // the same frame), so its first chunks are requested before the PDL wait
     ring_walk<LIST>(pts, n, sc, sm, LIST && sc.early != 0u, [&](const PointRecord (&p)[kRingPerThread], uint32_t, uint32_t, uint32_t rot, uint32_t valid) {
-        uint32_t pix[kRingPerThread];
-        float depth[kRingPerThread];
-        bool live[kRingPerThread];
-        {
-            const float x[4] = {p[0].x, p[1].x, p[2].x, p[3].x}, y[4] = {p[0].y, p[1].y, p[2].y, p[3].y}, z[4] = {p[0].z, p[1].z, p[2].z, p[3].z};
-            project4<DISTORT>(pp, x, y, z, pix, depth, live);
-#pragma unroll
-            for (int s = 0; s < kRingPerThread; ++s) live[s] = live[s] & ((uint32_t(s) ^ rot) < valid);
+        BlendLanes b;
+        blend_project<DISTORT>(b, p, pp, rot, valid);
+        blend_gather(b, zbuf);
+        blend_commit<VARIANT>(b, p, accum2);
+    });
+}
+
+// ---------------------------------------------------------------- both passes over ONE stream of chunks
+// Frame k-1's blend and frame k's z-min share the chunks they read (consecutive poses of a trajectory see nearly the
+// same part of the cloud), so a frame sequence streams the union of the two visible lists once per frame: the tile's
+// records are loaded from the ring once and projected for both cameras.  Per tile (warp-uniform flags of the list
+// entry, classify_pair_kernel): kTileZmin -> z-min for pp_zmin into zbuf_zmin; kTileBlend -> blend for pp_blend against
+// zbuf_blend (complete: its z-min ran in the previous launch) into accum_blend.  The two frames use different frame
+// sets, so nothing one half writes is read by the other.  Both gathers are issued before either is consumed.
+// Registers: 2 CTAs x 512 threads x 64 registers are the SM's whole register file: nothing else runs beside the pass.
+// Capping the kernel lower (RTR_FUSED_REGS = 56 / 48 would leave room for a CTA of the clear / classification / image
+// kernels) was measured SLOWER: the spills land on the gathers' results and expose their latency (fused pass 88 -> 97 ->
+// 120 us, frames/s 8 900 -> 8 180 -> 6 970; profiles/r02c_exp_fused_ab.json, ncu: 25 % of the stall samples on two STL).
+#ifndef RTR_FUSED_REGS
+#define RTR_FUSED_REGS 64
+#endif
+#if RTR_FUSED_REGS >= 64
+#define RTR_FUSED_BOUNDS __launch_bounds__(kRingThreads, kRingMinCtas)
+#else
+#define RTR_FUSED_BOUNDS __maxnreg__(RTR_FUSED_REGS)
+#endif
+template <int ZV, int BV, bool DISTORT>
+__global__ void RTR_FUSED_BOUNDS fused_ring_kernel(const PointRecord* __restrict__ pts, uint64_t n,
+                                                                  const __grid_constant__ ProjParams pp_blend,
+                                                                  const __grid_constant__ ProjParams pp_zmin,
+                                                                  const __grid_constant__ RingSchedule sc,
+                                                                  const uint32_t* __restrict__ zbuf_blend,
+                                                                  unsigned long long* __restrict__ accum_blend,
+                                                                  uint32_t* __restrict__ zbuf_zmin) {
+    RingSmem& sm = ring_setup();
+    ring_walk<true>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t entry, uint32_t, uint32_t rot, uint32_t valid) {
+        ZminLanes<0> z;
+        BlendLanes b;
+        z.any = false;
+        b.any = false;
+        if (entry & kTileZmin) {
+            zmin_project<ZV, DISTORT, 0>(z, p, pp_zmin, 0u, 0u, rot, valid, 0ull);
+            zmin_gather<ZV, 0>(z, zbuf_zmin, nullptr);
         }
-        if (!__any_sync(0xFFFFFFFFu, live[0] | live[1] | live[2] | live[3])) return;  // nothing of this warp is in the frustum
-        uint32_t zmin[kRingPerThread];
-#pragma unroll
-        for (int s = 0; s < kRingPerThread; ++s) {
-            zmin[s] = 0u;
-            if (live[s]) zmin[s] = __ldg(zbuf + pix[s]);
+        if (entry & kTileBlend) {
+            blend_project<DISTORT>(b, p, pp_blend, rot, valid);
+            blend_gather(b, zbuf_blend);
         }
-        uint32_t b[kRingPerThread], g[kRingPerThread], r[kRingPerThread], c[kRingPerThread];
-#pragma unroll
-        for (int s = 0; s < kRingPerThread; ++s) {
-            const float lim = __fadd_rn(__uint_as_float(zmin[s]), kDepthWindow);
-            live[s] = live[s] & !(depth[s] > lim);  // render.cu:106 (NaN depth is accepted, as there)
-            b[s] = p[s].bgra & 0xFFu; g[s] = (p[s].bgra >> 8) & 0xFFu; r[s] = (p[s].bgra >> 16) & 0xFFu; c[s] = 1u;
-        }
-        // accepted neighbours of the same pixel: sum their bytes into the first of them (integer, exact)
-#pragma unroll
-        for (int j = 1; j < ((VARIANT & 32) ? 0 : kRingPerThread); ++j) {
-#pragma unroll
-            for (int i = 0; i < j; ++i) {
-                const bool same = live[i] & live[j] & (pix[i] == pix[j]);
-                if (same) { b[i] += b[j]; g[i] += g[j]; r[i] += r[j]; c[i] += c[j]; }
-                live[j] = live[j] & !same;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < kRingPerThread; ++s) {
-            if (live[s]) {
-                unsigned long long* a = accum2 + uint64_t(pix[s]) * 2;
-                if constexpr (VARIANT & 4) {
-                    red_add_f32x4(a, float(b[s]), float(g[s]), float(r[s]), float(c[s]));
-                } else {
-                    red_add_u64(a + 0, static_cast<unsigned long long>(b[s]) | (static_cast<unsigned long long>(g[s]) << 32));
-                    red_add_u64(a + 1, static_cast<unsigned long long>(r[s]) | (static_cast<unsigned long long>(c[s]) << 32));
-                }
-            }
-        }
+        zmin_commit<ZV, 0>(z, zbuf_zmin, nullptr);
+        blend_commit<BV>(b, p, accum_blend);
     });
 }
 
@@ -452,6 +639,21 @@ void ring_geometry(uint32_t* stages, uint32_t* groups_per_cta, uint32_t* ctas_pe
     *ctas_per_sm = kRingCtasPerSm;
 }
 
+template <typename K>
+static cudaError_t launch_smem_tile(K kernel, bool* done, unsigned grid, cudaStream_t s, const PointRecord* pts, uint64_t n, const ProjParams& pp,
+                                    const RingSchedule& sc, uint32_t* zbuf, unsigned long long* stats) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!(dev >= 0 && dev < 64 && done[dev])) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(RingSmemTile)));
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    launch_pdl_smem(kernel, dim3(grid), dim3(kRingThreads), sizeof(RingSmemTile), s, pts, n, pp, sc, zbuf, stats);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const PointRecord* pts, uint64_t n,
                              uint64_t index_base, const ProjParams& pp, const RingSchedule& sc_in, bool list, uint32_t* zbuf,
                              unsigned long long* zkey) {
@@ -459,14 +661,22 @@ cudaError_t launch_zmin_ring(cudaStream_t s, int sm_count, int variant, const Po
     const unsigned grid = ring_grid(sm_count, sc_in, list);
     RingSchedule sc = sc_in;
     sc.n_queues = ring_effective_queues(grid, kRingGroups, sc.n_queues);
+    if ((variant & 64) && !zkey && !pp.distort) {  // shared-memory tile pre-reduction (pinhole, 32-bit z-buffer)
+        static bool done_l[64] = {false}, done_a[64] = {false};
+        unsigned long long* stats = sc.cull ? smem_tile_stats(const_cast<CullState*>(sc.cull)) : nullptr;
+        if (list) return launch_smem_tile(zmin_ring_smem_kernel<5, true>, done_l, grid, s, pts, n, pp, sc, zbuf, stats);
+        return launch_smem_tile(zmin_ring_smem_kernel<5, false>, done_a, grid, s, pts, n, pp, sc, zbuf, stats);
+    }
     switch (variant & 45) {  // bit 1 (warp aggregation) has no ring form: the in-register merge replaces it
-        case 37: return launch_zmin_ring_v<37>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
         case 0: return launch_zmin_ring_v<0>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
         case 1: return launch_zmin_ring_v<1>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
         case 5: return launch_zmin_ring_v<5>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
+#ifdef RTR_EXPERIMENTS  // measurement-only kernels (no RED / no merge: wrong frames) exist in experiment builds only
+        case 37: return launch_zmin_ring_v<37>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
         case 8: return launch_zmin_ring_v<8>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
         case 9: return launch_zmin_ring_v<9>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
         case 13: return launch_zmin_ring_v<13>(s, grid, pts, n, index_base, pp, sc, list, zbuf, zkey);
+#endif
         default: return cudaErrorInvalidValue;
     }
 }
@@ -479,10 +689,12 @@ cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const P
     sc.n_queues = ring_effective_queues(grid, kRingGroups, sc.n_queues);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     const bool f32 = (variant & 4) != 0;
+#ifdef RTR_EXPERIMENTS
     if (list && !pp.distort && f32 && (variant & 32)) {  // measurement: no in-register merge
         RTR_RING_LAUNCH((blend_ring_kernel<36, false, true>), pts, n, pp, sc, zbuf, a2);
         return cudaGetLastError();
     }
+#endif
     if (list && pp.distort) {
         if (f32) RTR_RING_LAUNCH((blend_ring_kernel<4, true, true>), pts, n, pp, sc, zbuf, a2);
         else RTR_RING_LAUNCH((blend_ring_kernel<0, true, true>), pts, n, pp, sc, zbuf, a2);
@@ -496,6 +708,35 @@ cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const P
         if (f32) RTR_RING_LAUNCH((blend_ring_kernel<4, false, false>), pts, n, pp, sc, zbuf, a2);
         else RTR_RING_LAUNCH((blend_ring_kernel<0, false, false>), pts, n, pp, sc, zbuf, a2);
     }
+    return cudaGetLastError();
+}
+
+
+cudaError_t launch_fused_ring(cudaStream_t s, int sm_count, int zmin_variant, int blend_variant, const PointRecord* pts,
+                              uint64_t n, const ProjParams& pp_blend, const ProjParams& pp_zmin, const RingSchedule& sc_in,
+                              const uint32_t* zbuf_blend, uint32_t* accum_blend, uint32_t* zbuf_zmin) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = ring_grid(sm_count, sc_in, true);
+    RingSchedule sc = sc_in;
+    sc.n_queues = ring_effective_queues(grid, kRingGroups, sc.n_queues);
+    unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum_blend);
+    const bool f32 = (blend_variant & 4) != 0, distort = pp_zmin.distort != 0;
+    // z-min variants 0 / 1 / 5 (early test off / through L2 / through L1); everything else maps to the default 5
+    const int zv = (zmin_variant & 5) == 0 ? 0 : ((zmin_variant & 5) == 1 ? 1 : 5);
+#define RTR_FUSED(ZV)                                                                                                      \
+    do {                                                                                                                   \
+        if (distort) {                                                                                                     \
+            if (f32) RTR_RING_LAUNCH((fused_ring_kernel<ZV, 4, true>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin);  \
+            else RTR_RING_LAUNCH((fused_ring_kernel<ZV, 0, true>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin);      \
+        } else {                                                                                                           \
+            if (f32) RTR_RING_LAUNCH((fused_ring_kernel<ZV, 4, false>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin); \
+            else RTR_RING_LAUNCH((fused_ring_kernel<ZV, 0, false>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin);     \
+        }                                                                                                                  \
+    } while (0)
+    if (zv == 0) RTR_FUSED(0);
+    else if (zv == 1) RTR_FUSED(1);
+    else RTR_FUSED(5);
+#undef RTR_FUSED
     return cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@
 // There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdio>
@@ -105,19 +106,24 @@ void free_cull_storage(rtr_renderer* r) {
         s.vis_list = nullptr; s.cull_state = nullptr; s.cull_parity = 0;
     }
 }
-// Both compute streams idle (stream2 only ever holds frames of a pipelined sequence).
+// The compute streams idle (stream2 / clear_stream only ever hold work of a pipelined frame sequence).
 cudaError_t sync_compute(rtr_renderer* r) {
     cudaError_t e = cudaStreamSynchronize(r->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream2);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->clear_stream);
     return e;
 }
 }  // namespace rtr
 namespace {
-bool pipelined(const rtr_renderer* r) { return r->pipeline && !r->peer.attached && !r->comm && !r->timing; }
+// timing 3 = per-stage events of the FUSED sequence (point pass on one stream, image passes on the other)
+bool pipelined(const rtr_renderer* r) { return r->pipeline && !r->peer.attached && !r->comm && (!r->timing || r->timing == 3); }
+// the set a non-fused pipelined sequence (and the trajectory call's D2H overlap) alternates to: sets 0 and 1 only
+int other_set(int cur) { return cur == 0 ? 1 : 0; }
 
 void free_frame_sets(rtr_renderer* r) {
     for (auto& s : r->set) {
-        cudaFree(s.fb.zbuf); cudaFree(s.fb.accum); cudaFree(s.fb.image); cudaFree(s.fb.tensor); cudaFree(s.fb.minmax);
+        cudaFree(s.arena); cudaFree(s.fb.tensor); cudaFree(s.fb.minmax);
+        s.arena = nullptr;
         cudaFree(s.fb.zkey);
         for (int i = 1; i <= 4; ++i) cudaFree(s.fb.level[i]);
         for (int i = 0; i < 4; ++i) cudaFree(s.fb.mask[i]);
@@ -138,15 +144,22 @@ template <typename T> cudaError_t zalloc(T** p, size_t bytes, cudaStream_t s) {
 int ensure_buffers(rtr_renderer* r) {
     const int W = r->W, H = r->H;
     if (r->alloc_W != W || r->alloc_H != H) {
+        const int frc = flush_pending(r);  // a frame of the old resolution may still lack its blend / image passes
+        if (frc != RTR_OK) return frc;
         RTR_CUDA(r, sync_compute(r));
         RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
         free_frame_sets(r);
         r->dims = make_pyramid_dims(W, H);
         const size_t P = size_t(W) * H;
+        auto up256 = [](size_t b) { return (b + 255) & ~size_t(255); };
         for (auto& s : r->set) {
-            RTR_CUDA(r, zalloc(&s.fb.zbuf, P * 4, r->stream));
-            RTR_CUDA(r, zalloc(&s.fb.accum, P * 16, r->stream));
-            RTR_CUDA(r, zalloc(&s.fb.image, P * 3 + 16, r->stream));
+            s.zbuf_off = up256(P * 16);
+            s.image_off = s.zbuf_off + up256(P * 4);
+            s.arena_bytes = s.image_off + up256(P * 3 + 16);
+            RTR_CUDA(r, zalloc(&s.arena, s.arena_bytes, r->stream));
+            s.fb.accum = reinterpret_cast<uint32_t*>(s.arena);
+            s.fb.zbuf = reinterpret_cast<uint32_t*>(s.arena + s.zbuf_off);
+            s.fb.image = s.arena + s.image_off;
             RTR_CUDA(r, zalloc(&s.fb.tensor, P * 5 * 2, r->stream));
             RTR_CUDA(r, zalloc(&s.fb.minmax, 16, r->stream));
             s.fb.level[0] = reinterpret_cast<float*>(s.fb.zbuf);
@@ -248,22 +261,26 @@ int drain_event_pool(rtr_renderer* r) {
 }
 
 // Two-shot all-reduce of one frame buffer over the peers' memory (rtr_peer.cu).
-int peer_merge(rtr_renderer* r, int si, bool accum, int op) {
+// what: 0 z-buffer, 1 colour sums, 2 64-bit keys, 3 image bytes;  op: 0 min u32, 1 sum u32, 2 min u64.
+int peer_merge(rtr_renderer* r, int si, int what, int op) {
     rtr_renderer::Peer& pe = r->peer;
+    if (si > 1) return fail(r, RTR_ERR_STATE, "point-sharded frames use frame sets 0 and 1");
     const uint64_t P = uint64_t(r->W) * r->H;
     PeerMergeParams pm;
     std::memset(&pm, 0, sizeof(pm));
     for (int p = 0; p < pe.n; ++p) {
-        pm.buf[p] = reinterpret_cast<uint4*>(accum ? pe.peer_accum[si][p] : pe.peer_zbuf[si][p]);
+        pm.buf[p] = static_cast<uint4*>(pe.peer_buf[what][si][p]);
         pm.flags[p] = pe.peer_flags[p];
+        if (!pm.buf[p]) return fail(r, RTR_ERR_STATE, what == 2 ? "key64 frames need option key64 = 1 on every rank BEFORE rtr_peer_export" : "peer buffer not mapped");
     }
     pm.rank = pe.rank;
     pm.n_ranks = pe.n;
-    pm.n_vec = accum ? P : P / 4;
+    pm.n_vec = what == 0 ? P / 4 : (what == 1 ? P : (what == 2 ? P / 2 : (P * 3 + 15) / 16));
     pm.epoch = pe.epoch;
     pm.local_bar = pe.flags + 64;
     pm.local_base = pe.local_base;
-    pm.err = pe.flags + 65;
+    pm.err = pe.err_dev;
+    pm.timeout_ns = uint64_t(pe.timeout_ms < 1 ? 1 : pe.timeout_ms) * 1000000ull;
     pe.epoch += 3;
     pe.local_base += 2u * unsigned(r->sm_count) * 2u;
     RTR_CUDA(r, launch_peer_allreduce(r->stream, r->sm_count, op, pm));
@@ -271,15 +288,93 @@ int peer_merge(rtr_renderer* r, int si, bool accum, int op) {
     return RTR_OK;
 }
 
-// Enqueue one frame into frame set `si`: on `stream`, or — second set of a pipelined sequence — on `stream2`.
+// After a synchronisation: did a cross-GPU wait of the peer merge give up?  The frame is then invalid.
+int peer_status(rtr_renderer* r) {
+    if (r->peer.err_host && *reinterpret_cast<volatile uint32_t*>(r->peer.err_host)) {
+        *reinterpret_cast<volatile uint32_t*>(r->peer.err_host) = 0u;
+        return fail(r, RTR_ERR_COMM, "point-sharded merge: a peer did not reach the barrier within peer_timeout_ms; the frame is invalid "
+                                     "(is every rank rendering the same frames? detach / export / attach again before the next frame)");
+    }
+    return RTR_OK;
+}
+
+// Everything a frame needs besides its buffers, from the renderer's current camera and options.
+int plan_frame(rtr_renderer* r, FramePlan& pl) {
+    int rc = make_params(r, pl.pp);
+    if (rc != RTR_OK) return rc;
+    const ProjParams& pp = pl.pp;
+    // chunk-level frustum culling: exact (conservative) for the pinhole path.  Under distortion (ring kernels only)
+    // the chunk test runs against the square [-r*, r*]^2 of normalised coordinates that contains every point able to
+    // reach the image (make_params), written as a pinhole camera of 2001 x 2001 "pixels" of r*/1000 each.
+    pl.cull = r->chunk_cull && r->bounds && (!pp.distort || (r->ring && r->cull_rstar > 0));
+    // ring = 1: the TMA-fed kernels for culled frames, the per-thread LDG.128 kernels when every chunk is streamed
+    // (measured 3 % faster there, profiles/r01h_exp_ring_c3.json); ring = 2: always; ring = 0: never
+    pl.use_ring = r->ring == 2 || (r->ring == 1 && pl.cull);
+    CullParams& cp = pl.cp;
+    std::memset(&cp, 0, sizeof(cp));
+    if (pl.cull && !pp.distort) {
+        for (int k = 0; k < 4; ++k) { cp.r0[k] = pp.m[k]; cp.r1[k] = pp.m[4 + k]; cp.r2[k] = pp.m[8 + k]; }
+        cp.W = r->W; cp.H = r->H;
+    } else if (pl.cull) {
+        const double a = 1000.0 / r->cull_rstar;
+        for (int k = 0; k < 4; ++k) {
+            cp.r0[k] = a * double(pp.e[k]) + 1000.0 * double(pp.e[8 + k]);
+            cp.r1[k] = a * double(pp.e[4 + k]) + 1000.0 * double(pp.e[8 + k]);
+            cp.r2[k] = double(pp.e[8 + k]);
+        }
+        cp.W = 2001.0; cp.H = 2001.0;
+    }
+    return RTR_OK;
+}
+
+// The ring kernels' schedule for a pass over `fs`'s visible list (or every chunk when cull is false).
+RingSchedule ring_schedule_for(const rtr_renderer* r, const FrameSet& fs, bool cull) {
+    RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
+    if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
+    sched.early = r->ring_early ? 1u : 0u;
+    sched.ctas_per_sm = uint32_t(r->ring_ctas);
+    sched.claim_min_tiles_per_cta = uint32_t(r->ring_claim_min < 0 ? 0 : r->ring_claim_min);
+    sched.n_queues = uint32_t(r->ring_dynamic < 1 ? 1 : (r->ring_dynamic > kMaxTileQueues ? kMaxTileQueues : r->ring_dynamic));
+    sched.cull = cull ? fs.cull_state : nullptr;
+    sched.vis_list = cull ? fs.vis_list : nullptr;
+    return sched;
+}
+
+// Float colour sums (one 16-byte RED per point) unless the sums must be all-reduced as integers or an earlier frame
+// of this view overflowed them (the exact re-run left a note in a mapped host word).
+int blend_variant_now(rtr_renderer* r, bool merged_across_ranks) {
+    if (r->overflow_note && *reinterpret_cast<volatile uint32_t*>(r->overflow_note)) {
+        *reinterpret_cast<volatile uint32_t*>(r->overflow_note) = 0u;
+        r->int_sum_frames = 64;
+    }
+    const bool int_sums = merged_across_ranks || r->int_sum_frames > 0;
+    if (r->int_sum_frames > 0) r->int_sum_frames -= 1;
+    return int_sums ? (r->blend_variant & ~4) : r->blend_variant;
+}
+
+cudaEvent_t* timing_events(rtr_renderer* r, int* rc) {
+    *rc = RTR_OK;
+    if (r->timing < 2) return r->ev;
+    if (r->ev_pool.empty()) {
+        r->ev_pool.resize(size_t(kEvPoolFrames) * 6);
+        for (auto& e : r->ev_pool)
+            if (cudaEventCreate(&e) != cudaSuccess) { *rc = fail(r, RTR_ERR_CUDA, "cudaEventCreate"); return r->ev; }
+    }
+    if (r->ev_frames == kEvPoolFrames && (*rc = drain_event_pool(r)) != RTR_OK) return r->ev;
+    return &r->ev_pool[size_t(r->ev_frames) * 6];
+}
+
+// Enqueue one whole frame into frame set `si` (two point passes): on `stream`, or — second set of a pipelined
+// non-fused sequence — on `stream2`.
 int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = false) {
     const bool peer = r->peer.attached;
     if (peer && (r->peer.W != r->W || r->peer.H != r->H)) return fail(r, RTR_ERR_STATE, "resolution changed while peers are attached: rtr_peer_detach first");
-    if (peer && r->key64) return fail(r, RTR_ERR_UNSUPPORTED, "key64 mode merges through rtr_comm_init (NCCL), not rtr_peer_attach");
     if (!r->points || r->n_points == 0) return fail(r, RTR_ERR_STATE, "no cloud uploaded");
-    ProjParams pp;
-    int rc = make_params(r, pp);
+    int rc = flush_pending(r);
     if (rc != RTR_OK) return rc;
+    FramePlan pl;
+    if ((rc = plan_frame(r, pl)) != RTR_OK) return rc;
+    const ProjParams& pp = pl.pp;
     rc = ensure_buffers(r);
     if (rc != RTR_OK) return rc;
     FrameSet& fs = r->set[si];
@@ -290,43 +385,12 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     cudaStream_t s = (allow_pipeline && si == 1 && pipelined(r)) ? r->stream2 : r->stream;
     RTR_CUDA(r, cudaStreamWaitEvent(s, fs.rendered, 0));               // this set's previous frame (may have run on the other stream)
     if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, fs.copied, 0));  // previous D2H of this set must be done
-    cudaEvent_t* ev = r->ev;
-    if (r->timing == 2) {
-        if (r->ev_pool.empty()) {
-            r->ev_pool.resize(size_t(kEvPoolFrames) * 6);
-            for (auto& e : r->ev_pool) RTR_CUDA(r, cudaEventCreate(&e));
-        }
-        if (r->ev_frames == kEvPoolFrames && (rc = drain_event_pool(r)) != RTR_OK) return rc;
-        ev = &r->ev_pool[size_t(r->ev_frames) * 6];
-    }
-    // chunk-level frustum culling: exact (conservative) for the pinhole path.  Under distortion (ring kernels only)
-    // the chunk test runs against the square [-r*, r*]^2 of normalised coordinates that contains every point able to
-    // reach the image (make_params), written as a pinhole camera of 2001 x 2001 "pixels" of r*/1000 each.
-    const bool cull = r->chunk_cull && r->bounds && (!pp.distort || (r->ring && r->cull_rstar > 0));
-    // ring = 1: the TMA-fed kernels for culled frames, the per-thread LDG.128 kernels when every chunk is streamed
-    // (measured 3 % faster there, profiles/r01h_exp_ring_c3.json); ring = 2: always; ring = 0: never
-    const bool use_ring = r->ring == 2 || (r->ring == 1 && cull);
-    CullParams cp;
-    if (cull && !pp.distort) {
-        for (int k = 0; k < 4; ++k) { cp.r0[k] = pp.m[k]; cp.r1[k] = pp.m[4 + k]; cp.r2[k] = pp.m[8 + k]; }
-        cp.W = r->W; cp.H = r->H;
-    } else if (cull) {
-        const double a = 1000.0 / r->cull_rstar;
-        for (int k = 0; k < 4; ++k) {
-            cp.r0[k] = a * double(pp.e[k]) + 1000.0 * double(pp.e[8 + k]);
-            cp.r1[k] = a * double(pp.e[4 + k]) + 1000.0 * double(pp.e[8 + k]);
-            cp.r2[k] = double(pp.e[8 + k]);
-        }
-        cp.W = 2001.0; cp.H = 2001.0;
-    }
-    RingSchedule sched = r->ring_sched;  // chunk permutation of the stream-all order, fixed at upload
-    if (!r->ring_perm) sched.perm_mul = 1;  // measurement: stream-all tiles in storage order
-    sched.early = r->ring_early ? 1u : 0u;
-    sched.ctas_per_sm = uint32_t(r->ring_ctas);
-    sched.claim_min_tiles_per_cta = uint32_t(r->ring_claim_min < 0 ? 0 : r->ring_claim_min);
-    sched.n_queues = uint32_t(r->ring_dynamic < 1 ? 1 : (r->ring_dynamic > kMaxTileQueues ? kMaxTileQueues : r->ring_dynamic));
-    sched.cull = cull ? fs.cull_state : nullptr;
-    sched.vis_list = cull ? fs.vis_list : nullptr;
+    RTR_CUDA(r, cudaStreamWaitEvent(s, fs.cleared, 0));  // (a fused sequence clears and classifies on the clear stream)
+    cudaEvent_t* ev = timing_events(r, &rc);
+    if (rc != RTR_OK) return rc;
+    const bool cull = pl.cull, use_ring = pl.use_ring;
+    const CullParams& cp = pl.cp;
+    RingSchedule sched = ring_schedule_for(r, fs, cull);
 
     if (r->timing) cudaEventRecord(ev[0], s);
     if (r->key64) {
@@ -345,15 +409,20 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         else if (cull) RTR_CUDA(r, launch_zmin_list(s, r->sm_count, r->zmin_variant & 5, r->points, r->n_points, r->index_base, pp, fs.cull_state, fs.vis_list, fb.zbuf, fb.zkey));
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant & 5, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, fb.zkey));
         r->launches += 1;
-        if (r->comm) {
+        if (peer) {  // north_star's merge: min over the ranks of the 64-bit (depth bits << 32 | point index) keys
+            if ((rc = peer_merge(r, si, 2, 2)) != RTR_OK) return rc;
+        } else if (r->comm) {
             rc = comm_allreduce(r, fb.zkey, fb.zkey, P, ncclUint64_, ncclMin_);
             if (rc != RTR_OK) return rc;
         }
         if (r->timing) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
         RTR_CUDA(r, launch_resolve_key64(s, fb.zkey, r->points, r->index_base, r->n_points, fb.zbuf, fb.image, P, cov));
         r->launches += 1;
-        if (r->comm) {  // colour of a winning point lives on exactly one rank; others wrote 0 -> sum == the colour
-            // image bytes are summed as u32 words; no carry can occur because at most one rank is non-zero per byte
+        // colour of a winning point lives on exactly one rank; the others wrote 0 -> the sum over the ranks is that colour.
+        // The image bytes are summed as u32 words; no carry can occur because at most one rank is non-zero per byte.
+        if (peer) {
+            if ((rc = peer_merge(r, si, 3, 1)) != RTR_OK) return rc;
+        } else if (r->comm) {
             rc = comm_allreduce(r, fb.image, fb.image, (P * 3 + 3) / 4, ncclUint32_, ncclSum_);
             if (rc != RTR_OK) return rc;
         }
@@ -374,20 +443,13 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         else RTR_CUDA(r, launch_zmin(s, r->zmin_variant, r->zmin_unroll, r->points, r->n_points, r->index_base, pp, fb.zbuf, nullptr));
         r->launches += 1;
         if (peer) {
-            if ((rc = peer_merge(r, si, false, 0)) != RTR_OK) return rc;
+            if ((rc = peer_merge(r, si, 0, 0)) != RTR_OK) return rc;
         } else if (r->comm) {
             rc = comm_allreduce(r, fb.zbuf, fb.zbuf, P, ncclUint32_, ncclMin_);
             if (rc != RTR_OK) return rc;
         }
         if (r->timing) cudaEventRecord(ev[2], s);
-        // float accumulators (one 16-byte RED per point) unless the sums must be all-reduced as integers
-        if (r->overflow_note && *reinterpret_cast<volatile uint32_t*>(r->overflow_note)) {  // an earlier frame's float sums overflowed
-            *reinterpret_cast<volatile uint32_t*>(r->overflow_note) = 0u;
-            r->int_sum_frames = 64;
-        }
-        const bool int_sums = r->comm || peer || r->int_sum_frames > 0;
-        if (r->int_sum_frames > 0) r->int_sum_frames -= 1;
-        const int bv = int_sums ? (r->blend_variant & ~4) : r->blend_variant;
+        const int bv = blend_variant_now(r, r->comm || peer);
         const bool f32acc = (bv & 4) != 0;
         fs.f32acc = f32acc;
         sched.tile_counter = (cull && r->ring_dynamic > 0) ? tile_counters(fs.cull_state, 1) : nullptr;
@@ -396,7 +458,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         else RTR_CUDA(r, launch_blend(s, bv, r->blend_unroll, r->points, r->n_points, pp, fb.zbuf, fb.accum, nullptr));
         r->launches += 1;
         if (peer) {
-            if ((rc = peer_merge(r, si, true, 1)) != RTR_OK) return rc;
+            if ((rc = peer_merge(r, si, 1, 1)) != RTR_OK) return rc;
         } else if (r->comm) {
             rc = comm_allreduce(r, fb.accum, fb.accum, P * 4, ncclUint32_, ncclSum_);
             if (rc != RTR_OK) return rc;
@@ -419,10 +481,149 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         r->launches += uint64_t(up_pass_launches(fb, r->dims, r->force_generic != 0, r->fused_up != 0));
     }
     if (r->timing) cudaEventRecord(ev[5], s);
-    if (r->timing == 2) r->ev_frames += 1;
+    if (r->timing >= 2) r->ev_frames += 1;
     RTR_CUDA(r, cudaEventRecord(fs.rendered, s));
     return RTR_OK;
 }
+
+int enqueue_copy(rtr_renderer* r, int si, uint8_t* bgr, float* depth);
+
+// ---- fused frame sequences: one stream of chunks per frame
+// Consecutive frames of an asynchronous sequence (rtr_render_device back to back, rtr_render_trajectory) see nearly the
+// same chunks.  Frame k is therefore enqueued as
+//     point stream:  classify_pair(k-1, k)  ->  fused pass: blend(k-1) + z-min(k) over the union of the two lists
+//     image stream:  [wait fused pass]  resolve(k-1) -> exact fix-up gate -> up-pass(k-1)  [-> D2H(k-1) on the copy stream]
+//     clear stream:  clear of the set frame k+1 will use (it only waits for that set's previous frame, k-2)
+// so every chunk is read from HBM once per frame instead of twice, the point stream holds nothing but point passes,
+// and frame k stays "pending" (z-min done, blend outstanding) until frame k+1 arrives or flush_pending() runs its
+// blend alone.  Three frame sets: k (z-min), k-1 (blend, image passes), k-2 (D2H).  Frames are byte-identical to the
+// two-pass path (tests/test_gpu_fused.py).
+bool fused_sequence(const rtr_renderer* r, const FramePlan& pl) {
+    return r->fuse && pipelined(r) && pl.cull && pl.use_ring && !r->key64 && r->ring >= 1;
+}
+
+// resolve -> fix-up gate -> up-pass (+ D2H) of the pending frame, on the image stream, once the point pass that
+// blended it (recorded in `pass_set`'s points_done; the pass's list lives in pass_set too) has finished.
+int finish_images(rtr_renderer* r, PendingFrame& pf, int pass_set, bool f32acc, cudaEvent_t* ev) {
+    FrameSet& fs = r->set[pf.si];
+    FrameSet& ps = r->set[pass_set];
+    FrameBuffers fb = fs.fb;
+    if (!r->keep_masks) for (auto& m : fb.mask) m = nullptr;
+    const int W = r->alloc_W, H = r->alloc_H;
+    const uint64_t P = uint64_t(W) * H, cov = clear_coverage(W, H);
+    const bool filtered = pf.stage == RTR_STAGE_FILTERED;
+    cudaStream_t s = r->stream2;
+    RTR_CUDA(r, cudaStreamWaitEvent(s, ps.points_done, 0));
+    if (ev) cudaEventRecord(ev[4], s);
+    RTR_CUDA(r, launch_resolve_pyramid(s, fb, W, H, r->dims, filtered, true, r->force_generic != 0, f32acc));
+    r->launches += ((W % 16) == 0 && !r->force_generic) ? 1 : (filtered ? 6 : 1);
+    if (f32acc) {
+        // exact re-run of the colour sums if a pixel left the float sums' exact range (resolve raised minmax[2]); three gated
+        // launches that return at once otherwise (no cooperative grid here: it would wait for the point stream's kernel)
+        RTR_CUDA(r, launch_clear_accum_gated(s, r->sm_count, fb.accum, P, fb.minmax + 2, r->overflow_note_dev));
+        RTR_CUDA(r, launch_blend_list(s, r->sm_count, 0, r->points, r->n_points, pf.plan.pp, ps.cull_state, ps.vis_list, fb.zbuf, fb.accum,
+                                      fb.minmax + 2, kTileBlend));
+        RTR_CUDA(r, launch_resolve_gated(s, fb, W, H));
+        r->launches += 3;
+        (void)cov;
+    }
+    if (filtered) {
+        RTR_CUDA(r, launch_up_pass(s, fb, r->dims, r->force_generic != 0, r->fused_up != 0));
+        r->launches += uint64_t(up_pass_launches(fb, r->dims, r->force_generic != 0, r->fused_up != 0));
+    }
+    if (ev) cudaEventRecord(ev[5], s);
+    RTR_CUDA(r, cudaEventRecord(fs.rendered, s));
+    if (pf.bgr || pf.depth) {
+        const int rc = enqueue_copy(r, pf.si, pf.bgr, pf.depth);
+        if (rc != RTR_OK) return rc;
+    }
+    pf.active = false;
+    return RTR_OK;
+}
+
+int enqueue_fused(rtr_renderer* r, int stage, const FramePlan& pl, uint8_t* bgr, float* depth) {
+    int rc = ensure_buffers(r);  // (flushes a pending frame of another resolution first)
+    if (rc != RTR_OK) return rc;
+    PendingFrame& pf = r->pending;
+    if (pf.active && pf.plan.pp.distort != pl.pp.distort && (rc = flush_pending(r)) != RTR_OK) return rc;  // one kernel, one projection model
+    const int si = (pf.active ? pf.si + 1 : r->cur + 1) % kFrameSets;
+    FrameSet& fs = r->set[si];
+    const uint64_t P = uint64_t(r->W) * r->H, cov = clear_coverage(r->W, r->H);
+    cudaStream_t s = r->stream, c = r->clear_stream;
+    cudaEvent_t* ev = nullptr;
+    if (r->timing == 3 && pf.active) {  // only passes that carry both halves are timed
+        ev = timing_events(r, &rc);
+        if (rc != RTR_OK) return rc;
+    }
+    // clear stream: once the set is free (its previous frame's image passes and D2H are done — they also were the last
+    // readers of the set's visible list), clear it and classify the chunks for the two cameras.  The host enqueues
+    // frames ahead of the GPU, so this runs while the point stream is still busy with the previous pass.
+    RTR_CUDA(r, cudaStreamWaitEvent(c, fs.rendered, 0));
+    if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(c, fs.copied, 0));
+    if (ev) cudaEventRecord(ev[0], c);
+    RTR_CUDA(r, launch_clear(c, r->sm_count, fs.fb.zbuf, cov, fs.fb.accum, P, fs.fb.minmax, nullptr));
+    fs.cull_parity ^= 1u;
+    RTR_CUDA(r, launch_classify_pair(c, r->sm_count, r->bounds, r->n_chunks, pf.active ? pf.plan.cp : pl.cp, pf.active, pl.cp, true,
+                                     fs.vis_list, fs.cull_state, fs.cull_parity));
+    if (ev) cudaEventRecord(ev[1], c);
+    RTR_CUDA(r, cudaEventRecord(fs.cleared, c));
+    // point stream: nothing but the passes, back to back
+    RTR_CUDA(r, cudaStreamWaitEvent(s, fs.cleared, 0));
+    if (ev) cudaEventRecord(ev[2], s);
+    RingSchedule sched = ring_schedule_for(r, fs, true);
+    sched.tile_counter = r->ring_dynamic > 0 ? tile_counters(fs.cull_state, 0) : nullptr;
+    int bv = r->blend_variant;
+    if (pf.active) {
+        bv = blend_variant_now(r, false);
+        r->set[pf.si].f32acc = (bv & 4) != 0;
+    }
+    const FrameSet& prev = r->set[pf.active ? pf.si : si];
+    RTR_CUDA(r, launch_fused_ring(s, r->sm_count, r->zmin_variant, bv, r->points, r->n_points, pf.active ? pf.plan.pp : pl.pp, pl.pp, sched,
+                                  prev.fb.zbuf, prev.fb.accum, fs.fb.zbuf));
+    r->launches += 3;
+    if (ev) cudaEventRecord(ev[3], s);
+    RTR_CUDA(r, cudaEventRecord(fs.points_done, s));
+    if (pf.active) {
+        if ((rc = finish_images(r, pf, si, (bv & 4) != 0, ev)) != RTR_OK) return rc;
+        if (ev) r->ev_frames += 1;
+    }
+    pf.active = true;
+    pf.si = si;
+    pf.stage = stage;
+    pf.plan = pl;
+    pf.bgr = bgr;
+    pf.depth = depth;
+    r->cur = si;
+    return RTR_OK;
+}
+
+}  // namespace
+
+namespace rtr {
+int flush_pending(rtr_renderer* r) {
+    PendingFrame& pf = r->pending;
+    if (!pf.active) return RTR_OK;
+    FrameSet& fs = r->set[pf.si];
+    cudaStream_t s = r->stream;
+    // the frame's blend alone: a list of its own chunks (all flagged kTileBlend) through the same kernel.  The list is
+    // rebuilt in place: the previous frame's gated fix-up (image stream) may still have to read the old one.
+    RTR_CUDA(r, cudaStreamWaitEvent(s, r->set[(pf.si + kFrameSets - 1) % kFrameSets].rendered, 0));
+    fs.cull_parity ^= 1u;
+    RTR_CUDA(r, launch_classify_pair(s, r->sm_count, r->bounds, r->n_chunks, pf.plan.cp, true, pf.plan.cp, false, fs.vis_list, fs.cull_state,
+                                     fs.cull_parity));
+    RingSchedule sched = ring_schedule_for(r, fs, true);
+    sched.tile_counter = r->ring_dynamic > 0 ? tile_counters(fs.cull_state, 0) : nullptr;
+    const int bv = blend_variant_now(r, false);
+    fs.f32acc = (bv & 4) != 0;
+    RTR_CUDA(r, launch_fused_ring(s, r->sm_count, r->zmin_variant, bv, r->points, r->n_points, pf.plan.pp, pf.plan.pp, sched, fs.fb.zbuf,
+                                  fs.fb.accum, fs.fb.zbuf));
+    r->launches += 2;
+    RTR_CUDA(r, cudaEventRecord(fs.points_done, s));
+    return finish_images(r, pf, pf.si, (bv & 4) != 0, nullptr);
+}
+}  // namespace rtr
+
+namespace {
 
 // D2H of one frame set's outputs on the copy stream (after its render event).
 int enqueue_copy(rtr_renderer* r, int si, uint8_t* bgr, float* depth) {
@@ -444,7 +645,7 @@ int render_to_host(rtr_renderer* r, int stage, uint8_t* bgr, float* depth) {
     rc = enqueue_copy(r, r->cur, bgr, depth);
     if (rc != RTR_OK) return rc;
     RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
-    return RTR_OK;
+    return peer_status(r);
 }
 
 }  // namespace
@@ -523,16 +724,25 @@ int rtr_create(int device, rtr_renderer** out) {
     rtr_renderer* r = new rtr_renderer;
     r->device = device;
     r->sm_count = prop.multiProcessorCount;
+    // Fused sequences keep three streams busy; when CTAs of several are ready the small kernels should go first: the
+    // clear + classification (the next point pass waits for them) and the image passes (short CTAs that fit beside the
+    // persistent point pass) get the higher priority.  RTR_STREAM_PRIORITY=0: all equal (A/B).
+    int prio_lo = 0, prio_hi = 0;
+    const char* pe = std::getenv("RTR_STREAM_PRIORITY");
+    if (!(pe && pe[0] == '0')) (void)cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&r->stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&r->clear_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
         delete r;
         return cuda_fail(nullptr, e, "stream creation");
     }
     for (auto& s : r->set) {
         cudaEventCreateWithFlags(&s.rendered, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.points_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.cleared, cudaEventDisableTiming);
     }
     for (auto& ev : r->ev) cudaEventCreate(&ev);
     if (cudaHostAlloc(reinterpret_cast<void**>(&r->overflow_note), 64, cudaHostAllocMapped) == cudaSuccess) {
@@ -549,22 +759,25 @@ int rtr_create(int device, rtr_renderer** out) {
 void rtr_destroy(rtr_renderer* r) {
     if (!r) return;
     cudaSetDevice(r->device);
+    r->pending.active = false;  // an outstanding blend is simply dropped
     sync_compute(r);
     cudaStreamSynchronize(r->copy_stream);
     if (r->comm) g_nccl.CommDestroy(r->comm);
     rtr_peer_detach(r);
     cudaFree(r->peer.flags);
+    if (r->peer.err_host) cudaFreeHost(r->peer.err_host);
     cudaFree(r->post_scratch);
     if (r->overflow_note) cudaFreeHost(r->overflow_note);
     free_frame_sets(r);
     if (r->owns_points) cudaFree(r->points);
     free_cull_storage(r);
-    for (auto& s : r->set) { cudaEventDestroy(s.rendered); cudaEventDestroy(s.copied); }
+    for (auto& s : r->set) { cudaEventDestroy(s.rendered); cudaEventDestroy(s.copied); cudaEventDestroy(s.points_done); cudaEventDestroy(s.cleared); }
     for (auto& ev : r->ev) cudaEventDestroy(ev);
     for (auto& ev : r->ev_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(r->stream);
     cudaStreamDestroy(r->stream2);
     cudaStreamDestroy(r->copy_stream);
+    cudaStreamDestroy(r->clear_stream);
     delete r;
 }
 
@@ -575,9 +788,11 @@ const char* rtr_last_error(const rtr_renderer* r) { return r ? r->err.c_str() : 
 namespace rtr {
 int replace_cloud(rtr_renderer* r, uint64_t n) {
     RTR_CUDA(r, cudaSetDevice(r->device));
+    r->pending.active = false;  // a frame of the old cloud whose blend is outstanding is dropped with the cloud
     RTR_CUDA(r, sync_compute(r));
     if (r->owns_points) cudaFree(r->points);
     free_cull_storage(r);
+    r->index_base = 0;
     r->n_chunks = 0;
     r->points = nullptr; r->n_points = 0; r->owns_points = false;
     if (n == 0) return RTR_OK;
@@ -742,27 +957,43 @@ int rtr_render_tensor(rtr_renderer* r, void** device_fp16) {
     if (rc != RTR_OK) return rc;
     RTR_CUDA(r, sync_compute(r));
     *device_fp16 = r->set[r->cur].fb.tensor;
-    return RTR_OK;
+    return peer_status(r);
+}
+
+// One asynchronous frame of a sequence: fused with its neighbours when the sequence qualifies (see enqueue_fused),
+// else a whole frame alternating between two frame sets / streams (pipeline) or into the current set.
+static int enqueue_sequence_frame(rtr_renderer* r, int stage, uint8_t* bgr, float* depth) {
+    if (!r->points || r->n_points == 0) return fail(r, RTR_ERR_STATE, "no cloud uploaded");
+    FramePlan pl;
+    int rc = plan_frame(r, pl);
+    if (rc != RTR_OK) return rc;
+    if (fused_sequence(r, pl)) return enqueue_fused(r, stage, pl, bgr, depth);
+    if ((rc = flush_pending(r)) != RTR_OK) return rc;
+    if (r->cur >= 2) r->cur = 0;  // whole frames alternate between sets 0 and 1
+    const int si = (bgr || depth || pipelined(r)) ? other_set(r->cur) : r->cur;  // the other set: this one may still drain over PCIe
+    rc = enqueue_frame(r, stage, si, true);
+    if (rc != RTR_OK) return rc;
+    r->cur = si;
+    if (bgr || depth) rc = enqueue_copy(r, si, bgr, depth);
+    return rc;
 }
 
 int rtr_render_device(rtr_renderer* r, int stage) {
     if (!r) return RTR_ERR_ARG;
     if (stage != RTR_STAGE_RGBD && stage != RTR_STAGE_FILTERED) return fail(r, RTR_ERR_ARG, "bad stage");
     RTR_CUDA(r, cudaSetDevice(r->device));
-    // back-to-back asynchronous frames alternate between the two frame sets and the two streams: the point passes of
-    // one frame overlap the image passes of the previous one.  r->cur = the set of the frame enqueued last.
-    const int si = pipelined(r) ? (r->cur ^ 1) : r->cur;
-    const int rc = enqueue_frame(r, stage, si, true);
-    if (rc == RTR_OK) r->cur = si;
-    return rc;
+    // back-to-back asynchronous frames: r->cur = the set of the frame enqueued last
+    return enqueue_sequence_frame(r, stage, nullptr, nullptr);
 }
 
 int rtr_sync(rtr_renderer* r) {
     if (!r) return RTR_ERR_ARG;
     RTR_CUDA(r, cudaSetDevice(r->device));
+    const int rc = flush_pending(r);
+    if (rc != RTR_OK) return rc;
     RTR_CUDA(r, sync_compute(r));
     RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
-    return RTR_OK;
+    return peer_status(r);
 }
 
 int rtr_render_trajectory(rtr_renderer* r, int stage, const double* poses, int n_frames, uint8_t* bgr, float* depth) {
@@ -773,23 +1004,18 @@ int rtr_render_trajectory(rtr_renderer* r, int stage, const double* poses, int n
     for (int f = 0; f < n_frames; ++f) {
         int rc = rtr_set_pose_w2c(r, poses + size_t(f) * 16);
         if (rc != RTR_OK) return rc;
-        const int si = (bgr || depth || pipelined(r)) ? (r->cur ^ 1) : r->cur;  // the other set: this one may still drain over PCIe
-        rc = enqueue_frame(r, stage, si, true);
+        rc = enqueue_sequence_frame(r, stage, bgr ? bgr + size_t(f) * P * 3 : nullptr, depth ? depth + size_t(f) * P : nullptr);
         if (rc != RTR_OK) return rc;
-        r->cur = si;
-        if (bgr || depth) {
-            rc = enqueue_copy(r, si, bgr ? bgr + size_t(f) * P * 3 : nullptr, depth ? depth + size_t(f) * P : nullptr);
-            if (rc != RTR_OK) return rc;
-        }
     }
-    RTR_CUDA(r, sync_compute(r));
-    RTR_CUDA(r, cudaStreamSynchronize(r->copy_stream));
-    return RTR_OK;
+    return rtr_sync(r);
 }
 
 int rtr_get_device_buffers(rtr_renderer* r, rtr_device_buffers* out) {
     if (!r || !out) return RTR_ERR_ARG;
     if (r->alloc_W == 0) return fail(r, RTR_ERR_STATE, "no frame rendered yet");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    const int frc = flush_pending(r);
+    if (frc != RTR_OK) return frc;
     const FrameBuffers& fb = r->set[r->cur].fb;
     std::memset(out, 0, sizeof(*out));
     out->points = r->points; out->zbuf = fb.zbuf; out->accum = fb.accum; out->image = fb.image; out->tensor = fb.tensor;
@@ -811,6 +1037,9 @@ int rtr_get_device_buffers(rtr_renderer* r, rtr_device_buffers* out) {
 int rtr_read_buffer(rtr_renderer* r, int what, void* dst, size_t bytes) {
     if (!r || !dst) return RTR_ERR_ARG;
     if (r->alloc_W == 0) return fail(r, RTR_ERR_STATE, "no frame rendered yet");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    const int frc = flush_pending(r);
+    if (frc != RTR_OK) return frc;
     const FrameBuffers& fb = r->set[r->cur].fb;
     const size_t P = size_t(r->alloc_W) * r->alloc_H;
     const void* src = nullptr;
@@ -955,20 +1184,42 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "ring_ctas")) return &r->ring_ctas;
     if (!std::strcmp(key, "ring_claim_min")) return &r->ring_claim_min;
     if (!std::strcmp(key, "pipeline")) return &r->pipeline;
+    if (!std::strcmp(key, "fuse")) return &r->fuse;
+    if (!std::strcmp(key, "peer_timeout_ms")) return &r->peer.timeout_ms;
     return nullptr;
 }
 
 int rtr_set_option(rtr_renderer* r, const char* key, int64_t value) {
     if (!r || !key) return RTR_ERR_ARG;
-    if (!std::strcmp(key, "index_base")) { r->index_base = uint64_t(value); return RTR_OK; }
+    // options apply to frames enqueued from now on: a frame whose blend is still outstanding is completed first
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    const int frc = flush_pending(r);
+    if (frc != RTR_OK) return frc;
+    if (!std::strcmp(key, "index_base")) {
+        // the 64-bit key holds the global point index in its low word
+        if (value < 0 || uint64_t(value) + r->n_points > (1ull << 32)) return fail(r, RTR_ERR_ARG, "index_base + cloud size must not exceed 2^32");
+        r->index_base = uint64_t(value);
+        return RTR_OK;
+    }
     int* slot = option_slot(r, key);
     if (!slot) return fail(r, RTR_ERR_ARG, std::string("unknown option: ") + key);
     if ((!std::strcmp(key, "zmin_unroll") || !std::strcmp(key, "blend_unroll")) && value != 1 && value != 2 && value != 4 && value != 8)
         return fail(r, RTR_ERR_ARG, "unroll must be 1, 2, 4 or 8");
-    if (!std::strcmp(key, "zmin_variant") && !((value & 7) == 0 || (value & 7) == 1 || (value & 7) == 2 || (value & 7) == 3 || (value & 7) == 5 || (value & 7) == 7))
-        return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7 (+8/16 measurement bits)");
-    if (!std::strcmp(key, "blend_variant") && (value < 0 || (value & ~38)))
-        return fail(r, RTR_ERR_ARG, "blend_variant must be 0, 2, 4 or 6 (+32 measurement bit)");
+    // Bits 8 / 16 / 32 select measurement-only kernels (no RED issued, ATOMG builtin, no in-register merge) whose frames
+    // are WRONG or slower by design: they exist only in -DRTR_EXPERIMENTS builds (RTR_EXPERIMENTS=1 python build.py),
+    // never in the library a caller links.
+    // (bit 64 = shared-memory tile pre-reduction of the z-min ring pass: exact, a supported variant)
+#ifdef RTR_EXPERIMENTS
+    const int64_t zmask = 7 | 8 | 16 | 32 | 64, bmask = 6 | 32;
+#else
+    const int64_t zmask = 7 | 64, bmask = 6;
+#endif
+    if (!std::strcmp(key, "zmin_variant") &&
+        (value < 0 || (value & ~zmask) || !((value & 7) == 0 || (value & 7) == 1 || (value & 7) == 2 || (value & 7) == 3 || (value & 7) == 5 || (value & 7) == 7)))
+        return fail(r, RTR_ERR_ARG, "zmin_variant must be one of 0,1,2,3,5,7 (measurement bits 8/16/32 only in RTR_EXPERIMENTS builds)");
+    if (!std::strcmp(key, "blend_variant") && (value < 0 || (value & ~bmask)))
+        return fail(r, RTR_ERR_ARG, "blend_variant must be 0, 2, 4 or 6 (measurement bit 32 only in RTR_EXPERIMENTS builds)");
+    if (!std::strcmp(key, "timing") && (value < 0 || value > 3)) return fail(r, RTR_ERR_ARG, "timing must be 0 ... 3");
     *slot = int(value);
     return RTR_OK;
 }
@@ -978,11 +1229,16 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "index_base")) return int64_t(r->index_base);
     if (!std::strcmp(key, "sm_count")) return r->sm_count;
     if (!std::strcmp(key, "int_sum_frames")) return r->int_sum_frames;  // frames left that start with integer colour sums
-    if (!std::strcmp(key, "peer_error")) {  // 1 when a cross-GPU wait of the peer merge timed out
-        uint32_t v = 0;
-        if (r->peer.flags) { cudaSetDevice(r->device); sync_compute(const_cast<rtr_renderer*>(r)); cudaMemcpy(&v, r->peer.flags + 65, 4, cudaMemcpyDeviceToHost); }
-        return v;
+    if (!std::strcmp(key, "pending")) return r->pending.active ? 1 : 0;  // a fused sequence's last frame still lacks its blend
+    if (!std::strcmp(key, "experiments")) {
+#ifdef RTR_EXPERIMENTS
+        return 1;
+#else
+        return 0;
+#endif
     }
+    if (!std::strcmp(key, "peer_error"))  // 1 while a timed-out wait of the peer merge has not been reported by a render / sync call yet
+        return r->peer.err_host ? int64_t(*reinterpret_cast<volatile uint32_t*>(r->peer.err_host)) : 0;
     const int* slot = option_slot(const_cast<rtr_renderer*>(r), key);
     return slot ? *slot : RTR_ERR_ARG;
 }
@@ -1011,24 +1267,63 @@ int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, i
     return RTR_OK;
 }
 
-int rtr_get_cull_stats(rtr_renderer* r, uint64_t* frames, uint64_t* visible_chunks_total, uint64_t* n_chunks, int reset) {
-    if (!r || !frames || !visible_chunks_total || !n_chunks) return RTR_ERR_ARG;
-    *frames = *visible_chunks_total = 0;
-    *n_chunks = r->n_chunks;
+static int read_cull_totals(rtr_renderer* r, CullState* sum, int reset) {
+    std::memset(sum, 0, sizeof(*sum));
     if (!r->set[0].cull_state) return RTR_OK;
     RTR_CUDA(r, cudaSetDevice(r->device));
+    const int frc = flush_pending(r);
+    if (frc != RTR_OK) return frc;
     RTR_CUDA(r, sync_compute(r));
-    for (auto& fs : r->set) {  // frames of a pipelined sequence alternate between the two sets
+    for (auto& fs : r->set) {  // frames of a sequence rotate through the sets
         CullState st;
         RTR_CUDA(r, cudaMemcpy(&st, fs.cull_state, sizeof(st), cudaMemcpyDeviceToHost));
-        *frames += uint64_t(st.frames) + (st.armed ? 1u : 0u);   // the frame in flight is folded at the next clear
-        *visible_chunks_total += st.total_visible + (st.armed ? cull_count(&st) : 0u);
+        if (st.armed) cull_fold(&st, st.parity & 1u);  // the list in flight is folded on the device by the next classification
+        sum->frames += st.frames;
+        sum->total_visible += st.total_visible;
+        sum->total_streamed += st.total_streamed;
+        sum->passes += st.passes;
         if (reset) {
             RTR_CUDA(r, cudaMemset(fs.cull_state, 0, sizeof(CullState)));
+            RTR_CUDA(r, cudaMemset(smem_tile_stats(fs.cull_state), 0, 64));
             fs.cull_parity = 0;
         }
     }
     return RTR_OK;
+}
+
+int rtr_get_smem_tile_stats(rtr_renderer* r, uint64_t* stats4) {
+    if (!r || !stats4) return RTR_ERR_ARG;
+    for (int i = 0; i < 4; ++i) stats4[i] = 0;
+    if (!r->set[0].cull_state) return RTR_OK;
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    const int frc = flush_pending(r);
+    if (frc != RTR_OK) return frc;
+    RTR_CUDA(r, sync_compute(r));
+    for (auto& fs : r->set) {
+        unsigned long long v[4];
+        RTR_CUDA(r, cudaMemcpy(v, smem_tile_stats(fs.cull_state), sizeof(v), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 4; ++i) stats4[i] += v[i];
+    }
+    return RTR_OK;
+}
+
+int rtr_get_cull_stats(rtr_renderer* r, uint64_t* frames, uint64_t* visible_chunks_total, uint64_t* n_chunks, int reset) {
+    if (!r || !frames || !visible_chunks_total || !n_chunks) return RTR_ERR_ARG;
+    CullState t;
+    const int rc = read_cull_totals(r, &t, reset);
+    *frames = t.frames;
+    *visible_chunks_total = t.total_visible;
+    *n_chunks = r->n_chunks;
+    return rc;
+}
+
+int rtr_get_stream_stats(rtr_renderer* r, uint64_t* passes, uint64_t* chunks_streamed, int reset) {
+    if (!r || !passes || !chunks_streamed) return RTR_ERR_ARG;
+    CullState t;
+    const int rc = read_cull_totals(r, &t, reset);
+    *passes = t.passes;
+    *chunks_streamed = t.total_streamed;
+    return rc;
 }
 
 uint64_t rtr_launch_count(const rtr_renderer* r) { return r ? r->launches : 0; }
@@ -1064,7 +1359,12 @@ namespace {
 struct PeerBlob {
     uint32_t magic;
     int32_t W, H;
-    cudaIpcMemHandle_t flags, zbuf[2], accum[2];
+    int32_t pid, device, has_zkey;
+    uint64_t zbuf_off, image_off;
+    void* raw_flags;             // the addresses themselves: peers inside ONE process (one thread per GPU) use them directly
+    void* raw_arena[2];
+    void* raw_zkey[2];
+    cudaIpcMemHandle_t flags, arena[2], zkey[2];
 };
 static_assert(sizeof(PeerBlob) <= 512, "blob must fit RTR_PEER_BLOB_BYTES");
 }  // namespace
@@ -1074,21 +1374,43 @@ int rtr_peer_export(rtr_renderer* r, void* blob512) {
     RTR_CUDA(r, cudaSetDevice(r->device));
     if (r->W < 16 || r->H < 16) return fail(r, RTR_ERR_STATE, "set the intrinsics before rtr_peer_export");
     if ((uint64_t(r->W) * r->H) % 4) return fail(r, RTR_ERR_UNSUPPORTED, "peer merge needs W*H divisible by 4");
-    int rc = ensure_buffers(r);
+    int rc = rtr_peer_detach(r);  // (completes an outstanding frame, waits for the streams)
     if (rc != RTR_OK) return rc;
-    if (!r->peer.flags) {
-        RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->peer.flags), 4096));
-        RTR_CUDA(r, cudaMemset(r->peer.flags, 0, 4096));
+    rc = ensure_buffers(r);
+    if (rc != RTR_OK) return rc;
+    rtr_renderer::Peer& pe = r->peer;
+    if (!pe.flags) RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&pe.flags), 4096));
+    if (!pe.err_host) {
+        RTR_CUDA(r, cudaHostAlloc(reinterpret_cast<void**>(&pe.err_host), 64, cudaHostAllocMapped));
+        RTR_CUDA(r, cudaHostGetDevicePointer(reinterpret_cast<void**>(&pe.err_dev), pe.err_host, 0));
     }
+    // A fresh protocol state with every export: flag words and epochs start from zero on every rank, so a re-attach
+    // (after a resolution change, a lost peer, a different set of ranks) can never meet stale epochs.  Nobody writes
+    // this rank's flags any more: its last merge kernel only finished after every peer's last signal had arrived.
+    RTR_CUDA(r, cudaMemset(pe.flags, 0, 4096));
+    *reinterpret_cast<volatile uint32_t*>(pe.err_host) = 0u;
+    pe.epoch = 1;
+    pe.local_base = 0;
+    pe.exported = true;
     RTR_CUDA(r, sync_compute(r));
     PeerBlob b;
     std::memset(&b, 0, sizeof(b));
-    b.magic = 0x52545250u;
+    b.magic = 0x52545251u;
     b.W = r->W; b.H = r->H;
-    RTR_CUDA(r, cudaIpcGetMemHandle(&b.flags, r->peer.flags));
+    b.pid = int32_t(getpid());
+    b.device = r->device;
+    b.has_zkey = r->key64 ? 1 : 0;
+    b.zbuf_off = r->set[0].zbuf_off;
+    b.image_off = r->set[0].image_off;
+    b.raw_flags = pe.flags;
+    RTR_CUDA(r, cudaIpcGetMemHandle(&b.flags, pe.flags));
     for (int i = 0; i < 2; ++i) {
-        RTR_CUDA(r, cudaIpcGetMemHandle(&b.zbuf[i], r->set[i].fb.zbuf));
-        RTR_CUDA(r, cudaIpcGetMemHandle(&b.accum[i], r->set[i].fb.accum));
+        b.raw_arena[i] = r->set[i].arena;
+        RTR_CUDA(r, cudaIpcGetMemHandle(&b.arena[i], r->set[i].arena));
+        if (r->key64) {
+            b.raw_zkey[i] = r->set[i].fb.zkey;
+            RTR_CUDA(r, cudaIpcGetMemHandle(&b.zkey[i], r->set[i].fb.zkey));
+        }
     }
     std::memset(blob512, 0, 512);
     std::memcpy(blob512, &b, sizeof(b));
@@ -1098,6 +1420,7 @@ int rtr_peer_export(rtr_renderer* r, void* blob512) {
 int rtr_peer_detach(rtr_renderer* r) {
     if (!r) return RTR_ERR_ARG;
     cudaSetDevice(r->device);
+    flush_pending(r);
     sync_compute(r);
     for (void* p : r->peer.opened) cudaIpcCloseMemHandle(p);
     r->peer.opened.clear();
@@ -1107,37 +1430,57 @@ int rtr_peer_detach(rtr_renderer* r) {
 
 int rtr_peer_attach(rtr_renderer* r, const void* blobs, int rank, int n_ranks) {
     if (!r || !blobs || n_ranks < 1 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks) return RTR_ERR_ARG;
-    if (!r->peer.flags) return fail(r, RTR_ERR_STATE, "call rtr_peer_export first");
-    RTR_CUDA(r, cudaSetDevice(r->device));
-    rtr_peer_detach(r);
     rtr_renderer::Peer& pe = r->peer;
+    if (!pe.flags || !pe.exported) return fail(r, RTR_ERR_STATE, "call rtr_peer_export first (every attach needs a fresh export on every rank)");
+    RTR_CUDA(r, cudaSetDevice(r->device));
+    for (void* p : pe.opened) cudaIpcCloseMemHandle(p);
+    pe.opened.clear();
+    pe.attached = false;
+    std::memset(pe.peer_buf, 0, sizeof(pe.peer_buf));
     for (int p = 0; p < n_ranks; ++p) {
         PeerBlob b;
         std::memcpy(&b, static_cast<const char*>(blobs) + size_t(p) * 512, sizeof(b));
-        if (b.magic != 0x52545250u) return fail(r, RTR_ERR_ARG, "bad peer blob");
+        if (b.magic != 0x52545251u) return fail(r, RTR_ERR_ARG, "bad peer blob");
         if (b.W != r->W || b.H != r->H) return fail(r, RTR_ERR_ARG, "peers render different resolutions");
+        void* flags = nullptr;
+        void* arena[2] = {nullptr, nullptr};
+        void* zkey[2] = {nullptr, nullptr};
         if (p == rank) {
-            pe.peer_flags[p] = pe.flags;
-            for (int i = 0; i < 2; ++i) { pe.peer_zbuf[i][p] = r->set[i].fb.zbuf; pe.peer_accum[i][p] = r->set[i].fb.accum; }
-            continue;
+            flags = pe.flags;
+            for (int i = 0; i < 2; ++i) { arena[i] = r->set[i].arena; zkey[i] = r->set[i].fb.zkey; }
+        } else if (b.pid == int32_t(getpid())) {  // a renderer of this process (one thread per GPU): plain peer access
+            if (b.device != r->device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(r, e, "cudaDeviceEnablePeerAccess");
+                (void)cudaGetLastError();
+            }
+            flags = b.raw_flags;
+            for (int i = 0; i < 2; ++i) { arena[i] = b.raw_arena[i]; zkey[i] = b.has_zkey ? b.raw_zkey[i] : nullptr; }
+        } else {
+            auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> cudaError_t {
+                cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+                if (e == cudaSuccess) pe.opened.push_back(*out);
+                return e;
+            };
+            RTR_CUDA(r, open(b.flags, &flags));
+            for (int i = 0; i < 2; ++i) {
+                RTR_CUDA(r, open(b.arena[i], &arena[i]));
+                if (b.has_zkey) RTR_CUDA(r, open(b.zkey[i], &zkey[i]));
+            }
         }
-        auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> cudaError_t {
-            cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
-            if (e == cudaSuccess) pe.opened.push_back(*out);
-            return e;
-        };
-        void* q = nullptr;
-        RTR_CUDA(r, open(b.flags, &q));
-        pe.peer_flags[p] = static_cast<uint32_t*>(q);
+        pe.peer_flags[p] = static_cast<uint32_t*>(flags);
         for (int i = 0; i < 2; ++i) {
-            RTR_CUDA(r, open(b.zbuf[i], &q));
-            pe.peer_zbuf[i][p] = static_cast<uint32_t*>(q);
-            RTR_CUDA(r, open(b.accum[i], &q));
-            pe.peer_accum[i][p] = static_cast<uint32_t*>(q);
+            char* a = static_cast<char*>(arena[i]);
+            pe.peer_buf[1][i][p] = a;                  // colour sums at the start of the arena
+            pe.peer_buf[0][i][p] = a + b.zbuf_off;
+            pe.peer_buf[3][i][p] = a + b.image_off;
+            pe.peer_buf[2][i][p] = zkey[i];
         }
     }
     pe.rank = rank; pe.n = n_ranks; pe.W = r->W; pe.H = r->H;
     pe.attached = n_ranks > 1;
+    pe.exported = false;
+    r->cur = 0;
     return RTR_OK;
 }
 

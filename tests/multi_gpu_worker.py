@@ -94,8 +94,67 @@ def main():
         print(f"[rank {rank}] peer merge: a cross-GPU wait timed out", flush=True)
         ok = False
     dist.barrier()
+
+    def reattach(pc):
+        """detach / export / all-gather / attach: every attach needs a fresh export on every rank."""
+        pc.peer_detach()
+        blob = torch.frombuffer(bytearray(pc.peer_export()), dtype=torch.uint8).cuda()
+        blobs = [torch.zeros(512, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(blobs, blob)
+        pc.peer_attach(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs), rank, world)
+
+    # ---- a lost peer: only rank 0 renders; its merge kernel must give up after peer_timeout_ms and the CALL must fail
+    peer.set_option("peer_timeout_ms", 400)
+    if rank == 0:
+        try:
+            frame(peer, pkg, calib, case.poses[0], P)
+            print("[rank 0] lost peer: the render call returned success", flush=True)
+            ok = False
+        except pkg.RtrError as e:
+            if e.code != pkg.RTR_ERR_COMM:
+                print(f"[rank 0] lost peer: wrong error {e}", flush=True)
+                ok = False
+    dist.barrier()
+    peer.set_option("peer_timeout_ms", 10000)
+    reattach(peer)                                   # fresh flags and epochs on every rank: the next frames merge again
+    for E in case.poses:
+        got = frame(peer, pkg, calib, E, P)
+        dig = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in got)).digest()
+        t = torch.frombuffer(bytearray(dig), dtype=torch.uint8).cuda()
+        if rank == 0:
+            want = frame(full, pkg, calib, E, P)
+            t = torch.frombuffer(bytearray(hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in want)).digest()), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        same = bytes(t.cpu().numpy().tobytes()) == dig
+        if not same:
+            print(f"[rank {rank}] peer merge after re-attach: frame differs from the single-GPU frame", flush=True)
+        ok &= same
+    dist.barrier()
     peer.peer_detach()
     peer.close()
+    # ---- north_star's merge through the peer kernels: min over the ranks of the 64-bit (depth bits << 32 | point index) keys
+    pk = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, first=first, count=count, hall=case.hall, n_boxes=case.n_boxes, device=local, sort=SORT)
+    pk.set_option("key64", 1)                        # before the export: the key buffers are mapped by the peers too
+    pk.set_camera(calib)
+    reattach(pk)
+    for E in case.poses:
+        got = frame(pk, pkg, calib, E, P)
+        dig = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in got)).digest()
+        t = torch.frombuffer(bytearray(dig), dtype=torch.uint8).cuda()
+        if rank == 0:
+            full.set_option("key64", 1)
+            want = frame(full, pkg, calib, E, P)
+            t = torch.frombuffer(bytearray(hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in want)).digest()), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        same = bytes(t.cpu().numpy().tobytes()) == dig
+        if not same:
+            print(f"[rank {rank}] peer merge of 64-bit keys: frame differs from the single-GPU frame", flush=True)
+        ok &= same
+    if rank == 0:
+        full.set_option("key64", 0)
+    dist.barrier()
+    pk.peer_detach()
+    pk.close()
     # ---- frame-sharded
     poses = pkg.trajectory_w2c(11, center=(6.0, 5.0, 1.5), radius=2.0)
     rep = pkg.ProjectCloud.synthetic(seed=case.seed, n_total=n, hall=case.hall, n_boxes=case.n_boxes, device=local, sort=SORT)

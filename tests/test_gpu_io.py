@@ -131,3 +131,20 @@ def test_config1_ply_file_to_reference_frame(gpu, cpu_oracle, tmp_path):
         assert scenes.sha(depth) == bytes(g["f0_flt_depth_host_sha"]).decode()
         assert scenes.sha(color) == bytes(g["f0_flt_color_host_sha"]).decode()
         assert scenes.sha(tensor) == bytes(g["f0_flt_tensor_sha"]).decode()
+
+
+def test_ply_header_promising_more_vertices_than_the_file_holds(gpu, tmp_path):
+    """A corrupt vertex count (2^32 - 1 here: 64 GB of records if trusted) is checked against the file size before
+    anything is allocated; the call returns RTR_ERR_ARG instead of throwing bad_alloc through the C ABI."""
+    p = tmp_path / "lying.ply"
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex 4294967295\nproperty float x\nproperty float y\n"
+              "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n").encode()
+    p.write_bytes(header + b"\0" * 150)
+    with pytest.raises(gpu.RtrError) as e:
+        gpu.ProjectCloud.from_ply(str(p))
+    assert e.value.code == gpu.RTR_ERR_ARG and "truncated" in str(e.value)
+    q = tmp_path / "lying_ascii.ply"
+    q.write_bytes(b"ply\nformat ascii 1.0\nelement vertex 100000000\nproperty float x\nproperty float y\nproperty float z\nend_header\n1 2 3\n")
+    with pytest.raises(gpu.RtrError) as e:
+        gpu.ProjectCloud.from_ply(str(q))
+    assert e.value.code == gpu.RTR_ERR_ARG

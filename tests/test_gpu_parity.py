@@ -164,8 +164,11 @@ def test_cuda_vs_live_reference(gpu, cpu_oracle, name):
 VARIANTS = [dict(zmin_variant=v, zmin_unroll=u, blend_variant=b, blend_unroll=u, chunk_cull=c, ring=r)
             for v, u, b, c, r in [(0, 1, 0, 0, 0), (1, 2, 2, 0, 0), (2, 4, 0, 0, 0), (3, 8, 2, 0, 0), (5, 4, 0, 0, 0), (7, 4, 2, 0, 0),
                                   (0, 4, 2, 1, 0), (1, 4, 0, 1, 0), (3, 4, 0, 1, 0), (7, 4, 2, 1, 0), (5, 4, 4, 1, 0), (5, 4, 6, 0, 0),
-                                  (5, 2, 4, 0, 0), (21, 4, 4, 1, 0),
+                                  (5, 2, 4, 0, 0),
                                   (0, 4, 0, 0, 2), (1, 4, 4, 0, 2), (5, 4, 4, 0, 2), (0, 4, 4, 1, 1), (1, 4, 0, 1, 1), (5, 4, 0, 1, 2)]]
+# zmin_variant bit 6: shared-memory tile pre-reduction in the z-min ring pass (two-pass frames; list and stream-all)
+VARIANTS += [dict(zmin_variant=64 | 5, ring=1, chunk_cull=1, fuse=0), dict(zmin_variant=64 | 5, ring=2, chunk_cull=0),
+             dict(zmin_variant=64 | 5, ring=1, chunk_cull=1, fuse=0, ring_claim_min=0, ring_ctas=1)]
 # ring_dynamic: how the list passes of the ring kernels hand out tiles — 0 round-robin, q > 0 claimed from q counters
 VARIANTS += [dict(ring=1, chunk_cull=1, ring_dynamic=q, ring_claim_min=0) for q in (0, 1, 3, 8, 64)] + [dict(ring=1, chunk_cull=1, clear_lean=0)]
 # ring_ctas = 1: one ring-kernel CTA per SM (half the grid)
@@ -179,6 +182,24 @@ def test_kernel_variants_give_identical_frames(gpu, cpu_oracle, opts):
     base, _, _ = render_mine(gpu, case, rec, with_taps=False)
     other, _, _ = render_mine(gpu, case, rec, options=opts, with_taps=False)
     assert_frames_equal(other, base, f"variant {opts}")
+
+
+def test_measurement_only_kernels_are_not_selectable(gpu, cpu_oracle):
+    """Variant bits 8 / 16 / 32 (no RED issued, ATOMG builtin, no in-register merge) select kernels whose frames are wrong
+    or slower by design; they exist only in -DRTR_EXPERIMENTS builds and a caller of the shipped library cannot reach them."""
+    pc = gpu.ProjectCloud.from_packed(cloud_of(cpu_oracle, scenes.CASES["small_160x96"]))
+    if pc.get_option("experiments") == 1:
+        pc.close()
+        pytest.skip("this is an RTR_EXPERIMENTS build")
+    for key, value in (("zmin_variant", 8 | 5), ("zmin_variant", 16 | 5), ("zmin_variant", 32 | 5), ("zmin_variant", 128 | 5),
+                       ("blend_variant", 32 | 4), ("blend_variant", 8), ("zmin_variant", -1)):
+        with pytest.raises(gpu.RtrError) as e:
+            pc.set_option(key, value)
+        assert e.value.code == gpu.RTR_ERR_ARG
+        assert pc.get_option(key) in (5, 4)                     # unchanged defaults
+    with pytest.raises(gpu.RtrError):
+        pc.set_option("index_base", (1 << 32) - 5)              # index_base + cloud size must fit the key's 32-bit index
+    pc.close()
 
 
 def test_generic_path_equals_fused_path(gpu, cpu_oracle):

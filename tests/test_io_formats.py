@@ -180,3 +180,25 @@ def test_ply_writer_layout(pkg, small_cloud, tmp_path):
     assert head.startswith(b"ply\nformat binary_little_endian 1.0\nelement vertex 100\n") and len(body) == 100 * 15
     rec = np.frombuffer(body, dtype=np.dtype([("p", "<f4", 3), ("rgb", "u1", 3)]))
     assert np.array_equal(rec["p"], xyz[:100]) and np.array_equal(rec["rgb"][:, ::-1], bgr[:100])   # file is R,G,B
+
+
+def test_corrupt_files_return_errors_instead_of_throwing(pkg, tmp_path):
+    """Header fields of a corrupt / truncated file are bounded by the file size before anything is allocated, and no
+    C++ exception crosses the C ABI: the calls return RTR_ERR_ARG (a 2^32-vertex PLY header, an .oct header announcing
+    2^31 - 1 blocks, a block announcing 2^40 points, truncated payloads)."""
+    import ctypes as C
+    import struct
+    lib = pkg.load_library()
+    # .oct: absurd block count / absurd block size / truncated block
+    for name, payload in (("blocks.oct", struct.pack("<4i", 4, 4, 4, 2**31 - 1)),
+                          ("count.oct", struct.pack("<4i", 4, 4, 4, 1) + struct.pack("<iQ", 7, 2**40)),
+                          ("trunc.oct", struct.pack("<4i", 4, 4, 4, 1) + struct.pack("<iQ", 7, 1000) + b"\0" * 100),
+                          ("neg.oct", struct.pack("<4i", 4, 4, 4, -5))):
+        p = tmp_path / name
+        p.write_bytes(payload)
+        xyz, bgr, n = C.POINTER(C.c_float)(), C.POINTER(C.c_uint8)(), C.c_uint64(0)
+        hdr = (C.c_int * 4)()
+        rc = lib.rtr_io_read_oct(os.fsencode(str(p)), C.byref(xyz), C.byref(bgr), C.byref(n), hdr, None, None)
+        assert rc == pkg.RTR_ERR_ARG, name
+        assert not xyz and not bgr and n.value == 0
+    # (the PLY loader needs a renderer, i.e. a GPU: its header bound is checked in tests/test_gpu_io.py)
