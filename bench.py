@@ -633,9 +633,9 @@ def run_b200(args, wl):
         # visible chunks), timed on the point stream while the previous frame's image passes run on the image stream
         st = staged_loop(3)
         streamed = min(count, st["chunks_per_pass"] * 1024.0)
-        names3 = ["clear_classify_pair (clear stream)", "wait", "fused_blend_zmin (point stream)", "wait_for_image_stream",
-                  "resolve_pyramid_minmax_fixup_gate_up_pass (image stream)", "first_to_last_event"]
-        fused_ms = st["stage_ms"][2]
+        names3 = ["classify_pair (point stream)", "fused_blend_zmin (point stream)", "wait_for_image_stream",
+                  "resolve_pyramid_minmax_fixup_gate (image stream)", "up_pass_tensor (image stream)", "first_to_last_event"]
+        fused_ms = st["stage_ms"][1]
         kl = kernel_line(fused_ms, streamed)
         roofline = {"bound": "hbm",
                     "kernel": (f"fused_ring_kernel: blend of frame k-1 + z-min of frame k over ONE stream of chunks (the union of the two frames' visible "

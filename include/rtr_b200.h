@@ -148,8 +148,8 @@ int rtr_get_stage_ms(rtr_renderer* r, float* ms6);
 /* With option timing=2 every frame records its own six events (pooled); this returns the per-stage
  * SUMS in ms over all frames rendered since the last reset, and how many frames that was.
  * timing=3 does the same for fused sequences, per point pass that carries both halves:
- * {clear + chunk classification for two cameras (clear stream), wait, fused pass: blend k-1 + z-min k (point stream),
- *  wait, resolve + fix-up gate + up-pass of frame k-1 (image stream), first to last event} — the three streams
+ * {chunk classification for two cameras, fused pass: blend k-1 + z-min k (both on the point stream), wait,
+ *  resolve + fix-up gate of frame k-1, up-pass of frame k-1 (image stream), first to last event} — the two streams
  * overlap one another across frames.  (timing 1 / 2 render whole frames one after the other.) */
 int rtr_get_stage_ms_sum(rtr_renderer* r, double* ms6_sum, uint64_t* n_frames, int reset);
 /* Chunk-level frustum culling statistics since the last reset: frames rendered with culling, the sum

@@ -185,12 +185,18 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) clear_classify_kernel(uint32_
 // the chunks the reference's per-point test would keep and the per-point tests inside the pass stay exact.
 // 128 threads x <= 64 registers = 8 K registers: what two resident CTAs of the fused point pass (2 x 512 x 56) leave free
 // on an SM, so the classification for the NEXT pass runs beside the current one (it is enqueued on the clear stream).
+// LATE_WAIT (fused sequences): nothing this kernel reads or writes is touched by the point pass in front of it, so it
+// lets its own dependents be scheduled at once, classifies while that pass is still draining, and only THEN waits for
+// it — completion stays transitive along the stream (the next pass waits for this kernel, this kernel for the previous
+// pass), but the classification no longer sits between two passes.
+template <bool LATE_WAIT>
 __global__ void __launch_bounds__(128, 8) classify_pair_kernel(const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
                                                                const __grid_constant__ CullParams cp_blend,
                                                                const __grid_constant__ CullParams cp_zmin, uint32_t have,
                                                                uint32_t* __restrict__ vis_list, CullState* __restrict__ cull,
                                                                uint32_t parity) {
-    pdl_prologue();
+    if constexpr (LATE_WAIT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else pdl_prologue();
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
     if (tid == 0) {
@@ -225,18 +231,20 @@ __global__ void __launch_bounds__(128, 8) classify_pair_kernel(const ChunkBounds
             if (flags) vis_list[base + __popc(m & ((1u << lane) - 1u))] = uint32_t(c) | flags;
         }
     }
+    if constexpr (LATE_WAIT) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 cudaError_t launch_classify_pair(cudaStream_t s, int sm_count, const ChunkBounds* bounds, uint32_t n_chunks,
                                  const CullParams& cp_blend, bool have_blend, const CullParams& cp_zmin, bool have_zmin,
-                                 uint32_t* vis_list, CullState* cull, uint32_t parity) {
+                                 uint32_t* vis_list, CullState* cull, uint32_t parity, bool late_wait) {
     const uint32_t have = (have_blend ? 1u : 0u) | (have_zmin ? 2u : 0u);
     // one thread per chunk, at most 8 CTAs per SM (the list is short: a few microseconds, latency-bound)
     unsigned grid = (n_chunks + 127u) / 128u;
     const unsigned cap = unsigned(sm_count) * 8u;
     if (grid > cap) grid = cap;
     if (grid < 1u) grid = 1u;
-    launch_pdl(classify_pair_kernel, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity);
+    if (late_wait) launch_pdl(classify_pair_kernel<true>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity);
+    else launch_pdl(classify_pair_kernel<false>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity);
     return cudaGetLastError();
 }
 

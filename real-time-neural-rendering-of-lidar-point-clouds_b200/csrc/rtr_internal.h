@@ -12,7 +12,7 @@
 typedef struct ncclComm* ncclComm_t;
 
 namespace rtr {
-constexpr int kFrameSets = 3;  // a fused frame sequence has three frames in flight: z-min of k, blend of k-1, image passes / D2H of k-2
+constexpr int kFrameSets = 4;  // a fused frame sequence: z-min of frame k, blend of k-1, image passes / D2H of k-2, and the set being cleared for k+1
 struct FrameSet {
     FrameBuffers fb{};
     // accum | zbuf | image live in ONE allocation (one CUDA IPC handle per set for the point-sharded merge)
@@ -20,9 +20,9 @@ struct FrameSet {
     size_t arena_bytes = 0, zbuf_off = 0, image_off = 0;
     bool f32acc = false;  // the last frame rendered into this set accumulated colour sums as floats
     cudaEvent_t rendered = nullptr, copied = nullptr;
-    // fused frame sequences: `points_done` = the point pass that z-min'ed this set's frame has finished; `cleared` =
-    // the clear stream has cleared the set and classified the chunks for the pass that z-mins into it
+    // fused frame sequences: `points_done` = the point pass that z-min'ed this set's frame has finished
     cudaEvent_t points_done = nullptr, cleared = nullptr;
+    bool clean = false;  // a point pass has cleared this set for the next frame of the sequence (no clear launch needed)
     // chunk-level frustum culling state of the frame rendered into this set (rtr_cull.cu); per set so that two frames
     // can be in flight on two streams
     uint32_t* vis_list = nullptr;
@@ -52,8 +52,8 @@ struct rtr_renderer {
     int device = 0;
     int sm_count = 148;
     // `stream`: everything; `stream2`: every other frame of an asynchronous frame sequence (option "pipeline")
-    // fused sequences: point passes on `stream`, image passes on `stream2`, clears of the set after next on `clear_stream`
-    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr, clear_stream = nullptr;
+    // fused sequences: point passes on `stream`, image passes on `stream2`
+    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
     // cloud
     rtr::PointRecord* points = nullptr;
     uint64_t n_points = 0;

@@ -195,9 +195,18 @@ cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const P
 // One stream of chunks for two frames: tiles flagged kTileBlend are blended for the camera pp_blend against
 // zbuf_blend (complete) into accum_blend, tiles flagged kTileZmin are z-min'ed for the camera pp_zmin into zbuf_zmin.
 // The list (sc.vis_list / sc.cull) comes from launch_classify_pair.  blend_variant bit 2: float colour sums.
+// `clear`: frame buffers the pass leaves cleared for the frame after next (fillBuffer + cudaMemset + min/max reset of
+// a set nobody reads any more) — every CTA clears its slice once it has run out of tiles; all-null = nothing to clear.
+struct ClearTarget {
+    uint32_t* zbuf;      // [0, cov) <- FLT_MAX bits
+    uint64_t cov;
+    uint4* accum;        // [0, n_px) <- 0
+    uint64_t n_px;
+    uint32_t* minmax;    // {UINT_MAX, 0, 0, 0}
+};
 cudaError_t launch_fused_ring(cudaStream_t s, int sm_count, int zmin_variant, int blend_variant, const PointRecord* pts,
                               uint64_t n, const ProjParams& pp_blend, const ProjParams& pp_zmin, const RingSchedule& sc,
-                              const uint32_t* zbuf_blend, uint32_t* accum_blend, uint32_t* zbuf_zmin);
+                              const uint32_t* zbuf_blend, uint32_t* accum_blend, uint32_t* zbuf_zmin, const ClearTarget& clear);
 
 // ---- chunk-level frustum culling (rtr_cull.cu)
 cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t n, ChunkBounds* bounds);
@@ -209,7 +218,7 @@ cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, 
 // have_blend) | kTileZmin (visible for cp_zmin, if have_zmin); chunks visible for neither are dropped.
 cudaError_t launch_classify_pair(cudaStream_t s, int sm_count, const ChunkBounds* bounds, uint32_t n_chunks,
                                  const CullParams& cp_blend, bool have_blend, const CullParams& cp_zmin, bool have_zmin,
-                                 uint32_t* vis_list, CullState* cull, uint32_t parity);
+                                 uint32_t* vis_list, CullState* cull, uint32_t parity, bool late_wait = false);
 cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                         uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,

@@ -535,6 +535,9 @@ __global__ void __launch_bounds__(kRingThreads, kRingMinCtas) blend_ring_kernel(
 #ifndef RTR_FUSED_REGS
 #define RTR_FUSED_REGS 64
 #endif
+#ifndef RTR_FUSED_SEQ
+#define RTR_FUSED_SEQ 0
+#endif
 #if RTR_FUSED_REGS >= 64
 #define RTR_FUSED_BOUNDS __launch_bounds__(kRingThreads, kRingMinCtas)
 #else
@@ -547,9 +550,25 @@ __global__ void RTR_FUSED_BOUNDS fused_ring_kernel(const PointRecord* __restrict
                                                                   const __grid_constant__ RingSchedule sc,
                                                                   const uint32_t* __restrict__ zbuf_blend,
                                                                   unsigned long long* __restrict__ accum_blend,
-                                                                  uint32_t* __restrict__ zbuf_zmin) {
+                                                                  uint32_t* __restrict__ zbuf_zmin,
+                                                                  const __grid_constant__ ClearTarget clr) {
     RingSmem& sm = ring_setup();
     ring_walk<true>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t entry, uint32_t, uint32_t rot, uint32_t valid) {
+#if RTR_FUSED_SEQ
+        // (experiment build: one half after the other — fewer live registers, two exposed gather latencies per tile)
+        if (entry & kTileZmin) {
+            ZminLanes<0> z;
+            zmin_project<ZV, DISTORT, 0>(z, p, pp_zmin, 0u, 0u, rot, valid, 0ull);
+            zmin_gather<ZV, 0>(z, zbuf_zmin, nullptr);
+            zmin_commit<ZV, 0>(z, zbuf_zmin, nullptr);
+        }
+        if (entry & kTileBlend) {
+            BlendLanes b;
+            blend_project<DISTORT>(b, p, pp_blend, rot, valid);
+            blend_gather(b, zbuf_blend);
+            blend_commit<BV>(b, p, accum_blend);
+        }
+#else
         ZminLanes<0> z;
         BlendLanes b;
         z.any = false;
@@ -564,7 +583,21 @@ __global__ void RTR_FUSED_BOUNDS fused_ring_kernel(const PointRecord* __restrict
         }
         zmin_commit<ZV, 0>(z, zbuf_zmin, nullptr);
         blend_commit<BV>(b, p, accum_blend);
+#endif
     });
+    // Out of tiles: clear this CTA's slice of the frame set the frame after next will use (fillBuffer + cudaMemset of
+    // the reference, render.cu:16-31, project_cloud.cu:316-317).  Nobody reads that set any more (the launch waited for
+    // its last frame's image passes and D2H), the stores are fire-and-forget, and the groups that finish first do
+    // them while the others still stream: no clear kernel, no launch on anybody's critical path.
+    if (clr.accum) {
+        const uint64_t t = uint64_t(blockIdx.x) * kRingThreads + threadIdx.x, stride = uint64_t(gridDim.x) * kRingThreads;
+        for (uint64_t i = t; i < clr.n_px; i += stride) clr.accum[i] = make_uint4(0u, 0u, 0u, 0u);
+        const uint64_t cov4 = clr.cov >> 2;
+        uint4* z4 = reinterpret_cast<uint4*>(clr.zbuf);
+        for (uint64_t i = t; i < cov4; i += stride) z4[i] = make_uint4(kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits);
+        for (uint64_t i = (cov4 << 2) + t; i < clr.cov; i += stride) clr.zbuf[i] = kEmptyDepthBits;
+        if (t == 0) { clr.minmax[0] = 0xFFFFFFFFu; clr.minmax[1] = 0u; clr.minmax[2] = 0u; clr.minmax[3] = 0u; }
+    }
 }
 
 // ---------------------------------------------------------------- host launchers
@@ -714,7 +747,7 @@ cudaError_t launch_blend_ring(cudaStream_t s, int sm_count, int variant, const P
 
 cudaError_t launch_fused_ring(cudaStream_t s, int sm_count, int zmin_variant, int blend_variant, const PointRecord* pts,
                               uint64_t n, const ProjParams& pp_blend, const ProjParams& pp_zmin, const RingSchedule& sc_in,
-                              const uint32_t* zbuf_blend, uint32_t* accum_blend, uint32_t* zbuf_zmin) {
+                              const uint32_t* zbuf_blend, uint32_t* accum_blend, uint32_t* zbuf_zmin, const ClearTarget& clear) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = ring_grid(sm_count, sc_in, true);
     RingSchedule sc = sc_in;
@@ -726,11 +759,11 @@ cudaError_t launch_fused_ring(cudaStream_t s, int sm_count, int zmin_variant, in
 #define RTR_FUSED(ZV)                                                                                                      \
     do {                                                                                                                   \
         if (distort) {                                                                                                     \
-            if (f32) RTR_RING_LAUNCH((fused_ring_kernel<ZV, 4, true>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin);  \
-            else RTR_RING_LAUNCH((fused_ring_kernel<ZV, 0, true>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin);      \
+            if (f32) RTR_RING_LAUNCH((fused_ring_kernel<ZV, 4, true>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin, clear);  \
+            else RTR_RING_LAUNCH((fused_ring_kernel<ZV, 0, true>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin, clear);      \
         } else {                                                                                                           \
-            if (f32) RTR_RING_LAUNCH((fused_ring_kernel<ZV, 4, false>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin); \
-            else RTR_RING_LAUNCH((fused_ring_kernel<ZV, 0, false>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin);     \
+            if (f32) RTR_RING_LAUNCH((fused_ring_kernel<ZV, 4, false>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin, clear); \
+            else RTR_RING_LAUNCH((fused_ring_kernel<ZV, 0, false>), pts, n, pp_blend, pp_zmin, sc, zbuf_blend, a2, zbuf_zmin, clear);     \
         }                                                                                                                  \
     } while (0)
     if (zv == 0) RTR_FUSED(0);

@@ -106,11 +106,10 @@ void free_cull_storage(rtr_renderer* r) {
         s.vis_list = nullptr; s.cull_state = nullptr; s.cull_parity = 0;
     }
 }
-// The compute streams idle (stream2 / clear_stream only ever hold work of a pipelined frame sequence).
+// The compute streams idle (stream2 only ever holds work of a pipelined frame sequence).
 cudaError_t sync_compute(rtr_renderer* r) {
     cudaError_t e = cudaStreamSynchronize(r->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream2);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(r->clear_stream);
     return e;
 }
 }  // namespace rtr
@@ -128,6 +127,7 @@ void free_frame_sets(rtr_renderer* r) {
         for (int i = 1; i <= 4; ++i) cudaFree(s.fb.level[i]);
         for (int i = 0; i < 4; ++i) cudaFree(s.fb.mask[i]);
         s.fb = FrameBuffers{};
+        s.clean = false;
     }
     r->alloc_W = r->alloc_H = 0;
     r->masks_allocated = r->key64_allocated = false;
@@ -385,7 +385,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     cudaStream_t s = (allow_pipeline && si == 1 && pipelined(r)) ? r->stream2 : r->stream;
     RTR_CUDA(r, cudaStreamWaitEvent(s, fs.rendered, 0));               // this set's previous frame (may have run on the other stream)
     if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, fs.copied, 0));  // previous D2H of this set must be done
-    RTR_CUDA(r, cudaStreamWaitEvent(s, fs.cleared, 0));  // (a fused sequence clears and classifies on the clear stream)
+    fs.clean = false;
     cudaEvent_t* ev = timing_events(r, &rc);
     if (rc != RTR_OK) return rc;
     const bool cull = pl.cull, use_ring = pl.use_ring;
@@ -491,13 +491,13 @@ int enqueue_copy(rtr_renderer* r, int si, uint8_t* bgr, float* depth);
 // ---- fused frame sequences: one stream of chunks per frame
 // Consecutive frames of an asynchronous sequence (rtr_render_device back to back, rtr_render_trajectory) see nearly the
 // same chunks.  Frame k is therefore enqueued as
-//     point stream:  classify_pair(k-1, k)  ->  fused pass: blend(k-1) + z-min(k) over the union of the two lists
+//     point stream:  classify_pair(k-1, k)  ->  fused pass: blend(k-1) + z-min(k) over the union of the two lists,
+//                    then every CTA clears its slice of the frame set frame k+1 will use
 //     image stream:  [wait fused pass]  resolve(k-1) -> exact fix-up gate -> up-pass(k-1)  [-> D2H(k-1) on the copy stream]
-//     clear stream:  clear of the set frame k+1 will use (it only waits for that set's previous frame, k-2)
-// so every chunk is read from HBM once per frame instead of twice, the point stream holds nothing but point passes,
-// and frame k stays "pending" (z-min done, blend outstanding) until frame k+1 arrives or flush_pending() runs its
-// blend alone.  Three frame sets: k (z-min), k-1 (blend, image passes), k-2 (D2H).  Frames are byte-identical to the
-// two-pass path (tests/test_gpu_fused.py).
+// so every chunk is read from HBM once per frame instead of twice, the point stream holds nothing but the passes and
+// their (overlapped) classification, and frame k stays "pending" (z-min done, blend outstanding) until frame k+1
+// arrives or flush_pending() runs its blend alone.  Four frame sets: k (z-min), k-1 (blend, then image passes),
+// k-2 (image passes / D2H), k+1 (being cleared).  Frames are byte-identical to the two-pass path (tests/test_gpu_fused.py).
 bool fused_sequence(const rtr_renderer* r, const FramePlan& pl) {
     return r->fuse && pipelined(r) && pl.cull && pl.use_ring && !r->key64 && r->ring >= 1;
 }
@@ -514,7 +514,7 @@ int finish_images(rtr_renderer* r, PendingFrame& pf, int pass_set, bool f32acc, 
     const bool filtered = pf.stage == RTR_STAGE_FILTERED;
     cudaStream_t s = r->stream2;
     RTR_CUDA(r, cudaStreamWaitEvent(s, ps.points_done, 0));
-    if (ev) cudaEventRecord(ev[4], s);
+    if (ev) cudaEventRecord(ev[3], s);
     RTR_CUDA(r, launch_resolve_pyramid(s, fb, W, H, r->dims, filtered, true, r->force_generic != 0, f32acc));
     r->launches += ((W % 16) == 0 && !r->force_generic) ? 1 : (filtered ? 6 : 1);
     if (f32acc) {
@@ -527,6 +527,7 @@ int finish_images(rtr_renderer* r, PendingFrame& pf, int pass_set, bool f32acc, 
         r->launches += 3;
         (void)cov;
     }
+    if (ev) cudaEventRecord(ev[4], s);
     if (filtered) {
         RTR_CUDA(r, launch_up_pass(s, fb, r->dims, r->force_generic != 0, r->fused_up != 0));
         r->launches += uint64_t(up_pass_launches(fb, r->dims, r->force_generic != 0, r->fused_up != 0));
@@ -548,28 +549,35 @@ int enqueue_fused(rtr_renderer* r, int stage, const FramePlan& pl, uint8_t* bgr,
     if (pf.active && pf.plan.pp.distort != pl.pp.distort && (rc = flush_pending(r)) != RTR_OK) return rc;  // one kernel, one projection model
     const int si = (pf.active ? pf.si + 1 : r->cur + 1) % kFrameSets;
     FrameSet& fs = r->set[si];
+    FrameSet& nx = r->set[(si + 1) % kFrameSets];  // the set the NEXT frame will use: this pass leaves it cleared
     const uint64_t P = uint64_t(r->W) * r->H, cov = clear_coverage(r->W, r->H);
-    cudaStream_t s = r->stream, c = r->clear_stream;
+    cudaStream_t s = r->stream;
     cudaEvent_t* ev = nullptr;
     if (r->timing == 3 && pf.active) {  // only passes that carry both halves are timed
         ev = timing_events(r, &rc);
         if (rc != RTR_OK) return rc;
     }
-    // clear stream: once the set is free (its previous frame's image passes and D2H are done — they also were the last
-    // readers of the set's visible list), clear it and classify the chunks for the two cameras.  The host enqueues
-    // frames ahead of the GPU, so this runs while the point stream is still busy with the previous pass.
-    RTR_CUDA(r, cudaStreamWaitEvent(c, fs.rendered, 0));
-    if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(c, fs.copied, 0));
-    if (ev) cudaEventRecord(ev[0], c);
-    RTR_CUDA(r, launch_clear(c, r->sm_count, fs.fb.zbuf, cov, fs.fb.accum, P, fs.fb.minmax, nullptr));
+    if (!fs.clean) {  // first frame of a sequence: nobody has cleared this set ahead of time
+        RTR_CUDA(r, cudaStreamWaitEvent(s, fs.rendered, 0));
+        if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, fs.copied, 0));
+        RTR_CUDA(r, launch_clear(s, r->sm_count, fs.fb.zbuf, cov, fs.fb.accum, P, fs.fb.minmax, nullptr));
+        r->launches += 1;
+    }
+    // the set this pass clears must be free: its last frame's image passes (which were also the last readers of that
+    // set's visible list) and D2H copy done — three frames back, long finished unless the copies are the bottleneck
+    ClearTarget clr{nullptr, 0, nullptr, 0, nullptr};
+    if (!nx.clean) {
+        RTR_CUDA(r, cudaStreamWaitEvent(s, nx.rendered, 0));
+        if (nx.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, nx.copied, 0));
+        clr = ClearTarget{nx.fb.zbuf, cov, reinterpret_cast<uint4*>(nx.fb.accum), P, nx.fb.minmax};
+    }
+    // point stream: classification for the two cameras (it starts while the previous pass drains and waits for it only
+    // at its end), then the pass
+    if (ev) cudaEventRecord(ev[0], s);
     fs.cull_parity ^= 1u;
-    RTR_CUDA(r, launch_classify_pair(c, r->sm_count, r->bounds, r->n_chunks, pf.active ? pf.plan.cp : pl.cp, pf.active, pl.cp, true,
-                                     fs.vis_list, fs.cull_state, fs.cull_parity));
-    if (ev) cudaEventRecord(ev[1], c);
-    RTR_CUDA(r, cudaEventRecord(fs.cleared, c));
-    // point stream: nothing but the passes, back to back
-    RTR_CUDA(r, cudaStreamWaitEvent(s, fs.cleared, 0));
-    if (ev) cudaEventRecord(ev[2], s);
+    RTR_CUDA(r, launch_classify_pair(s, r->sm_count, r->bounds, r->n_chunks, pf.active ? pf.plan.cp : pl.cp, pf.active, pl.cp, true,
+                                     fs.vis_list, fs.cull_state, fs.cull_parity, true));
+    if (ev) cudaEventRecord(ev[1], s);
     RingSchedule sched = ring_schedule_for(r, fs, true);
     sched.tile_counter = r->ring_dynamic > 0 ? tile_counters(fs.cull_state, 0) : nullptr;
     int bv = r->blend_variant;
@@ -579,9 +587,11 @@ int enqueue_fused(rtr_renderer* r, int stage, const FramePlan& pl, uint8_t* bgr,
     }
     const FrameSet& prev = r->set[pf.active ? pf.si : si];
     RTR_CUDA(r, launch_fused_ring(s, r->sm_count, r->zmin_variant, bv, r->points, r->n_points, pf.active ? pf.plan.pp : pl.pp, pl.pp, sched,
-                                  prev.fb.zbuf, prev.fb.accum, fs.fb.zbuf));
-    r->launches += 3;
-    if (ev) cudaEventRecord(ev[3], s);
+                                  prev.fb.zbuf, prev.fb.accum, fs.fb.zbuf, clr));
+    r->launches += 2;
+    fs.clean = false;
+    nx.clean = true;
+    if (ev) cudaEventRecord(ev[2], s);
     RTR_CUDA(r, cudaEventRecord(fs.points_done, s));
     if (pf.active) {
         if ((rc = finish_images(r, pf, si, (bv & 4) != 0, ev)) != RTR_OK) return rc;
@@ -616,7 +626,7 @@ int flush_pending(rtr_renderer* r) {
     const int bv = blend_variant_now(r, false);
     fs.f32acc = (bv & 4) != 0;
     RTR_CUDA(r, launch_fused_ring(s, r->sm_count, r->zmin_variant, bv, r->points, r->n_points, pf.plan.pp, pf.plan.pp, sched, fs.fb.zbuf,
-                                  fs.fb.accum, fs.fb.zbuf));
+                                  fs.fb.accum, fs.fb.zbuf, ClearTarget{nullptr, 0, nullptr, 0, nullptr}));
     r->launches += 2;
     RTR_CUDA(r, cudaEventRecord(fs.points_done, s));
     return finish_images(r, pf, pf.si, (bv & 4) != 0, nullptr);
@@ -724,17 +734,16 @@ int rtr_create(int device, rtr_renderer** out) {
     rtr_renderer* r = new rtr_renderer;
     r->device = device;
     r->sm_count = prop.multiProcessorCount;
-    // Fused sequences keep three streams busy; when CTAs of several are ready the small kernels should go first: the
-    // clear + classification (the next point pass waits for them) and the image passes (short CTAs that fit beside the
-    // persistent point pass) get the higher priority.  RTR_STREAM_PRIORITY=0: all equal (A/B).
+    // Fused sequences keep two compute streams busy (point passes / image passes).  The image stream gets the higher
+    // priority: its short CTAs fill an SM the moment a CTA of the persistent point pass leaves it, instead of queueing
+    // behind the next pass (+4 % frames/s, profiles/r02e_exp_fused_ab.json; RTR_STREAM_PRIORITY=0: equal priorities).
     int prio_lo = 0, prio_hi = 0;
     const char* pe = std::getenv("RTR_STREAM_PRIORITY");
     if (!(pe && pe[0] == '0')) (void)cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&r->stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithPriority(&r->clear_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete r;
         return cuda_fail(nullptr, e, "stream creation");
     }
@@ -777,7 +786,6 @@ void rtr_destroy(rtr_renderer* r) {
     cudaStreamDestroy(r->stream);
     cudaStreamDestroy(r->stream2);
     cudaStreamDestroy(r->copy_stream);
-    cudaStreamDestroy(r->clear_stream);
     delete r;
 }
 
