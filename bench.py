@@ -251,16 +251,17 @@ def run_reference(args, wl):
 
 # ------------------------------------------------------------------------------------------
 def pose_schedule(n_steps, n_poses, world, rank, segments=4):
-    """Which trajectory pose each of this rank's frames renders.  Frame f of the trajectory goes to rank f mod N
-    (SURVEY.md §8 e), so a rank's consecutive frames are N poses apart.  A run shorter than the loop is cut into
-    `segments` arcs of consecutive frames spread evenly over the loop: any step count samples the easy and the hard
-    parts of the trajectory alike, and within an arc the frame-to-frame motion is the real trajectory's (which is what
-    the fused sequences' shared chunk stream depends on).  At 1000 steps the arcs tile the whole loop."""
+    """Which trajectory pose each of this rank's frames renders.  The trajectory is dealt to the ranks in contiguous runs
+    of frames (SURVEY.md §8 e allows "f mod G or contiguous chunks"; contiguous keeps the frame-to-frame motion the real
+    trajectory's, which is what the fused sequences' shared chunk stream depends on).  A run shorter than the loop is cut
+    into `segments` arcs per rank, and the segments x world arcs are spread evenly over the loop, so any step count
+    samples the easy and the hard parts of the trajectory alike; at 1000 steps on one GPU the arcs tile the whole loop."""
     seg_len = -(-n_steps // segments)
     out = []
     for i in range(n_steps):
         seg, off = divmod(i, seg_len)
-        out.append((seg * n_poses // segments + off * world + rank) % n_poses)
+        start = ((seg * world + rank) * n_poses) // (segments * world)
+        out.append((start + off) % n_poses)
     return out
 
 
@@ -556,7 +557,7 @@ def run_b200(args, wl):
         if world > 1:
             attach_merge(pkg, torch, dist, pc, "nccl" if args.nccl else "peer", rank, world)
     poses = trajectory(pkg, hall, n_poses)
-    idx = pose_schedule(K_steps + Wm, n_poses, world if args.mode == "frames" else 1, rank if args.mode == "frames" else 0)
+    idx = pose_schedule(K_steps + Wm, n_poses, world if args.mode == "frames" else 1, rank if args.mode == "frames" else 0)   # points mode: every rank renders the same poses
     my = np.ascontiguousarray(np.stack([poses[i] for i in idx]).reshape(-1, 16))
 
     def set_pose(i):
@@ -778,7 +779,7 @@ def run_b200(args, wl):
                        "sharding": ("frame-sharded, cloud replicated" if args.mode == "frames" else
                                     ("point-sharded, ncclAllReduce min/sum" if args.nccl else "point-sharded, two-shot min/sum all-reduce kernels over NVLink peer memory")),
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
-                       "poses": f"{K_steps} timed frames per rank in 4 arcs of consecutive trajectory frames spread over the {n_poses}-pose loop (frame f -> rank f mod N)",
+                       "poses": f"{K_steps} timed frames per rank in 4 arcs of consecutive trajectory frames; the 4 x {world} arcs are spread evenly over the {n_poses}-pose loop",
                        "distortion": bool(args.distort),
                        "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "ring_dynamic", "clear_lean", "fused_up", "pipeline", "fuse", "zmin_variant", "blend_variant", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),

@@ -94,6 +94,10 @@ struct rtr_renderer {
     int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)
     int ring_dynamic = 8;  // list passes of the ring kernels: tiles beyond a CTA's first ring-full are claimed from this many counters (0: round-robin)
     int ring_claim_min = 12;  // tiles are claimed only in list passes with more tiles per CTA than this (0: always)
+    int fused_tiles_per_cta = 0;  // fused pass: 0 = persistent grid (2 CTAs per SM claim tiles until the list is empty); t > 0 = about t tiles
+                                  // per CTA, i.e. many short-lived CTAs between which the block scheduler slots the image stream's CTAs
+    uint32_t* tiles_hint = nullptr;      // mapped pinned word: tiles of the last fused pass (sizes the next launch when fused_tiles_per_cta > 0)
+    uint32_t* tiles_hint_dev = nullptr;
     int ring_ctas = 2;  // ring-kernel CTAs per SM: 2 fill the SM's shared memory, 1 leaves room for the other frame's ring kernel
     int clear_lean = 1;  // clear + classify compiled for <= 64 registers, so that it fits beside the other frame's ring kernel (0: 80 registers)
     int ring_perm = 1;  // stream-all ring passes visit the chunks in a low-discrepancy order (0: storage order)

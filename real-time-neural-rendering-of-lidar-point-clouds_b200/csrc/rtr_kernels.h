@@ -167,6 +167,10 @@ struct RingSchedule {
     uint32_t n_queues;       // 1 ... kMaxTileQueues
     uint32_t claim_min_tiles_per_cta;  // list passes with no more tiles per CTA than this stay round-robin (default 12)
     uint32_t ctas_per_sm;    // host side: CTAs launched per SM (2 fill an SM's shared memory; 1 leaves room for another frame's ring kernel)
+    uint32_t grid_override;  // host side, fused pass: launch this many CTAs instead of a persistent grid (0: persistent); tiles are
+                             // then dealt round-robin, a CTA takes a handful of tiles and leaves, and the SM's block scheduler can
+                             // slot the image stream's CTAs in between (option fused_tiles_per_cta)
+    uint32_t* tiles_hint;    // mapped host word: the fused pass reports how many tiles its list held (sizes the next launch)
 };
 // Claimed tiles (list passes): a CTA's first `stages` tiles are tiles blockIdx.x + k * grid of the launch; the tiles from
 // stages * grid on are dealt round-robin into n_queues queues, entry c of queue q being this tile.  Every tile index

@@ -553,6 +553,10 @@ __global__ void RTR_FUSED_BOUNDS fused_ring_kernel(const PointRecord* __restrict
                                                                   uint32_t* __restrict__ zbuf_zmin,
                                                                   const __grid_constant__ ClearTarget clr) {
     RingSmem& sm = ring_setup();
+    if (sc.tiles_hint && blockIdx.x == 0 && threadIdx.x == 0) {  // (the list is older than this grid's PDL wait only in flush passes; a stale hint is harmless)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        *reinterpret_cast<volatile uint32_t*>(sc.tiles_hint) = __ldcg(sc.cull->n_visible + (__ldcg(&sc.cull->parity) & 1u));
+    }
     ring_walk<true>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t entry, uint32_t, uint32_t rot, uint32_t valid) {
 #if RTR_FUSED_SEQ
         // (experiment build: one half after the other — fewer live registers, two exposed gather latencies per tile)
@@ -609,6 +613,8 @@ RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const 
     sc.tile_counter = nullptr;
     sc.n_queues = 1;
     sc.ctas_per_sm = kRingCtasPerSm;
+    sc.grid_override = 0;
+    sc.tiles_hint = nullptr;
     sc.claim_min_tiles_per_cta = 12;
     sc.n_chunks = uint32_t((n_points + kChunkPoints - 1) / kChunkPoints);
     // golden-ratio stride, made coprime with n_chunks: t -> (t * mul) mod n_chunks is a permutation whose every
@@ -749,8 +755,12 @@ cudaError_t launch_fused_ring(cudaStream_t s, int sm_count, int zmin_variant, in
                               uint64_t n, const ProjParams& pp_blend, const ProjParams& pp_zmin, const RingSchedule& sc_in,
                               const uint32_t* zbuf_blend, uint32_t* accum_blend, uint32_t* zbuf_zmin, const ClearTarget& clear) {
     if (n == 0) return cudaSuccess;
-    const unsigned grid = ring_grid(sm_count, sc_in, true);
+    unsigned grid = ring_grid(sm_count, sc_in, true);
     RingSchedule sc = sc_in;
+    if (sc.grid_override > grid) {  // short-lived CTAs, tiles dealt round-robin (no claims)
+        grid = sc.grid_override;
+        sc.tile_counter = nullptr;
+    }
     sc.n_queues = ring_effective_queues(grid, kRingGroups, sc.n_queues);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum_blend);
     const bool f32 = (blend_variant & 4) != 0, distort = pp_zmin.distort != 0;

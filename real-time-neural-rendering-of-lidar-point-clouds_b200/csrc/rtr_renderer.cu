@@ -337,6 +337,8 @@ RingSchedule ring_schedule_for(const rtr_renderer* r, const FrameSet& fs, bool c
     sched.n_queues = uint32_t(r->ring_dynamic < 1 ? 1 : (r->ring_dynamic > kMaxTileQueues ? kMaxTileQueues : r->ring_dynamic));
     sched.cull = cull ? fs.cull_state : nullptr;
     sched.vis_list = cull ? fs.vis_list : nullptr;
+    sched.grid_override = 0;
+    sched.tiles_hint = nullptr;
     return sched;
 }
 
@@ -502,6 +504,12 @@ bool fused_sequence(const rtr_renderer* r, const FramePlan& pl) {
     return r->fuse && pipelined(r) && pl.cull && pl.use_ring && !r->key64 && r->ring >= 1;
 }
 
+#ifdef RTR_EXPERIMENTS
+// Measurement only (wrong frames): RTR_EXP_NO_IMAGES=1 skips the image passes of fused sequences, RTR_EXP_NO_EVENTS=1 the
+// event records / waits between the point stream's kernels — what the point stream costs on its own.
+static bool exp_flag(const char* name) { const char* e = std::getenv(name); return e && e[0] == '1'; }
+#endif
+
 // resolve -> fix-up gate -> up-pass (+ D2H) of the pending frame, on the image stream, once the point pass that
 // blended it (recorded in `pass_set`'s points_done; the pass's list lives in pass_set too) has finished.
 int finish_images(rtr_renderer* r, PendingFrame& pf, int pass_set, bool f32acc, cudaEvent_t* ev) {
@@ -513,6 +521,9 @@ int finish_images(rtr_renderer* r, PendingFrame& pf, int pass_set, bool f32acc, 
     const uint64_t P = uint64_t(W) * H, cov = clear_coverage(W, H);
     const bool filtered = pf.stage == RTR_STAGE_FILTERED;
     cudaStream_t s = r->stream2;
+#ifdef RTR_EXPERIMENTS
+    if (exp_flag("RTR_EXP_NO_IMAGES")) { pf.active = false; return RTR_OK; }
+#endif
     RTR_CUDA(r, cudaStreamWaitEvent(s, ps.points_done, 0));
     if (ev) cudaEventRecord(ev[3], s);
     RTR_CUDA(r, launch_resolve_pyramid(s, fb, W, H, r->dims, filtered, true, r->force_generic != 0, f32acc));
@@ -566,9 +577,15 @@ int enqueue_fused(rtr_renderer* r, int stage, const FramePlan& pl, uint8_t* bgr,
     // the set this pass clears must be free: its last frame's image passes (which were also the last readers of that
     // set's visible list) and D2H copy done — three frames back, long finished unless the copies are the bottleneck
     ClearTarget clr{nullptr, 0, nullptr, 0, nullptr};
+    bool no_events = false;
+#ifdef RTR_EXPERIMENTS
+    no_events = exp_flag("RTR_EXP_NO_EVENTS");
+#endif
     if (!nx.clean) {
-        RTR_CUDA(r, cudaStreamWaitEvent(s, nx.rendered, 0));
-        if (nx.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, nx.copied, 0));
+        if (!no_events) {
+            RTR_CUDA(r, cudaStreamWaitEvent(s, nx.rendered, 0));
+            if (nx.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, nx.copied, 0));
+        }
         clr = ClearTarget{nx.fb.zbuf, cov, reinterpret_cast<uint4*>(nx.fb.accum), P, nx.fb.minmax};
     }
     // point stream: classification for the two cameras (it starts while the previous pass drains and waits for it only
@@ -585,6 +602,11 @@ int enqueue_fused(rtr_renderer* r, int stage, const FramePlan& pl, uint8_t* bgr,
         bv = blend_variant_now(r, false);
         r->set[pf.si].f32acc = (bv & 4) != 0;
     }
+    if (r->fused_tiles_per_cta > 0 && r->tiles_hint) {
+        sched.tiles_hint = r->tiles_hint_dev;
+        const uint32_t last = *reinterpret_cast<volatile uint32_t*>(r->tiles_hint);  // a few passes old: a hint, any grid is correct
+        sched.grid_override = last / uint32_t(r->fused_tiles_per_cta);
+    }
     const FrameSet& prev = r->set[pf.active ? pf.si : si];
     RTR_CUDA(r, launch_fused_ring(s, r->sm_count, r->zmin_variant, bv, r->points, r->n_points, pf.active ? pf.plan.pp : pl.pp, pl.pp, sched,
                                   prev.fb.zbuf, prev.fb.accum, fs.fb.zbuf, clr));
@@ -592,7 +614,7 @@ int enqueue_fused(rtr_renderer* r, int stage, const FramePlan& pl, uint8_t* bgr,
     fs.clean = false;
     nx.clean = true;
     if (ev) cudaEventRecord(ev[2], s);
-    RTR_CUDA(r, cudaEventRecord(fs.points_done, s));
+    if (!no_events) RTR_CUDA(r, cudaEventRecord(fs.points_done, s));
     if (pf.active) {
         if ((rc = finish_images(r, pf, si, (bv & 4) != 0, ev)) != RTR_OK) return rc;
         if (ev) r->ev_frames += 1;
@@ -754,6 +776,13 @@ int rtr_create(int device, rtr_renderer** out) {
         cudaEventCreateWithFlags(&s.cleared, cudaEventDisableTiming);
     }
     for (auto& ev : r->ev) cudaEventCreate(&ev);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&r->tiles_hint), 64, cudaHostAllocMapped) == cudaSuccess) {
+        *r->tiles_hint = 0u;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&r->tiles_hint_dev), r->tiles_hint, 0) != cudaSuccess) { cudaFreeHost(r->tiles_hint); r->tiles_hint = nullptr; }
+    } else {
+        (void)cudaGetLastError();
+        r->tiles_hint = nullptr;
+    }
     if (cudaHostAlloc(reinterpret_cast<void**>(&r->overflow_note), 64, cudaHostAllocMapped) == cudaSuccess) {
         *r->overflow_note = 0u;
         if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&r->overflow_note_dev), r->overflow_note, 0) != cudaSuccess) r->overflow_note_dev = nullptr;
@@ -777,6 +806,7 @@ void rtr_destroy(rtr_renderer* r) {
     if (r->peer.err_host) cudaFreeHost(r->peer.err_host);
     cudaFree(r->post_scratch);
     if (r->overflow_note) cudaFreeHost(r->overflow_note);
+    if (r->tiles_hint) cudaFreeHost(r->tiles_hint);
     free_frame_sets(r);
     if (r->owns_points) cudaFree(r->points);
     free_cull_storage(r);
@@ -1193,6 +1223,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "ring_claim_min")) return &r->ring_claim_min;
     if (!std::strcmp(key, "pipeline")) return &r->pipeline;
     if (!std::strcmp(key, "fuse")) return &r->fuse;
+    if (!std::strcmp(key, "fused_tiles_per_cta")) return &r->fused_tiles_per_cta;
     if (!std::strcmp(key, "peer_timeout_ms")) return &r->peer.timeout_ms;
     return nullptr;
 }
