@@ -608,8 +608,7 @@ def run_b200(args, wl):
     # ---- leg 2: the same loop with per-stage CUDA events (roofline of the dominant kernel)
     peak, peak_src = peaks()
     culling = bool(pc.get_option("chunk_cull"))
-    fused = bool(pc.get_option("fuse")) and bool(pc.get_option("pipeline")) and culling and pc.get_option("ring") >= 1 and \
-        not pc.get_option("key64") and args.mode == "frames"
+    fused = pc.get_option("fuse_active") == 1 and args.mode == "frames"   # large clouds by default (option fuse)
 
     def staged_loop(timing):
         pc.set_option("timing", timing)
@@ -651,10 +650,11 @@ def run_b200(args, wl):
                     "note": "the pass does the arithmetic, gathers and reductions of BOTH of the reference's point passes on every record it reads; "
                             "`two_pass` is the same trajectory with fuse=0 (each frame streams its own list twice)"}
         # the same frames as two passes per frame (option fuse = 0): what each pass costs on its own
+        fuse_opt = pc.get_option("fuse")
         pc.set_option("fuse", 0)
         ms2, _ = timed_device_loop()
         st2 = staged_loop(2)
-        pc.set_option("fuse", 1)
+        pc.set_option("fuse", fuse_opt)
         vis2 = min(count, st2["visible_chunks_per_frame"] * 1024.0)
         roofline["two_pass"] = {"note": "fuse=0: zmin_ring_kernel and blend_ring_kernel each walk the frame's own visible list",
                                 "zmin": kernel_line(st2["stage_ms"][1], vis2), "blend": kernel_line(st2["stage_ms"][2], vis2),
@@ -781,7 +781,7 @@ def run_b200(args, wl):
                        "l2": f"inputs larger than L2 ({count * 16 / 1e6:.0f} MB cloud per GPU vs 126 MB)",
                        "poses": f"{K_steps} timed frames per rank in 4 arcs of consecutive trajectory frames; the 4 x {world} arcs are spread evenly over the {n_poses}-pose loop",
                        "distortion": bool(args.distort),
-                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "ring_dynamic", "clear_lean", "fused_up", "pipeline", "fuse", "zmin_variant", "blend_variant", "key64")}},
+                       "options": {k: pc.get_option(k) for k in ("chunk_cull", "ring", "ring_dynamic", "clear_lean", "fused_up", "pipeline", "fuse", "fuse_active", "zmin_variant", "blend_variant", "key64")}},
             "frames_per_s": frames_total / (ms * 1e-3), "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roofline, "e2e": e2e}
     if args.mode == "points" and world > 1 and not args.nccl:

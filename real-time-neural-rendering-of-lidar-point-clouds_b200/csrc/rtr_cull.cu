@@ -105,20 +105,22 @@ __device__ __forceinline__ bool chunk_visible(const ChunkBounds& b, const CullPa
     const bool sane = (ex < 1e30) & (ey < 1e30) & (ez < 1e30);  // false for NaN / inf / absurd matrices
     if (!sane) return true;
     const double cl = 1.5, cr = cp.W + 0.5, cb = cp.H + 0.5;
-    double f[4];
-    bool cut = box_range(cp.r2, lo, hi).hi + ez < 0.0;  // behind
+    // five independent plane tests, combined without short-circuit evaluation: a chain of `||` would make each test wait
+    // for the previous one's branch, and this kernel is nothing but the latency of its double-precision chain
+    double fl[4], fr[4], ft[4], fb[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] + cl * cp.r2[k];
-    cut = cut || (box_range(f, lo, hi).hi + (ex + cl * ez) < 0.0);  // left
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f[k] = cp.r0[k] - cr * cp.r2[k];
-    cut = cut || (box_range(f, lo, hi).lo - (ex + cr * ez) > 0.0);  // right
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] + cl * cp.r2[k];
-    cut = cut || (box_range(f, lo, hi).hi + (ey + cl * ez) < 0.0);  // top
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f[k] = cp.r1[k] - cb * cp.r2[k];
-    cut = cut || (box_range(f, lo, hi).lo - (ey + cb * ez) > 0.0);  // bottom
+    for (int k = 0; k < 4; ++k) {
+        fl[k] = cp.r0[k] + cl * cp.r2[k];
+        fr[k] = cp.r0[k] - cr * cp.r2[k];
+        ft[k] = cp.r1[k] + cl * cp.r2[k];
+        fb[k] = cp.r1[k] - cb * cp.r2[k];
+    }
+    const bool behind = box_range(cp.r2, lo, hi).hi + ez < 0.0;
+    const bool left = box_range(fl, lo, hi).hi + (ex + cl * ez) < 0.0;
+    const bool right = box_range(fr, lo, hi).lo - (ex + cr * ez) > 0.0;
+    const bool top = box_range(ft, lo, hi).hi + (ey + cl * ez) < 0.0;
+    const bool bottom = box_range(fb, lo, hi).lo - (ey + cb * ez) > 0.0;
+    const bool cut = behind | left | right | top | bottom;
     return !cut;
 }
 

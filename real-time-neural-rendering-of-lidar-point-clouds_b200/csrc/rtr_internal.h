@@ -75,7 +75,8 @@ struct rtr_renderer {
     rtr::FrameSet set[rtr::kFrameSets];
     int cur = 0;
     rtr::PendingFrame pending;
-    int fuse = 1;  // asynchronous frame sequences stream each chunk once per frame: blend of frame k-1 + z-min of frame k in one pass (0: two passes per frame)
+    int fuse = 1;  // asynchronous frame sequences stream each chunk once per frame (blend of frame k-1 + z-min of frame k in one pass):
+                   // 0 never, 2 always, 1 = for clouds of >= 40 000 chunks (where it pays, see fused_sequence)
     int alloc_W = 0, alloc_H = 0;
     rtr::PyramidDims dims{};
     bool masks_allocated = false, key64_allocated = false;
@@ -94,6 +95,7 @@ struct rtr_renderer {
     int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)
     int ring_dynamic = 8;  // list passes of the ring kernels: tiles beyond a CTA's first ring-full are claimed from this many counters (0: round-robin)
     int ring_claim_min = 12;  // tiles are claimed only in list passes with more tiles per CTA than this (0: always)
+    int fixup_launches = 1;  // fused sequences: the exact re-run gate as one cluster of 8 CTAs (1), a small cooperative grid (2) or three gated launches (3)
     int fused_tiles_per_cta = 0;  // fused pass: 0 = persistent grid (2 CTAs per SM claim tiles until the list is empty); t > 0 = about t tiles
                                   // per CTA, i.e. many short-lived CTAs between which the block scheduler slots the image stream's CTAs
     uint32_t* tiles_hint = nullptr;      // mapped pinned word: tiles of the last fused pass (sizes the next launch when fused_tiles_per_cta > 0)

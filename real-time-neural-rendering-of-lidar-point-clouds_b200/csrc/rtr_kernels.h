@@ -229,11 +229,12 @@ cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRec
                          const ProjParams& pp, const uint32_t* zbuf, uint32_t* accum, const uint32_t* gate);
 // The in-stream exact re-run after a float-accumulator overflow (clear + integer blend + resolve in one launch
 // that returns at once when minmax[2] == 0).  cull/vis_list null = all tiles.
+constexpr unsigned kFixupClusterCtas = 8;  // launch_exact_fixup(grid_ctas = kFixupClusterCtas): one thread-block cluster, no cooperative launch
 // need_flag: 0 for one-camera lists; kTileBlend for two-camera lists (only the entries carrying the flag are redone).
 cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf, uint32_t* accum,
                                uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note,
-                               uint32_t need_flag = 0u);
+                               uint32_t need_flag = 0u, unsigned grid_ctas = 0u);  // grid_ctas 0: two CTAs per SM
 // The exact re-run as three gated launches without a grid barrier (fused sequences: a cooperative grid on the image
 // stream would have to wait for the point stream's persistent kernel to leave the SMs): clear -> launch_blend_list
 // (integer sums, gate) -> launch_resolve_gated.  Each returns at once unless *gate != 0.

@@ -271,7 +271,14 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t target)
     __syncthreads();
 }
 
-template <bool LIST, bool DISTORT>
+// The same barrier for a grid that is ONE thread-block cluster: the hardware co-schedules a cluster's CTAs, so no
+// cooperative launch (which has to wait until the whole grid fits beside whatever occupies the SMs) is needed.
+__device__ __forceinline__ void cluster_barrier() {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool LIST, bool DISTORT, bool CLUSTER = false>
 __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRecord* __restrict__ pts, uint64_t n,
                                                                   const __grid_constant__ ProjParams pp,
                                                                   const CullState* __restrict__ cull,
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRec
     // it renders the next frames with integer sums straight away instead of paying for this re-run every frame
     if (tid == 0 && host_note) *reinterpret_cast<volatile uint32_t*>(host_note) = 1u;
     for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
-    grid_barrier(minmax + 3, gridDim.x);
+    if constexpr (CLUSTER) cluster_barrier(); else grid_barrier(minmax + 3, gridDim.x);
     unsigned long long* a2 = reinterpret_cast<unsigned long long*>(accum);
     if constexpr (LIST) {
         const uint32_t n_vis = cull_count(cull);
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(kPointBlock) exact_fixup_kernel(const PointRec
         for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
             blend_tile<kChunkPoints / kPointBlock, 0, DISTORT>(pts, n, t * kChunkPoints + threadIdx.x, pp, zbuf, a2);
     }
-    grid_barrier(minmax + 3, 2u * gridDim.x);
+    if constexpr (CLUSTER) cluster_barrier(); else grid_barrier(minmax + 3, 2u * gridDim.x);
     for (uint64_t id = tid; id < cov; id += stride) {  // resolvePass on the integer sums (render.cu:147-162)
         const uint4 a = __ldcg(accum + id);
         uint8_t b = 0, g = 0, r = 0;
@@ -387,10 +394,28 @@ cudaError_t launch_blend_list(cudaStream_t s, int sm_count, int variant, const P
 cudaError_t launch_exact_fixup(cudaStream_t s, int sm_count, const PointRecord* pts, uint64_t n, const ProjParams& pp,
                                const CullState* cull, const uint32_t* vis_list, const uint32_t* zbuf, uint32_t* accum,
                                uint64_t n_px, uint8_t* image, uint64_t cov, uint32_t* minmax, uint32_t* host_note,
-                               uint32_t need_flag) {
+                               uint32_t need_flag, unsigned grid_ctas) {
     if (n == 0) return cudaSuccess;
-    const dim3 grid(unsigned(sm_count) * 2u), block(kPointBlock);
     uint4* a4 = reinterpret_cast<uint4*>(accum);
+    if (grid_ctas == kFixupClusterCtas && cull) {
+        // fused sequences: ONE cluster of 8 CTAs (barrier.cluster between the phases).  The launch returns at once unless a pixel
+        // overflowed; when it has to work it is slow (8 SMs redo the frame's blend: of the order of a millisecond) — once, after
+        // which the renderer starts the next 64 frames of that view with integer sums.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kFixupClusterCtas);
+        cfg.blockDim = dim3(kPointBlock);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kFixupClusterCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        if (pp.distort) return cudaLaunchKernelEx(&cfg, exact_fixup_kernel<true, true, true>, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
+        return cudaLaunchKernelEx(&cfg, exact_fixup_kernel<true, false, true>, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
+    }
+    const dim3 grid(grid_ctas ? grid_ctas : unsigned(sm_count) * 2u), block(kPointBlock);
     if (cull && pp.distort) return launch_pdl_cooperative((exact_fixup_kernel<true, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
     if (cull) return launch_pdl_cooperative((exact_fixup_kernel<true, false>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);
     if (pp.distort) return launch_pdl_cooperative((exact_fixup_kernel<false, true>), grid, block, s, pts, n, pp, cull, vis_list, zbuf, a4, n_px, image, cov, minmax, host_note, need_flag);

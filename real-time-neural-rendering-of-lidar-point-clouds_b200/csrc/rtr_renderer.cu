@@ -500,8 +500,15 @@ int enqueue_copy(rtr_renderer* r, int si, uint8_t* bgr, float* depth);
 // their (overlapped) classification, and frame k stays "pending" (z-min done, blend outstanding) until frame k+1
 // arrives or flush_pending() runs its blend alone.  Four frame sets: k (z-min), k-1 (blend, then image passes),
 // k-2 (image passes / D2H), k+1 (being cleared).  Frames are byte-identical to the two-pass path (tests/test_gpu_fused.py).
+// Option fuse: 0 never, 2 always, 1 (default) when the cloud is large enough for the shared stream to pay: the fused
+// sequence trades one of the two chunk streams per frame for fewer, longer kernel boundaries in which the image passes
+// can run, which wins once a point pass is long (C3, 100 M points: 9 100 vs 8 020 frames/s) and loses on small clouds
+// whose frames are a few short kernels (C1, 1 M points: 46 200 vs 52 800; C2, 20 M points: 21 900 vs 23 400;
+// profiles/r02m_exp_fixup_gate.json).  The switch is the cloud's chunk count — known on the host without a read-back.
+constexpr uint32_t kFuseAutoMinChunks = 40000;  // 41 M points
 bool fused_sequence(const rtr_renderer* r, const FramePlan& pl) {
-    return r->fuse && pipelined(r) && pl.cull && pl.use_ring && !r->key64 && r->ring >= 1;
+    const bool want = r->fuse == 2 || (r->fuse == 1 && r->n_chunks >= kFuseAutoMinChunks);
+    return want && pipelined(r) && pl.cull && pl.use_ring && !r->key64 && r->ring >= 1;
 }
 
 #ifdef RTR_EXPERIMENTS
@@ -529,13 +536,24 @@ int finish_images(rtr_renderer* r, PendingFrame& pf, int pass_set, bool f32acc, 
     RTR_CUDA(r, launch_resolve_pyramid(s, fb, W, H, r->dims, filtered, true, r->force_generic != 0, f32acc));
     r->launches += ((W % 16) == 0 && !r->force_generic) ? 1 : (filtered ? 6 : 1);
     if (f32acc) {
-        // exact re-run of the colour sums if a pixel left the float sums' exact range (resolve raised minmax[2]); three gated
-        // launches that return at once otherwise (no cooperative grid here: it would wait for the point stream's kernel)
-        RTR_CUDA(r, launch_clear_accum_gated(s, r->sm_count, fb.accum, P, fb.minmax + 2, r->overflow_note_dev));
-        RTR_CUDA(r, launch_blend_list(s, r->sm_count, 0, r->points, r->n_points, pf.plan.pp, ps.cull_state, ps.vis_list, fb.zbuf, fb.accum,
-                                      fb.minmax + 2, kTileBlend));
-        RTR_CUDA(r, launch_resolve_gated(s, fb, W, H));
-        r->launches += 3;
+        // Exact re-run of the colour sums if a pixel left the float sums' exact range (resolve raised minmax[2]): ONE launch
+        // that returns at once otherwise.  Its two barriers need every CTA resident at the same time, and the SMs belong to the
+        // point stream's persistent pass, so a cooperative grid would wait for a drain window (measured: -4 % frames/s on C3);
+        // the grid is therefore ONE thread-block cluster of 8 CTAs, which the hardware co-schedules wherever 8 SMs have a free
+        // slot.  fixup_launches = 3 (option): the same work as three gated launches without a barrier; 2: small cooperative grid
+        // (A/B in profiles/r02l_exp_fixup_gate.json).
+        if (r->fixup_launches == 3) {
+            RTR_CUDA(r, launch_clear_accum_gated(s, r->sm_count, fb.accum, P, fb.minmax + 2, r->overflow_note_dev));
+            RTR_CUDA(r, launch_blend_list(s, r->sm_count, 0, r->points, r->n_points, pf.plan.pp, ps.cull_state, ps.vis_list, fb.zbuf, fb.accum,
+                                          fb.minmax + 2, kTileBlend));
+            RTR_CUDA(r, launch_resolve_gated(s, fb, W, H));
+            r->launches += 3;
+        } else {
+            RTR_CUDA(r, launch_exact_fixup(s, r->sm_count, r->points, r->n_points, pf.plan.pp, ps.cull_state, ps.vis_list, fb.zbuf, fb.accum, P,
+                                           fb.image, cov, fb.minmax, r->overflow_note_dev, kTileBlend,
+                                           r->fixup_launches == 2 ? unsigned(r->sm_count) / 2u : kFixupClusterCtas));
+            r->launches += 1;
+        }
         (void)cov;
     }
     if (ev) cudaEventRecord(ev[4], s);
@@ -1224,6 +1242,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "pipeline")) return &r->pipeline;
     if (!std::strcmp(key, "fuse")) return &r->fuse;
     if (!std::strcmp(key, "fused_tiles_per_cta")) return &r->fused_tiles_per_cta;
+    if (!std::strcmp(key, "fixup_launches")) return &r->fixup_launches;
     if (!std::strcmp(key, "peer_timeout_ms")) return &r->peer.timeout_ms;
     return nullptr;
 }
@@ -1259,6 +1278,7 @@ int rtr_set_option(rtr_renderer* r, const char* key, int64_t value) {
     if (!std::strcmp(key, "blend_variant") && (value < 0 || (value & ~bmask)))
         return fail(r, RTR_ERR_ARG, "blend_variant must be 0, 2, 4 or 6 (measurement bit 32 only in RTR_EXPERIMENTS builds)");
     if (!std::strcmp(key, "timing") && (value < 0 || value > 3)) return fail(r, RTR_ERR_ARG, "timing must be 0 ... 3");
+    if (!std::strcmp(key, "fuse") && (value < 0 || value > 2)) return fail(r, RTR_ERR_ARG, "fuse must be 0 (never), 1 (large clouds) or 2 (always)");
     *slot = int(value);
     return RTR_OK;
 }
@@ -1268,6 +1288,11 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "index_base")) return int64_t(r->index_base);
     if (!std::strcmp(key, "sm_count")) return r->sm_count;
     if (!std::strcmp(key, "int_sum_frames")) return r->int_sum_frames;  // frames left that start with integer colour sums
+    if (!std::strcmp(key, "fuse_active")) {  // would the next frame of a sequence take the fused path (camera set, options as they are)?
+        FramePlan pl;
+        rtr_renderer* m = const_cast<rtr_renderer*>(r);
+        return (m->points && plan_frame(m, pl) == RTR_OK && fused_sequence(r, pl)) ? 1 : 0;
+    }
     if (!std::strcmp(key, "pending")) return r->pending.active ? 1 : 0;  // a fused sequence's last frame still lacks its blend
     if (!std::strcmp(key, "experiments")) {
 #ifdef RTR_EXPERIMENTS

@@ -108,6 +108,10 @@ def test_full_size_frames_equal_the_live_reference(gpu, name):
     calib = gpu.CameraCalibration()
     calib.loadCalibration(f, f, cx, cy, [0.0] * 5, W, H)
     K = calib.getIntrinsicsMatrix()
+    pc.set_camera(calib)
+    # frame sequences of the 100 M-point cloud are fused (one chunk stream per frame) by default; the 20 M-point cloud's
+    # take two passes per frame unless told otherwise: both are compared with the reference below
+    assert pc.get_option("fuse_active") == (1 if name == "c3" else 0)
     traj = gpu.trajectory_w2c(n_poses, center=(hall[0] * 0.125, hall[1] * 0.125, 1.5), radius=2.0)
     dense, dense_vis = _densest_pose(gpu, pc, calib, traj)
     idx = [0, n_poses // 3, (2 * n_poses) // 3 + 1, dense]
@@ -117,18 +121,26 @@ def test_full_size_frames_equal_the_live_reference(gpu, name):
     acc = mine[-1]["raw_accum"].reshape(-1, 4)[:, 3]
     covered = int((mine[-1]["raw_zbuf"] != 0x7F7FFFFF).sum())
     assert covered > 0.5 * P, "the densest view should cover most of the image"
-    # the same poses through the asynchronous trajectory call (several frames in flight), twice around
-    seq = np.stack(poses + poses)
+    # the same poses through the asynchronous trajectory call (several frames in flight), twice around, and a run of 12
+    # consecutive trajectory poses (what a fused sequence is made for: the frames share nearly all their chunks)
+    run = [traj[(dense + i) % n_poses] for i in range(12)]
+    seq = np.stack(poses + poses + run)
     color = np.zeros((len(seq), P * 3), np.uint8)
     depth = np.zeros((len(seq), P), np.float32)
     pc.render_trajectory(gpu.STAGE_FILTERED, seq, color, depth)
+    if name == "c2":   # ... and the smaller cloud through the fused path as well
+        pc.set_option("fuse", 2)
+        color2 = np.zeros((len(seq), P * 3), np.uint8)
+        depth2 = np.zeros((len(seq), P), np.float32)
+        pc.render_trajectory(gpu.STAGE_FILTERED, seq, color2, depth2)
+        assert np.array_equal(color2, color) and np.array_equal(depth2.view(np.uint32), depth.view(np.uint32)), "fused sequence differs from two-pass sequence"
     rec = pc.download_cloud()          # resident (Morton) order; no output depends on point order
     pc.close()
-    ref = _reference_frames(rec, W, H, K, poses)
+    ref = _reference_frames(rec, W, H, K, poses + run)
     del rec
-    _assert_equal(mine, ref, f"{name} ({n} points, {W}x{H})")
+    _assert_equal(mine, ref[:len(poses)], f"{name} ({n} points, {W}x{H})")
     for i in range(len(seq)):
-        r = ref[i % len(poses)]
+        r = ref[i % len(poses)] if i < 2 * len(poses) else ref[len(poses) + i - 2 * len(poses)]
         assert np.array_equal(color[i], r["flt_color_host"]) and np.array_equal(depth[i].view(np.uint32), r["flt_depth_host"]), \
             f"{name}: trajectory frame {i} differs from the reference"
     if name == "c3":

@@ -37,8 +37,10 @@ def test_fused_trajectory_equals_frame_by_frame_64_poses(gpu, cpu_oracle):
     P = case.W * case.H
     poses = _trajectory(gpu, 1000)[100:164]           # 64 consecutive poses of the 1000-pose loop
     want = _blocking(gpu, rec, calib, poses)
-    for opts in ({}, {"fuse": 0}, {"ring_dynamic": 0}, {"ring_ctas": 1}, {"ring_claim_min": 0, "ring_dynamic": 3}):
+    for opts in ({}, {"fuse": 0}, {"ring_dynamic": 0}, {"ring_ctas": 1}, {"ring_claim_min": 0, "ring_dynamic": 3}, {"fused_tiles_per_cta": 3}):
         pc = gpu.ProjectCloud.from_packed(rec)
+        assert pc.get_option("fuse") == 1                       # default: fused sequences for large clouds only ...
+        pc.set_option("fuse", 2)                                # ... this 2 M-point cloud takes them when told to
         for k, v in opts.items():
             pc.set_option(k, v)
         pc.set_camera(calib)
@@ -54,7 +56,7 @@ def test_fused_trajectory_equals_frame_by_frame_64_poses(gpu, cpu_oracle):
             assert np.array_equal(color[i], want[i][0]) and np.array_equal(depth[i].view(np.uint32), want[i][1]), f"{opts}: frame {i}"
         assert np.array_equal(tensor, want[-1][2]), f"{opts}: tensor of the last frame"
         assert frames == len(poses) and 0 < visible <= frames * n_chunks
-        if opts.get("fuse", 1):
+        if opts.get("fuse", 2):
             # one pass per frame plus the last frame's blend; consecutive poses share nearly all their chunks
             assert passes == len(poses) + 1
             assert visible <= streamed < 1.35 * visible, (visible, streamed)
@@ -79,7 +81,8 @@ def test_fused_sequence_with_api_calls_in_between(gpu, cpu_oracle):
         steps.append((case, E, filtered, dist, rng.integers(0, 4)))
     pc = gpu.ProjectCloud.from_packed(rec, apply_distortion=True)
     ref = gpu.ProjectCloud.from_packed(rec, apply_distortion=True)
-    assert pc.get_option("fuse") == 1 and pc.get_option("pipeline") == 1
+    pc.set_option("fuse", 2)
+    assert pc.get_option("pipeline") == 1
     saw_pending = False
     for i, (case, E, filtered, dist, action) in enumerate(steps):
         P = case.W * case.H
@@ -125,6 +128,7 @@ def test_fused_sequence_of_disjoint_views(gpu, cpu_oracle):
     poses = np.stack(poses)
     want = _blocking(gpu, rec, calib, poses)
     pc = gpu.ProjectCloud.from_packed(rec)
+    pc.set_option("fuse", 2)
     pc.set_camera(calib)
     color = np.zeros((len(poses), P * 3), np.uint8)
     depth = np.zeros((len(poses), P), np.float32)
@@ -138,9 +142,11 @@ def test_fused_sequence_of_disjoint_views(gpu, cpu_oracle):
     assert streamed > 1.6 * visible          # hardly anything is shared between these views
 
 
-def test_fused_sequence_float_sum_overflow(gpu, cpu_oracle):
-    """A pixel with > 65 793 accepted points inside a fused sequence: the gated exact re-run (three launches on the image
-    stream) redoes that frame's colour sums from the two-camera list; later frames start with integer sums."""
+@pytest.mark.parametrize("fixup_launches", [1, 2, 3])
+def test_fused_sequence_float_sum_overflow(gpu, cpu_oracle, fixup_launches):
+    """A pixel with > 65 793 accepted points inside a fused sequence: the gated exact re-run on the image stream (one
+    thread-block cluster, a small cooperative grid, or three gated launches) redoes that frame's colour sums from the
+    two-camera list; later frames start with integer sums."""
     W, H, heavy = 64, 48, 70_000
     m = np.array([32, 0, 31.5, 0, 0, 32, 23.5, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)
     rng = np.random.default_rng(9)
@@ -150,6 +156,8 @@ def test_fused_sequence_float_sum_overflow(gpu, cpu_oracle):
     xyz[:heavy] = np.array([0.013, 0.009, 1.0], np.float32)
     bgr = rng.integers(0, 256, (n, 3), dtype=np.uint8)
     pc = gpu.ProjectCloud.from_packed(gpu.pack_records(xyz, bgr))
+    pc.set_option("fuse", 2)
+    pc.set_option("fixup_launches", fixup_launches)
     c = gpu.CameraCalibration()
     c.setWidth(W)
     c.setHeight(H)
@@ -177,7 +185,9 @@ def test_fused_sequence_replaced_cloud_and_reuse(gpu, cpu_oracle):
     calib = calib_of(gpu, case)
     P = case.W * case.H
     pc = gpu.ProjectCloud.from_packed(rec)
+    pc.set_option("fuse", 2)
     pc.set_camera(calib, case.poses[0])
+    assert pc.get_option("fuse_active") == 1
     pc.render_device(gpu.STAGE_FILTERED)
     assert pc.get_option("pending") == 1
     other = cpu_oracle.synth_packed(99, 30_000, 0, 30_000, case.hall, case.n_boxes)

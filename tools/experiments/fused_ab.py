@@ -57,7 +57,7 @@ def child(args):
     out = {"ms_per_frame": best, "frames_per_s": 1e3 / best}
     print("RESULT " + json.dumps(out), flush=True)     # (the per-stage part below can fail in measurement-only builds)
     # per-stage events of the same loop
-    timing = 3 if pc.get_option("fuse") and pc.get_option("pipeline") else 2
+    timing = 3 if pc.get_option("fuse_active") == 1 else 2
     pc.set_option("timing", timing)
     pc.stage_ms_sum(reset=True)
     pc.stream_stats(reset=True)
