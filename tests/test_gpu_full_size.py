@@ -108,11 +108,11 @@ def test_full_size_frames_equal_the_live_reference(gpu, name):
     calib = gpu.CameraCalibration()
     calib.loadCalibration(f, f, cx, cy, [0.0] * 5, W, H)
     K = calib.getIntrinsicsMatrix()
-    pc.set_camera(calib)
+    traj = gpu.trajectory_w2c(n_poses, center=(hall[0] * 0.125, hall[1] * 0.125, 1.5), radius=2.0)
+    pc.set_camera(calib, traj[0])
     # frame sequences of the 100 M-point cloud are fused (one chunk stream per frame) by default; the 20 M-point cloud's
     # take two passes per frame unless told otherwise: both are compared with the reference below
     assert pc.get_option("fuse_active") == (1 if name == "c3" else 0)
-    traj = gpu.trajectory_w2c(n_poses, center=(hall[0] * 0.125, hall[1] * 0.125, 1.5), radius=2.0)
     dense, dense_vis = _densest_pose(gpu, pc, calib, traj)
     idx = [0, n_poses // 3, (2 * n_poses) // 3 + 1, dense]
     poses = [traj[i] for i in idx]
