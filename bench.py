@@ -334,9 +334,12 @@ def points_mode_record(args, pkg, torch, dist, wl, rank, world, local, n_per_gpu
     out = {"points_per_gpu": n_per_gpu, "points_total": n_per_gpu * world, "resolution": f"{W}x{H}", "steps": steps, "variants": {}}
 
     def digest_of(pc, E):
+        """sha256 of the frame plus one sha256 per buffer (colour, depth, tensor): 128 bytes."""
         color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
         assert pc.computeFilteredRGBD(calib, E, color, depth) == 1
-        return hashlib.sha256(color.tobytes() + depth.tobytes() + pc.read("tensor", np.uint16, P * 5).tobytes()).digest()
+        tensor = pc.read("tensor", np.uint16, P * 5)
+        parts = [color.tobytes(), depth.tobytes(), tensor.tobytes()]
+        return hashlib.sha256(b"".join(parts)).digest() + b"".join(hashlib.sha256(p).digest() for p in parts)
 
     # ---- parity on a down-sampled cloud (2 M points per rank), all variants
     n_small = 2_000_000
@@ -354,6 +357,7 @@ def points_mode_record(args, pkg, torch, dist, wl, rank, world, local, n_per_gpu
         small.set_option("key64", key64)
         attach_merge(pkg, torch, dist, small, merge, rank, world)
         equal = True
+        differing = torch.zeros(3, dtype=torch.int32, device="cuda")   # poses on which colour / depth / tensor differ, summed over the ranks
         for E in check_poses:
             mine = digest_of(small, E)
             t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
@@ -361,11 +365,16 @@ def points_mode_record(args, pkg, torch, dist, wl, rank, world, local, n_per_gpu
                 union.set_option("key64", key64)
                 t = torch.frombuffer(bytearray(digest_of(union, E)), dtype=torch.uint8).cuda()
             dist.broadcast(t, 0)
-            equal &= bytes(t.cpu().numpy().tobytes()) == mine
+            want = bytes(t.cpu().numpy().tobytes())
+            equal &= want[:32] == mine[:32]
+            for b in range(3):
+                differing[b] += int(want[32 * (b + 1):32 * (b + 2)] != mine[32 * (b + 1):32 * (b + 2)])
         flag = torch.tensor([1 if equal else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(differing, op=dist.ReduceOp.SUM)
         detach_merge(small, dist, merge)
         out["variants"][f"{merge}{'_key64' if key64 else ''}"] = {"digest_equal": bool(int(flag.item()) == 1),
+                                                                "differing_rank_poses": dict(zip(["colour", "depth", "tensor"], differing.tolist())),
                                                                 "digest_check": f"{world} x {n_small} points, {len(check_poses)} poses: every rank's merged frame (colour, depth, tensor) "
                                                                                 "== the frame one GPU renders from the union of the shards"}
     small.close()

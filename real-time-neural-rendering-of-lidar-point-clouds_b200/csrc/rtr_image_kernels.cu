@@ -21,6 +21,10 @@
 
 #include "rtr_kernels.h"
 
+#ifndef RTR_L2_HINTS
+#define RTR_L2_HINTS 0
+#endif
+
 namespace rtr {
 
 __device__ __forceinline__ float sel_min(float a, float b) { return a < b ? a : b; }  // project_cloud.cu:46-49
@@ -90,7 +94,11 @@ __global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __
         const uint2 z0 = *reinterpret_cast<const uint2*>(zbuf + p0);
         const uint2 z1 = *reinterpret_cast<const uint2*>(zbuf + p1);
         if constexpr (RESOLVE) {
+#if RTR_L2_HINTS & 2
+            const uint4 a00 = __ldcs(accum + p0), a01 = __ldcs(accum + p0 + 1), a10 = __ldcs(accum + p1), a11 = __ldcs(accum + p1 + 1);  // last use of the sums
+#else
             const uint4 a00 = accum[p0], a01 = accum[p0 + 1], a10 = accum[p1], a11 = accum[p1 + 1];
+#endif
             uint8_t c[12];
             if constexpr (F32ACC) {
                 resolve_px_f32(a00, minmax + 2, c[0], c[1], c[2]);
@@ -495,7 +503,11 @@ __device__ __forceinline__ void up_final_group(const Lo& lo, int lw, int lh, flo
         v.y = uint32_t(tp[k][2]) | (uint32_t(tp[k][3]) << 16);
         v.z = uint32_t(tp[k][4]) | (uint32_t(tp[k][5]) << 16);
         v.w = uint32_t(tp[k][6]) | (uint32_t(tp[k][7]) << 16);
+#if RTR_L2_HINTS & 1
+        __stcs(reinterpret_cast<uint4*>(tensor + plane * k + idx), v);  // nobody on this stream reads the tensor again: evict first
+#else
         *reinterpret_cast<uint4*>(tensor + plane * k + idx) = v;
+#endif
     }
 }
 

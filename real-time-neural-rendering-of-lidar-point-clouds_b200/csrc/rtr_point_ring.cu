@@ -538,6 +538,9 @@ __global__ void __launch_bounds__(kRingThreads, kRingMinCtas) blend_ring_kernel(
 #ifndef RTR_FUSED_SEQ
 #define RTR_FUSED_SEQ 0
 #endif
+#ifndef RTR_L2_HINTS
+#define RTR_L2_HINTS 0
+#endif
 #if RTR_FUSED_REGS >= 64
 #define RTR_FUSED_BOUNDS __launch_bounds__(kRingThreads, kRingMinCtas)
 #else
@@ -595,10 +598,18 @@ __global__ void RTR_FUSED_BOUNDS fused_ring_kernel(const PointRecord* __restrict
     // them while the others still stream: no clear kernel, no launch on anybody's critical path.
     if (clr.accum) {
         const uint64_t t = uint64_t(blockIdx.x) * kRingThreads + threadIdx.x, stride = uint64_t(gridDim.x) * kRingThreads;
+#if RTR_L2_HINTS & 4
+        for (uint64_t i = t; i < clr.n_px; i += stride) __stcs(clr.accum + i, make_uint4(0u, 0u, 0u, 0u));
+#else
         for (uint64_t i = t; i < clr.n_px; i += stride) clr.accum[i] = make_uint4(0u, 0u, 0u, 0u);
+#endif
         const uint64_t cov4 = clr.cov >> 2;
         uint4* z4 = reinterpret_cast<uint4*>(clr.zbuf);
+#if RTR_L2_HINTS & 8
+        for (uint64_t i = t; i < cov4; i += stride) __stcs(z4 + i, make_uint4(kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits));
+#else
         for (uint64_t i = t; i < cov4; i += stride) z4[i] = make_uint4(kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits, kEmptyDepthBits);
+#endif
         for (uint64_t i = (cov4 << 2) + t; i < clr.cov; i += stride) clr.zbuf[i] = kEmptyDepthBits;
         if (t == 0) { clr.minmax[0] = 0xFFFFFFFFu; clr.minmax[1] = 0u; clr.minmax[2] = 0u; clr.minmax[3] = 0u; }
     }
