@@ -97,9 +97,9 @@ int rtr_render_tensor(rtr_renderer* r, void** device_fp16);
  * rtr_get_device_buffers, rtr_read_buffer, rtr_set_option and every blocking render call, all of which complete the
  * outstanding frame first.  Frames are byte-identical to the blocking calls'.  rtr_get_device_buffers /
  * rtr_read_buffer refer to the frame enqueued last; rtr_get_device_buffers makes `stream` wait for every frame in
- * flight.  "fuse": 1 (default) = fused sequences for clouds of >= 40 000 chunks (41 M points; below that a frame is a
- * few short kernels and two passes per frame, alternating between two frame sets and two streams, are faster), 0 = never,
- * 2 = always. */
+ * flight.  "fuse": 1 (default) = fused sequences for clouds of >= 40 000 chunks (41 M points) and for distorted cameras
+ * (below that a frame is a few short kernels and two passes per frame, alternating between two frame sets and two
+ * streams, are faster), 0 = never, 2 = always. */
 int rtr_render_device(rtr_renderer* r, int stage);
 int rtr_sync(rtr_renderer* r);
 /* Render n_frames poses (n_frames x 16 doubles, world->camera) back to back.  bgr/depth, when not
@@ -121,7 +121,11 @@ typedef struct {
     int level_w[5], level_h[5];   /* true pyramid dims */
     int up_w[5], up_h[5];         /* dims the up-pass uses (reference truncation) */
     uint64_t tensor_plane;        /* up_w[0]*up_h[0] */
-    void* stream;                 /* cudaStream_t the renderer launches on */
+    void* stream;                 /* cudaStream_t the renderer launches on.  Work enqueued here after rtr_get_device_buffers
+                                     sees the frame.  (The library's kernels trigger programmatic dependents early: a kernel
+                                     launched on this stream WITH the programmatic-stream-serialization attribute must
+                                     execute griddepcontrol.wait / cudaGridDependencySynchronize before reading a buffer;
+                                     plainly launched kernels — torch, cuDNN, TensorRT — are ordered as usual.) */
 } rtr_device_buffers;
 int rtr_get_device_buffers(rtr_renderer* r, rtr_device_buffers* out);
 

@@ -52,8 +52,9 @@ struct rtr_renderer {
     int device = 0;
     int sm_count = 148;
     // `stream`: everything; `stream2`: every other frame of an asynchronous frame sequence (option "pipeline")
-    // fused sequences: point passes on `stream`, image passes on `stream2`
-    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
+    // `stream`: everything; `stream2`: every other frame of a two-pass sequence (option "pipeline"); `image_stream`: the image
+    // passes of fused sequences (higher priority); `copy_stream`: D2H
+    cudaStream_t stream = nullptr, stream2 = nullptr, image_stream = nullptr, copy_stream = nullptr;
     // cloud
     rtr::PointRecord* points = nullptr;
     uint64_t n_points = 0;

@@ -285,6 +285,9 @@ struct PeerMergeParams {
 };
 // op 0: min of u32, op 1: sum of u32, op 2: min of u64.  Grid = 2 CTAs per SM (cooperative launch, see kernel).
 cudaError_t launch_peer_allreduce(cudaStream_t s, int sm_count, int op, const PeerMergeParams& pm);
+// Plainly launched empty kernel: what is enqueued behind it cannot start before what is in front of it has completed,
+// whatever launch attributes a library (NCCL) gives its kernels (see rtr_peer.cu).
+cudaError_t launch_stream_fence(cudaStream_t s);
 
 // ---- synthetic cloud on the device (rtr_synth.cu; bench/test support, same generator as the oracle)
 cudaError_t launch_synth(cudaStream_t s, uint64_t seed, uint64_t n_total, uint64_t first, uint64_t count, int lx,

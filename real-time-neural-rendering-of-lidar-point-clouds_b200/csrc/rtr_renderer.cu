@@ -106,10 +106,11 @@ void free_cull_storage(rtr_renderer* r) {
         s.vis_list = nullptr; s.cull_state = nullptr; s.cull_parity = 0;
     }
 }
-// The compute streams idle (stream2 only ever holds work of a pipelined frame sequence).
+// The compute streams idle (stream2 / image_stream only ever hold work of a pipelined frame sequence).
 cudaError_t sync_compute(rtr_renderer* r) {
     cudaError_t e = cudaStreamSynchronize(r->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream2);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->image_stream);
     return e;
 }
 }  // namespace rtr
@@ -234,6 +235,9 @@ int make_params(rtr_renderer* r, ProjParams& pp) {
 }
 
 int comm_allreduce(rtr_renderer* r, const void* src, void* dst, size_t count, int dtype, int op) {
+    // our kernels trigger their programmatic dependents early; NCCL's kernels are launched as such dependents but never wait
+    RTR_CUDA(r, launch_stream_fence(r->stream));
+    r->launches += 1;
     const int rc = g_nccl.AllReduce(src, dst, count, dtype, op, r->comm, r->stream);
     if (rc != 0) return fail(r, RTR_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     return RTR_OK;
@@ -504,10 +508,12 @@ int enqueue_copy(rtr_renderer* r, int si, uint8_t* bgr, float* depth);
 // sequence trades one of the two chunk streams per frame for fewer, longer kernel boundaries in which the image passes
 // can run, which wins once a point pass is long (C3, 100 M points: 9 100 vs 8 020 frames/s) and loses on small clouds
 // whose frames are a few short kernels (C1, 1 M points: 46 200 vs 52 800; C2, 20 M points: 21 900 vs 23 400;
-// profiles/r02m_exp_fixup_gate.json).  The switch is the cloud's chunk count — known on the host without a read-back.
+// profiles/r02m_exp_fixup_gate.json).  The switch is the cloud's chunk count — known on the host without a read-back —
+// or a distorted camera, whose heavier projection makes the passes long already at C2's size (20 M points, 1280x720:
+// 17 800 vs 12 400 frames/s, profiles/r02k_bench_c2_distort.json).
 constexpr uint32_t kFuseAutoMinChunks = 40000;  // 41 M points
 bool fused_sequence(const rtr_renderer* r, const FramePlan& pl) {
-    const bool want = r->fuse == 2 || (r->fuse == 1 && r->n_chunks >= kFuseAutoMinChunks);
+    const bool want = r->fuse == 2 || (r->fuse == 1 && (r->n_chunks >= kFuseAutoMinChunks || pl.pp.distort != 0));
     return want && pipelined(r) && pl.cull && pl.use_ring && !r->key64 && r->ring >= 1;
 }
 
@@ -527,7 +533,7 @@ int finish_images(rtr_renderer* r, PendingFrame& pf, int pass_set, bool f32acc, 
     const int W = r->alloc_W, H = r->alloc_H;
     const uint64_t P = uint64_t(W) * H, cov = clear_coverage(W, H);
     const bool filtered = pf.stage == RTR_STAGE_FILTERED;
-    cudaStream_t s = r->stream2;
+    cudaStream_t s = r->image_stream;
 #ifdef RTR_EXPERIMENTS
     if (exp_flag("RTR_EXP_NO_IMAGES")) { pf.active = false; return RTR_OK; }
 #endif
@@ -774,15 +780,17 @@ int rtr_create(int device, rtr_renderer** out) {
     rtr_renderer* r = new rtr_renderer;
     r->device = device;
     r->sm_count = prop.multiProcessorCount;
-    // Fused sequences keep two compute streams busy (point passes / image passes).  The image stream gets the higher
-    // priority: its short CTAs fill an SM the moment a CTA of the persistent point pass leaves it, instead of queueing
-    // behind the next pass (+4 % frames/s, profiles/r02e_exp_fused_ab.json; RTR_STREAM_PRIORITY=0: equal priorities).
+    // Fused sequences keep two compute streams busy: point passes on `stream`, image passes on `image_stream`, which gets
+    // the higher priority: its short CTAs fill an SM the moment a CTA of the persistent point pass leaves it, instead of
+    // queueing behind the next pass (+4 % frames/s, profiles/r02e_exp_fused_ab.json; RTR_STREAM_PRIORITY=0: equal).
+    // Two-pass sequences alternate whole frames between `stream` and `stream2`, which must stay equal in priority.
     int prio_lo = 0, prio_hi = 0;
     const char* pe = std::getenv("RTR_STREAM_PRIORITY");
     if (!(pe && pe[0] == '0')) (void)cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
-        (e = cudaStreamCreateWithPriority(&r->stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&r->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&r->image_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete r;
         return cuda_fail(nullptr, e, "stream creation");
@@ -834,6 +842,7 @@ void rtr_destroy(rtr_renderer* r) {
     cudaStreamDestroy(r->stream);
     cudaStreamDestroy(r->stream2);
     cudaStreamDestroy(r->copy_stream);
+    cudaStreamDestroy(r->image_stream);
     delete r;
 }
 

@@ -168,3 +168,27 @@ def test_ring_tile_claims_cover_every_tile_once(pkg):
             assert steps <= n_tiles + 1
         assert all(v == 1 for v in seen), (grid, nq, n_tiles, [j for j, v in enumerate(seen) if v != 1][:5])
         assert all(s["done"] for s in state)
+
+
+def test_bench_pose_schedule_covers_the_loop_in_contiguous_arcs():
+    """bench.py deals the trajectory in arcs of consecutive frames (what fused sequences rely on), spreads the arcs of all
+    ranks evenly over the loop, and tiles the whole loop when the run is as long as the trajectory."""
+    import bench
+    n_poses = 1000
+    # a 25-frame run on one GPU: four arcs of consecutive poses, a quarter of the loop apart
+    s = bench.pose_schedule(25, n_poses, 1, 0)
+    assert len(s) == 25
+    jumps = [i for i in range(1, 25) if s[i] != (s[i - 1] + 1) % n_poses]
+    assert len(jumps) == 3 and [s[j] for j in jumps] == [250, 500, 750]
+    # the full loop: every pose exactly once
+    assert sorted(bench.pose_schedule(1000, n_poses, 1, 0)) == list(range(1000))
+    # 8 ranks: arcs of different ranks never overlap, and together they sample every eighth of the loop
+    seen = set()
+    for r in range(8):
+        sr = bench.pose_schedule(25, n_poses, 8, r)
+        assert not (seen & set(sr))
+        seen |= set(sr)
+    assert {p * 8 // n_poses for p in seen} == set(range(8))
+    # the full trajectory dealt to 8 ranks in contiguous runs: a partition of the loop
+    every = sorted(p for r in range(8) for p in bench.pose_schedule(125, n_poses, 8, r))
+    assert len(set(every)) >= 970   # (arcs are whole frames: neighbouring arcs can overlap by a pose at the seams)

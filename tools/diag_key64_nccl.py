@@ -31,18 +31,20 @@ def main():
     union = pkg.ProjectCloud.from_packed(torch.cat(gathered).cpu().numpy(), device=local, sort=False) if rank == 0 else None
     small.set_option("index_base", n_small * rank)
     small.set_camera(calib)
-    small.set_option("key64", 1)
-    for merge in sys.argv[1:] or ["nccl"]:
+    reps = int(os.environ.get("DIAG_REPS", "1"))
+    for spec in sys.argv[1:] or ["nccl:1"]:
+        merge, key64 = spec.split(":")
+        small.set_option("key64", int(key64))
         bench.attach_merge(pkg, torch, dist, small, merge, rank, world)
-        for pi in (0, n_poses // 3, (2 * n_poses) // 3):
+        for pi in [0, n_poses // 3, (2 * n_poses) // 3] * reps:
             E = poses[pi]
             color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
-            assert small.computeRGBD(calib, E, color, depth) == 1
+            assert small.computeFilteredRGBD(calib, E, color, depth) == 1
             t = torch.cat([torch.from_numpy(depth.view(np.int32).copy()).cuda(), torch.from_numpy(color.astype(np.int32)).cuda()])
             if rank == 0:
-                union.set_option("key64", 1)
+                union.set_option("key64", int(key64))
                 c0, d0 = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
-                assert union.computeRGBD(calib, E, c0, d0) == 1
+                assert union.computeFilteredRGBD(calib, E, c0, d0) == 1
                 t0 = torch.cat([torch.from_numpy(d0.view(np.int32).copy()).cuda(), torch.from_numpy(c0.astype(np.int32)).cuda()])
             else:
                 t0 = torch.empty_like(t)
@@ -53,7 +55,10 @@ def main():
             if int(dc.sum()):
                 i = int(torch.nonzero(dc)[0])
                 msg += f"; first colour diff px {i} (row {i // W}, col {i % W}): mine {t[P + 3 * i:P + 3 * i + 3].tolist()} union {t0[P + 3 * i:P + 3 * i + 3].tolist()} depth bits {int(t[i])} / {int(t0[i])}"
-            print(msg, flush=True)
+            if int(dd.sum()) or int(dc.sum()):
+                print(msg, flush=True)
+        if rank == 0:
+            print(f"[{spec}] done", flush=True)
         bench.detach_merge(small, dist, merge)
     small.close()
     if union is not None:
