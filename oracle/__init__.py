@@ -265,6 +265,8 @@ class RefHost:
         self.lib.ref_oct_write.argtypes = [C.c_char_p, _vp, _vp, _vp, C.c_size_t, _i, _i, _i]
         self.lib.ref_oct_read.argtypes = [C.c_char_p, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp]
         self.lib.ref_load_calibration.argtypes = [C.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp]
+        if hasattr(self.lib, "ref_load_ply"):
+            self.lib.ref_load_ply.argtypes = [C.c_char_p, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
 
     def oct_write(self, path, xyz, bgr, keys, dims):
         xyz = np.ascontiguousarray(xyz, np.float32)
@@ -279,6 +281,13 @@ class RefHost:
         dims = np.zeros(3, np.int32)
         assert self.lib.ref_oct_read(os.fsencode(path), _p(xyz4), _p(bgra), cap, C.byref(n), _p(dims)) == 1
         return xyz4[:n.value], bgra[:n.value], tuple(int(d) for d in dims)
+
+    def load_ply(self, path, cap):
+        """CloudReader::loadCloud(path) for a .ply (cloudreader.cpp:122-177, 8-82): (xyz, bgr, block key per point, blocks)."""
+        xyz, bgr, keys = np.zeros((cap, 3), np.float32), np.zeros((cap, 3), np.uint8), np.zeros(cap, np.int32)
+        n, nb = C.c_size_t(0), C.c_size_t(0)
+        assert self.lib.ref_load_ply(os.fsencode(path), _p(xyz), _p(bgr), _p(keys), cap, C.byref(n), C.byref(nb)) == 1
+        return xyz[:n.value], bgr[:n.value], keys[:n.value], int(nb.value)
 
     def load_calibration(self, path):
         W, H, nd, fe = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)

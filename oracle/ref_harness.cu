@@ -31,6 +31,9 @@
 // The reference keeps its device buffers private; the oracle needs to read them.
 #define private public
 #include "project_cloud.h"
+#include "PointCloudReader.h"
+#include "Utils.h"
+#include "cloudreader.h"
 #undef private
 #include "render.cuh"
 
@@ -63,6 +66,17 @@ void cv::Mat::convertTo(cv::Mat& dst, int rtype, double alpha) const {
         d[i] = uint8_t(r < 0 ? 0 : r > 255 ? 255 : r);
     }
 }
+
+// cloudreader.cpp (compiled unmodified for its PLY path: loadPLY + computeGrid) also holds the E57 path, whose reader
+// class lives in libE57Format (not in this image).  The members it links against are defined here and abort: nothing
+// in the tests takes that path.
+static void no_e57() { std::fprintf(stderr, "oracle/_ref: the E57 path is not available (libE57Format is not installed)\n"); std::abort(); }
+PointCloudReader::PointCloudReader(const std::string&) : _reader(nullptr) { no_e57(); }
+int PointCloudReader::getNumberOfClouds() { no_e57(); return 0; }
+int PointCloudReader::getNumberOfImages() { no_e57(); return 0; }
+cv::Mat PointCloudReader::getImage(int, cv::Matx44d&, cv::Matx33d&) { no_e57(); return cv::Mat(); }
+void PointCloudReader::getScanCloud(int, cv::Matx44d&, std::vector<cv::Point3d>&, std::vector<cv::Vec3b>&, int) { no_e57(); }
+std::vector<cv::Point3d> Utils::transformCloud(const std::vector<cv::Point3d>& cloud, cv::Matx44d) { no_e57(); return cloud; }
 
 extern "C" cudaError_t rtr_ref_zero_malloc(void** p, size_t bytes) {
 #undef cudaMalloc
@@ -257,6 +271,28 @@ int ref_oct_read(const char* path, float* xyz4_out, uint8_t* bgra_out, size_t ca
     if (v.size() > cap) return -2;
     std::memcpy(xyz4_out, v.data(), v.size() * sizeof(float4));
     std::memcpy(bgra_out, c.data(), c.size() * sizeof(uchar4));
+    return 1;
+}
+// CloudReader::loadCloud for a .ply, no cache (cloudreader.cpp:122-177 loadPLY -> :8-82 computeGrid): every point with the key
+// of the 0.25 m block the reference put it in, blocks in the map's iteration order, points in arrival order inside a block.
+int ref_load_ply(const char* path, float* xyz_out, uint8_t* bgr_out, int* key_out, size_t cap, size_t* n, size_t* n_blocks) {
+    std::ostringstream sink;
+    std::streambuf* o = std::cout.rdbuf(sink.rdbuf());
+    const std::unordered_map<int, OctreeGrid::Block> grid = CloudReader::loadCloud(std::filesystem::path(path));
+    std::cout.rdbuf(o);
+    size_t k = 0;
+    for (const auto& kv : grid) {
+        const OctreeGrid::Block& b = kv.second;
+        for (size_t i = 0; i < b.positions.size(); ++i, ++k) {
+            if (k >= cap) return -2;
+            xyz_out[3 * k] = b.positions[i].x; xyz_out[3 * k + 1] = b.positions[i].y; xyz_out[3 * k + 2] = b.positions[i].z;
+            const cv::Vec3b c = i < b.colors.size() ? b.colors[i] : cv::Vec3b(0, 0, 0);
+            bgr_out[3 * k] = c[0]; bgr_out[3 * k + 1] = c[1]; bgr_out[3 * k + 2] = c[2];
+            key_out[k] = kv.first;
+        }
+    }
+    *n = k;
+    *n_blocks = grid.size();
     return 1;
 }
 // CameraCalibration::loadCalibration(file) (CameraCalibration.cpp:101-209).

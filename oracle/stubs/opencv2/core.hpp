@@ -30,6 +30,7 @@ typedef Matx<double, 3, 3> Matx33d;
 typedef Matx<float, 3, 3> Matx33f;
 typedef Matx<double, 4, 4> Matx44d;
 struct Point3f { float x, y, z; Point3f() : x(0), y(0), z(0) {} Point3f(float a, float b, float c) : x(a), y(b), z(c) {} };
+struct Point3d { double x, y, z; Point3d() : x(0), y(0), z(0) {} Point3d(double a, double b, double c) : x(a), y(b), z(c) {} };  // cloudreader.cpp's E57 path
 struct Vec3b { uchar val[3]; Vec3b() { val[0] = val[1] = val[2] = 0; } Vec3b(uchar a, uchar b, uchar c) { val[0] = a; val[1] = b; val[2] = c; }
     uchar& operator[](int i) { return val[i]; } const uchar& operator[](int i) const { return val[i]; } };
 struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
@@ -40,6 +41,7 @@ struct Mat {
     Mat() {}
     Mat(Size s, int t) : rows(s.height), cols(s.width), type_(t), own(size_t(s.width) * s.height * elemSize(t)) { data = own.data(); }
     Mat(int r, int c, int t, void* p) : rows(r), cols(c), type_(t), data(static_cast<uint8_t*>(p)) {}
+    Size size() const { return Size(cols, rows); }
     template <typename T> T* ptr() { return reinterpret_cast<T*>(data); }
     template <typename T> const T* ptr() const { return reinterpret_cast<const T*>(data); }
     // Only the CV_16FC3 -> CV_8UC3 scaling used by computeFull (project_cloud.cu:480).

@@ -202,3 +202,28 @@ def test_corrupt_files_return_errors_instead_of_throwing(pkg, tmp_path):
         assert rc == pkg.RTR_ERR_ARG, name
         assert not xyz and not bgr and n.value == 0
     # (the PLY loader needs a renderer, i.e. a GPU: its header bound is checked in tests/test_gpu_io.py)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_cell_binning_is_pinned_to_the_reference_loader(pkg, small_cloud, tmp_path):
+    """f1 against the reference's OWN loader: its cloudreader.cpp compiled unmodified (tinyply is vendored) reads a .ply and
+    bins it into 0.25 m blocks (loadPLY + computeGrid, cloudreader.cpp:122-177, 8-82).  Every point must come back with the
+    B,G,R colour the file implies and in the block our numpy restatement of computeGrid (grid_keys — what rtr_bin_cells /
+    rtr_io_write_oct are tested against on the GPU and above) assigns it, points in arrival order inside a block."""
+    import oracle
+    xyz, bgr = small_cloud
+    ref = oracle.RefHost()
+    if not hasattr(ref.lib, "ref_load_ply"):
+        pytest.skip("oracle/_ref predates ref_load_ply: rebuild it (make -C oracle ref)")
+    path = str(tmp_path / "cloud.ply")
+    pkg.write_ply(path, xyz, bgr)
+    rx, rc, rk, n_blocks = ref.load_ply(path, len(xyz) + 16)
+    assert len(rx) == len(xyz)
+    keys, dims, _, _ = grid_keys(xyz)
+    assert n_blocks == len(np.unique(keys))
+    # per block: the same points in the same (arrival) order
+    order_ref = np.argsort(rk, kind="stable")
+    order_mine = np.argsort(keys, kind="stable")
+    assert np.array_equal(rk[order_ref], keys[order_mine])
+    assert np.array_equal(rx[order_ref].view(np.uint32), xyz[order_mine].view(np.uint32))
+    assert np.array_equal(rc[order_ref], bgr[order_mine])          # red/green/blue of the file -> B,G,R (cloudreader.cpp:168)
