@@ -171,6 +171,8 @@ struct RingSchedule {
                              // then dealt round-robin, a CTA takes a handful of tiles and leaves, and the SM's block scheduler can
                              // slot the image stream's CTAs in between (option fused_tiles_per_cta)
     uint32_t* tiles_hint;    // mapped host word: the fused pass reports how many tiles its list held (sizes the next launch)
+    uint32_t zero;           // always 0, and not known to the compiler: (loaded word & zero) is how ring_walk makes an instruction
+                             // wait for a load without changing its operands
 };
 // Claimed tiles (list passes): a CTA's first `stages` tiles are tiles blockIdx.x + k * grid of the launch; the tiles from
 // stages * grid on are dealt round-robin into n_queues queues, entry c of queue q being this tile.  Every tile index

@@ -57,6 +57,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_at(uint32_t bar_smem_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_smem_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
@@ -220,8 +223,18 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a ^ (uint32_t(s) << 4)));
             p[s].x = __uint_as_float(v.x); p[s].y = __uint_as_float(v.y); p[s].z = __uint_as_float(v.z); p[s].bgra = v.w;
         }
+        // The stage may only be handed back once the records are IN the registers.  Issuing the four LDS is not enough:
+        // the mbarrier arrive overtakes them when the SM's load/store queue is backed up by scattered REDs and gathers
+        // (an unsorted cloud: hundreds of sector operations per warp instruction), the leader sees eight arrivals, re-arms
+        // the stage, and the bulk copy of the NEXT tile lands under loads that have not read the banks yet — a few
+        // records of the next tile processed twice, a few of this one never (found as frames that differ from run to run
+        // in a handful of pixels, tools/diag_repeat.py: 9 % of the frames of an unsorted 16 M-point cloud, 92 % with every
+        // chunk streamed; never with the per-thread kernels).  The arrive's address therefore DEPENDS on the loaded
+        // words — and-ed with a kernel parameter that is always 0, which ptxas cannot fold away — so the instruction waits
+        // on the loads' scoreboard (SASS: LOP3 on the four LDS destinations in front of SYNCS.ARRIVE).
+        const uint32_t landed = (p[0].bgra ^ p[1].bgra ^ p[2].bgra ^ p[3].bgra) & sc.zero;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        if (lane == 0) mbar_arrive_at(smem_addr(&sm.empty[stage]) + landed);
         if (leader) {
             mbar_wait(&sm.empty[stage], parity);  // the group's other warps are a few instructions behind at most
             if (t_refill != kNoTile) issue(stage, refill_chunk);
@@ -626,6 +639,7 @@ RingSchedule make_ring_schedule(uint64_t n_points, const CullState* cull, const 
     sc.ctas_per_sm = kRingCtasPerSm;
     sc.grid_override = 0;
     sc.tiles_hint = nullptr;
+    sc.zero = 0;
     sc.claim_min_tiles_per_cta = 12;
     sc.n_chunks = uint32_t((n_points + kChunkPoints - 1) / kChunkPoints);
     // golden-ratio stride, made coprime with n_chunks: t -> (t * mul) mod n_chunks is a permutation whose every
