@@ -235,7 +235,7 @@ int make_params(rtr_renderer* r, ProjParams& pp) {
 }
 
 int comm_allreduce(rtr_renderer* r, const void* src, void* dst, size_t count, int dtype, int op) {
-    // our kernels trigger their programmatic dependents early; NCCL's kernels are launched as such dependents but never wait
+    // our kernels trigger their programmatic dependents early; NCCL's kernels never execute griddepcontrol.wait (rtr_peer.cu)
     RTR_CUDA(r, launch_stream_fence(r->stream));
     r->launches += 1;
     const int rc = g_nccl.AllReduce(src, dst, count, dtype, op, r->comm, r->stream);
