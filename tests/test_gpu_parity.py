@@ -777,4 +777,15 @@ def test_ring_kernels_hand_a_stage_back_only_after_its_records_landed(gpu):
             pc.set_option(k, v)
         got = [digest() for _ in range(25)]
         assert all(g == want for g in got), f"{opts}: {sum(g != want for g in got)} of {len(got)} renders differ from the per-thread kernels' frame"
+    # ... and as a fused sequence (blend of frame k-1 + z-min of frame k through the same ring): 25 frames of the same pose
+    for k, v in dict(ring=1, chunk_cull=1, zmin_variant=5, blend_variant=4, ring_ctas=2, fuse=2).items():
+        pc.set_option(k, v)
+    pc.set_camera(calib, E)
+    bad = 0
+    for i in range(25):
+        pc.render_device(gpu.STAGE_RGBD)
+        if i % 4 == 3:   # every fourth frame is read back (which completes it); the others are completed by their successor
+            got = scenes.sha(pc.read("image", np.uint8, P * 3)) + scenes.sha(pc.read("zbuf", np.uint32, P)) + scenes.sha(pc.read("accum", np.uint32, P * 4))
+            bad += got != want
+    assert bad == 0, f"fused sequence: {bad} frames differ from the per-thread kernels' frame"
     pc.close()
