@@ -658,6 +658,15 @@ def run_b200(args, wl):
                     "frame_ms_with_stage_events": st["frame_ms"],
                     "note": "the pass does the arithmetic, gathers and reductions of BOTH of the reference's point passes on every record it reads; "
                             "`two_pass` is the same trajectory with fuse=0 (each frame streams its own list twice)"}
+        # SURVEY section 8(d) charges 16 B per point PER PASS: the launch does one z-min-pass unit (frame k) and one blend-pass
+        # unit (frame k-1) for the points of the two visible lists while reading their union once
+        units = 2.0 * min(count, (st["visible_chunks_per_frame"] or 0.0) * 1024.0)
+        eq = 16.0 * units / (fused_ms * 1e-3) / 1e9
+        roofline["per_reference_pass"] = {"point_pass_units_per_launch": units, "algorithmic_bytes": 16.0 * units, "achieved": eq, "frac": eq / peak,
+                                          "frac_of_nominal_8TBps": eq / 8000.0,
+                                          "note": "the reference's algorithm needs 16 B per point for EACH of minDepthPass and accumulatePass; `frac` above "
+                                                  "counts the bytes this launch really streams (each visible point once), this entry the two passes' worth of "
+                                                  "work it does on them — comparable with round 1's one-pass-per-launch 0.545 / 0.551"}
         # the same frames as two passes per frame (option fuse = 0): what each pass costs on its own
         fuse_opt = pc.get_option("fuse")
         pc.set_option("fuse", 0)

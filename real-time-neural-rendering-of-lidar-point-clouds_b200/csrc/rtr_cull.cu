@@ -124,6 +124,83 @@ __device__ __forceinline__ bool chunk_visible(const ChunkBounds& b, const CullPa
     return !cut;
 }
 
+// ---------------------------------------------------------------- screen-band ordering of the list (BandSort, rtr_kernels.h)
+// The band a chunk is filed under: the row band of the image its box centre projects into for camera cp.  It only
+// orders the list, so float arithmetic and an approximate divide do; centres behind the camera or with a non-finite
+// image land in band 0.
+__device__ __forceinline__ uint32_t chunk_band(const ChunkBounds& b, const CullParams& cp, uint32_t n_bands) {
+    const float cx = 0.5f * (b.lo[0] + b.hi[0]), cy = 0.5f * (b.lo[1] + b.hi[1]), cz = 0.5f * (b.lo[2] + b.hi[2]);
+    const float ry = float(cp.r1[0]) * cx + float(cp.r1[1]) * cy + float(cp.r1[2]) * cz + float(cp.r1[3]);
+    const float rz = float(cp.r2[0]) * cx + float(cp.r2[1]) * cy + float(cp.r2[2]) * cz + float(cp.r2[3]);
+    const float t = __fdividef(ry, rz) * (float(n_bands) / float(cp.H));
+    if (!(rz > 0.0f) || !(t >= 0.0f)) return 0u;
+    return t >= float(n_bands) ? n_bands - 1u : uint32_t(t);
+}
+// Warp-wide append of the lanes with keep = true to their bands' segments (every lane of the warp must call this).
+__device__ __forceinline__ void band_append(bool keep, uint32_t entry, uint32_t band, CullState* cull, const BandSort& bs) {
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, keep ? band : 0xFFFFFFFFu);  // the lanes filing under the same band
+    const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+    uint32_t base = 0;
+    if (keep && lane == leader) base = atomicAdd(&cull->band_count[band], uint32_t(__popc(grp)));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (keep) bs.scratch[size_t(band) * bs.cap + base + __popc(grp & ((1u << lane) - 1u))] = entry;
+}
+// Called by every thread of every CTA once its appends are done: the CTA that arrives last copies the segments, band
+// after band, into the list the point passes walk, and re-arms the counters for the next classification.
+__device__ __forceinline__ void band_compact(uint32_t* __restrict__ vis_list, CullState* cull, const BandSort& bs) {
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&cull->band_ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // One flat loop over the 16-byte vectors of all segments (a loop per band would pay a dependent L2 round trip or two
+    // for each band, one after the other, on the next pass's critical path): all eight counts in one go, then every
+    // thread finds the band of its vector from the running sums and has four loads in flight.
+    const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(cull->band_count)), c47 = __ldcg(reinterpret_cast<const uint4*>(cull->band_count) + 1);
+    const uint32_t cnt[kMaxBands] = {c03.x, c03.y, c03.z, c03.w, c47.x, c47.y, c47.z, c47.w};
+    uint32_t voff[kMaxBands + 1], eoff[kMaxBands + 1];  // vectors / entries in front of band b
+    voff[0] = 0u;
+    eoff[0] = 0u;
+#pragma unroll
+    for (int b = 0; b < kMaxBands; ++b) {
+        const uint32_t c = uint32_t(b) < bs.n_bands ? cnt[b] : 0u;
+        voff[b + 1] = voff[b] + ((c + 3u) >> 2);
+        eoff[b + 1] = eoff[b] + c;
+    }
+    const uint32_t total_v = voff[kMaxBands];
+    constexpr int kInFlight = 4;
+    for (uint32_t v0 = threadIdx.x; v0 < total_v; v0 += blockDim.x * kInFlight) {
+        uint4 val[kInFlight];
+        uint32_t dst0[kInFlight], left[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const uint32_t v = v0 + uint32_t(u) * blockDim.x;
+            uint32_t vb = 0u, eb = 0u, cb = cnt[0], bb = 0u;
+#pragma unroll
+            for (int k = 1; k < kMaxBands; ++k)
+                if (v >= voff[k]) { vb = voff[k]; eb = eoff[k]; cb = cnt[k]; bb = uint32_t(k); }
+            const uint32_t lv = v - vb;
+            left[u] = v < total_v ? cb - lv * 4u : 0u;  // entries of this vector that exist (the rest of it is stale)
+            dst0[u] = eb + lv * 4u;
+            // cap % 4 == 0: the segments are 16-byte aligned.  Written by other SMs: through L2.
+            if (v < total_v) val[u] = __ldcg(reinterpret_cast<const uint4*>(bs.scratch + size_t(bb) * bs.cap) + lv);
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            uint32_t* dst = vis_list + dst0[u];
+            if (left[u] > 0u) dst[0] = val[u].x;
+            if (left[u] > 1u) dst[1] = val[u].y;
+            if (left[u] > 2u) dst[2] = val[u].z;
+            if (left[u] > 3u) dst[3] = val[u].w;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < uint32_t(kMaxBands)) cull->band_count[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) cull->band_ticket = 0u;
+}
+
 // One launch per frame: fillBuffer + cudaMemset (render.cu:16-31, project_cloud.cu:316-317) and the chunk
 // classification.  The visible-chunk counter is double-buffered by frame parity so that the reset of one counter
 // and the atomic appends to the other need no ordering inside the launch.
@@ -131,14 +208,14 @@ __device__ __forceinline__ bool chunk_visible(const ChunkBounds& b, const CullPa
 // MIN_BLOCKS = 4 caps the kernel at 64 registers (the interval arithmetic in double wants 80): with two frames in
 // flight this kernel should start while the OTHER frame's ring kernel still holds its 2 x 512 threads x 48 registers
 // per SM, which leaves room for exactly 256 threads x 64 registers.
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool BANDS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS) clear_classify_kernel(uint32_t* __restrict__ zbuf, uint64_t cov,
                                                              uint4* __restrict__ accum, uint64_t n_px,
                                                              uint32_t* __restrict__ minmax,
                                                              const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
                                                              const __grid_constant__ CullParams cp,
                                                              uint32_t* __restrict__ vis_list, CullState* __restrict__ cull,
-                                                             uint32_t parity) {
+                                                             uint32_t parity, const __grid_constant__ BandSort bs) {
     pdl_prologue();
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
@@ -160,16 +237,23 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) clear_classify_kernel(uint32_
     // ---- classification first (its appends are what the next kernel waits for), whole warps at a time
     const uint32_t n_round = (n_chunks + 31u) & ~31u;
     for (uint64_t c = tid; c < n_round; c += stride) {
-        const bool visible = c < n_chunks && chunk_visible(bounds[c], cp);
+        ChunkBounds b;
+        if (c < n_chunks) b = bounds[c];
+        const bool visible = c < n_chunks && chunk_visible(b, cp);
         const unsigned m = __ballot_sync(0xFFFFFFFFu, visible);
         if (m) {
             const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(&cull->n_visible[parity], uint32_t(__popc(m)));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (visible) vis_list[base + __popc(m & ((1u << lane) - 1u))] = uint32_t(c);
+            if constexpr (BANDS) {
+                band_append(visible, uint32_t(c), visible ? chunk_band(b, cp, bs.n_bands) : 0u, cull, bs);
+            } else {
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (visible) vis_list[base + __popc(m & ((1u << lane) - 1u))] = uint32_t(c);
+            }
         }
     }
+    if constexpr (BANDS) band_compact(vis_list, cull, bs);  // (the next kernel waits for this; the clear below is bulk work)
     // ---- clear
     for (uint64_t i = tid; i < n_px; i += stride) accum[i] = make_uint4(0u, 0u, 0u, 0u);
     const uint64_t cov4 = cov >> 2;
@@ -191,12 +275,12 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) clear_classify_kernel(uint32_
 // lets its own dependents be scheduled at once, classifies while that pass is still draining, and only THEN waits for
 // it — completion stays transitive along the stream (the next pass waits for this kernel, this kernel for the previous
 // pass), but the classification no longer sits between two passes.
-template <bool LATE_WAIT>
+template <bool LATE_WAIT, bool BANDS>
 __global__ void __launch_bounds__(128, 8) classify_pair_kernel(const ChunkBounds* __restrict__ bounds, uint32_t n_chunks,
                                                                const __grid_constant__ CullParams cp_blend,
                                                                const __grid_constant__ CullParams cp_zmin, uint32_t have,
                                                                uint32_t* __restrict__ vis_list, CullState* __restrict__ cull,
-                                                               uint32_t parity) {
+                                                               uint32_t parity, const __grid_constant__ BandSort bs) {
     if constexpr (LATE_WAIT) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     else pdl_prologue();
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -214,8 +298,9 @@ __global__ void __launch_bounds__(128, 8) classify_pair_kernel(const ChunkBounds
     const uint32_t n_round = (n_chunks + 31u) & ~31u;
     for (uint64_t c = tid; c < n_round; c += stride) {
         uint32_t flags = 0u;
+        ChunkBounds b;
         if (c < n_chunks) {
-            const ChunkBounds b = bounds[c];
+            b = bounds[c];
             if ((have & 1u) && chunk_visible(b, cp_blend)) flags |= kTileBlend;
             if ((have & 2u) && chunk_visible(b, cp_zmin)) flags |= kTileZmin;
         }
@@ -229,24 +314,35 @@ __global__ void __launch_bounds__(128, 8) classify_pair_kernel(const ChunkBounds
                 if (mb) atomicAdd(&cull->n_blend[parity], uint32_t(__popc(mb)));
                 if (mz) atomicAdd(&cull->n_zmin[parity], uint32_t(__popc(mz)));
             }
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (flags) vis_list[base + __popc(m & ((1u << lane) - 1u))] = uint32_t(c) | flags;
+            if constexpr (BANDS) {
+                // (both cameras of a pair are consecutive poses: the newer one's image decides the band)
+                band_append(flags != 0u, uint32_t(c) | flags, flags ? chunk_band(b, (have & 2u) ? cp_zmin : cp_blend, bs.n_bands) : 0u, cull, bs);
+            } else {
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (flags) vis_list[base + __popc(m & ((1u << lane) - 1u))] = uint32_t(c) | flags;
+            }
         }
     }
+    if constexpr (BANDS) band_compact(vis_list, cull, bs);
     if constexpr (LATE_WAIT) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 cudaError_t launch_classify_pair(cudaStream_t s, int sm_count, const ChunkBounds* bounds, uint32_t n_chunks,
                                  const CullParams& cp_blend, bool have_blend, const CullParams& cp_zmin, bool have_zmin,
-                                 uint32_t* vis_list, CullState* cull, uint32_t parity, bool late_wait) {
+                                 uint32_t* vis_list, CullState* cull, uint32_t parity, bool late_wait, const BandSort& bands) {
     const uint32_t have = (have_blend ? 1u : 0u) | (have_zmin ? 2u : 0u);
     // one thread per chunk, at most 8 CTAs per SM (the list is short: a few microseconds, latency-bound)
     unsigned grid = (n_chunks + 127u) / 128u;
     const unsigned cap = unsigned(sm_count) * 8u;
     if (grid > cap) grid = cap;
     if (grid < 1u) grid = 1u;
-    if (late_wait) launch_pdl(classify_pair_kernel<true>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity);
-    else launch_pdl(classify_pair_kernel<false>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity);
+    const bool sort = bands.n_bands > 1u && bands.scratch != nullptr && bands.cap >= n_chunks;
+    BandSort bs = bands;
+    if (bs.n_bands > uint32_t(kMaxBands)) bs.n_bands = uint32_t(kMaxBands);
+    if (sort && late_wait) launch_pdl(classify_pair_kernel<true, true>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity, bs);
+    else if (sort) launch_pdl(classify_pair_kernel<false, true>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity, bs);
+    else if (late_wait) launch_pdl(classify_pair_kernel<true, false>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity, bs);
+    else launch_pdl(classify_pair_kernel<false, false>, dim3(grid), dim3(128), s, bounds, n_chunks, cp_blend, cp_zmin, have, vis_list, cull, parity, bs);
     return cudaGetLastError();
 }
 
@@ -258,13 +354,16 @@ cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t
 
 cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum,
                                   uint64_t n_px, uint32_t* minmax, const ChunkBounds* bounds, uint32_t n_chunks,
-                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity, bool lean) {
-    if (lean)
-        launch_pdl(clear_classify_kernel<4>, dim3(sm_count * 8), dim3(256), s, zbuf, cov, reinterpret_cast<uint4*>(accum), n_px,
-                   minmax, bounds, n_chunks, cp, vis_list, cull, parity);
-    else
-        launch_pdl(clear_classify_kernel<3>, dim3(sm_count * 8), dim3(256), s, zbuf, cov, reinterpret_cast<uint4*>(accum), n_px,
-                   minmax, bounds, n_chunks, cp, vis_list, cull, parity);
+                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity, bool lean,
+                                  const BandSort& bands) {
+    const bool sort = bands.n_bands > 1u && bands.scratch != nullptr && bands.cap >= n_chunks;
+    BandSort bs = bands;
+    if (bs.n_bands > uint32_t(kMaxBands)) bs.n_bands = uint32_t(kMaxBands);
+    uint4* a4 = reinterpret_cast<uint4*>(accum);
+    const dim3 grid(sm_count * 8), block(256);
+    if (sort) launch_pdl(clear_classify_kernel<4, true>, grid, block, s, zbuf, cov, a4, n_px, minmax, bounds, n_chunks, cp, vis_list, cull, parity, bs);
+    else if (lean) launch_pdl(clear_classify_kernel<4, false>, grid, block, s, zbuf, cov, a4, n_px, minmax, bounds, n_chunks, cp, vis_list, cull, parity, bs);
+    else launch_pdl(clear_classify_kernel<3, false>, grid, block, s, zbuf, cov, a4, n_px, minmax, bounds, n_chunks, cp, vis_list, cull, parity, bs);
     return cudaGetLastError();
 }
 

@@ -26,6 +26,8 @@ struct FrameSet {
     // chunk-level frustum culling state of the frame rendered into this set (rtr_cull.cu); per set so that two frames
     // can be in flight on two streams
     uint32_t* vis_list = nullptr;
+    uint32_t* band_scratch = nullptr;  // kMaxBands segments of band_cap entries: screen-band ordering of the list (BandSort)
+    uint32_t band_cap = 0;
     CullState* cull_state = nullptr;
     uint32_t cull_parity = 0;  // alternates per culled frame (CullState::n_visible double buffer)
 };
@@ -36,6 +38,7 @@ struct FramePlan {
     CullParams cp;
     bool cull = false;      // chunk-level frustum culling applies
     bool use_ring = false;  // the point passes run through the TMA-fed kernels
+    uint32_t bands = 1;     // screen bands the visible list is ordered by (1: list order)
 };
 // A frame of a fused sequence whose z-min pass has been enqueued and whose blend / image passes have not: they are
 // enqueued together with the NEXT frame's z-min (one stream of chunks for both) or by flush_pending().
@@ -105,6 +108,8 @@ struct rtr_renderer {
     int clear_lean = 1;  // clear + classify compiled for <= 64 registers, so that it fits beside the other frame's ring kernel (0: 80 registers)
     int ring_perm = 1;  // stream-all ring passes visit the chunks in a low-discrepancy order (0: storage order)
     int ring = 1;  // point passes through the TMA-fed persistent kernels: 1 = for culled frames, 2 = always, 0 = never
+    int bands = 0;  // visible list ordered by screen band (BandSort): 1 = off, 2 ... 8 = that many bands, 0 = by the size of the frame
+                    // buffers (off while z-buffer + colour sums of the frames in flight fit the L2)
     cudaEvent_t ev[6] = {nullptr};
     // timing == 2: per-frame event sextets from a pool, summed on demand (bench roofline leg)
     std::vector<cudaEvent_t> ev_pool;

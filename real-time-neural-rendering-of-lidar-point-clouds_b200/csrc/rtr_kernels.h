@@ -31,7 +31,12 @@ struct CullState {
     uint32_t n_blend[2], n_zmin[2];
     unsigned long long total_streamed;  // chunk reads from HBM: entries of every pair list, 2 x entries of every whole-frame list
     uint32_t passes, pad;               // point passes folded into total_streamed
+    // screen-band ordering of the list (BandSort below): entries per band of the classification in flight, and the
+    // ticket that tells the classification's last CTA that it is the last
+    uint32_t band_count[8];
+    uint32_t band_ticket, pad2[3];
 };
+static_assert(sizeof(CullState) <= 256, "the tile-claim counters start 256 bytes behind the CullState");
 constexpr uint32_t kListHasBlend = 1u, kListHasZmin = 2u, kListWhole = 4u;
 // Fold the list in flight (counter `old`) into the totals — device (next classification) and host (statistics read-out).
 __host__ __device__ inline void cull_fold(CullState* c, uint32_t old) {
@@ -72,6 +77,20 @@ __host__ __device__ inline uint32_t cull_count(const CullState* c) { return c->n
 struct CullParams {
     double r0[4], r1[4], r2[4];
     double W, H;
+};
+// Screen-band ordering of the visible list.  The order in which a pass walks its tiles changes no result (min and
+// integer / exact-float sums are order-free), but it decides WHICH z-buffer / accumulator lines the CTAs in flight are
+// hitting at any one time.  In list order (= Morton order of the cloud) that is the whole frame; once the frame
+// buffers outgrow the L2 (3840x2160: 33 MB z-buffer + 133 MB colour sums per frame against 126 MB) every reduction
+// and gather then goes to DRAM.  With n_bands > 1 the classification files every visible chunk under the horizontal
+// screen band its box centre projects into (per-band segments of `scratch`, `cap` entries each) and its last CTA
+// copies the segments band after band into the list, so the tiles in flight — a window of the list — share a band
+// and the band's lines stay in L2 while they are hot.  n_bands <= 1: the list is written directly, as before.
+constexpr int kMaxBands = 8;
+struct BandSort {
+    uint32_t n_bands;
+    uint32_t cap;        // entries per band segment (a multiple of 4, >= the cloud's chunk count)
+    uint32_t* scratch;   // kMaxBands * cap entries, one allocation per frame set
 };
 
 // Pyramid geometry exactly as applyDepthFilter derives it (project_cloud.cu:336-362): true level
@@ -219,12 +238,14 @@ cudaError_t launch_chunk_bounds(cudaStream_t s, const PointRecord* pts, uint64_t
 // clear (zbuf coverage, accum, minmax) + per-frame chunk classification in ONE launch; parity alternates per frame.
 cudaError_t launch_clear_classify(cudaStream_t s, int sm_count, uint32_t* zbuf, uint64_t cov, uint32_t* accum,
                                   uint64_t n_px, uint32_t* minmax, const ChunkBounds* bounds, uint32_t n_chunks,
-                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity, bool lean = true);
+                                  const CullParams& cp, uint32_t* vis_list, CullState* cull, uint32_t parity, bool lean = true,
+                                  const BandSort& bands = BandSort{1u, 0u, nullptr});
 // Chunk classification for two cameras at once, no clear: entry = chunk | kTileBlend (visible for cp_blend, if
 // have_blend) | kTileZmin (visible for cp_zmin, if have_zmin); chunks visible for neither are dropped.
 cudaError_t launch_classify_pair(cudaStream_t s, int sm_count, const ChunkBounds* bounds, uint32_t n_chunks,
                                  const CullParams& cp_blend, bool have_blend, const CullParams& cp_zmin, bool have_zmin,
-                                 uint32_t* vis_list, CullState* cull, uint32_t parity, bool late_wait = false);
+                                 uint32_t* vis_list, CullState* cull, uint32_t parity, bool late_wait = false,
+                                 const BandSort& bands = BandSort{1u, 0u, nullptr});
 cudaError_t launch_zmin(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,
                         uint64_t index_base, const ProjParams& pp, uint32_t* zbuf, unsigned long long* zkey);
 cudaError_t launch_blend(cudaStream_t s, int variant, int unroll, const PointRecord* pts, uint64_t n,

@@ -102,8 +102,8 @@ void free_cull_storage(rtr_renderer* r) {
     cudaFree(r->bounds);
     r->bounds = nullptr;
     for (auto& s : r->set) {
-        cudaFree(s.vis_list); cudaFree(s.cull_state);
-        s.vis_list = nullptr; s.cull_state = nullptr; s.cull_parity = 0;
+        cudaFree(s.vis_list); cudaFree(s.cull_state); cudaFree(s.band_scratch);
+        s.vis_list = nullptr; s.cull_state = nullptr; s.band_scratch = nullptr; s.band_cap = 0; s.cull_parity = 0;
     }
 }
 // The compute streams idle (stream2 / image_stream only ever hold work of a pipelined frame sequence).
@@ -244,6 +244,7 @@ int comm_allreduce(rtr_renderer* r, const void* src, void* dst, size_t count, in
 }
 
 constexpr int kEvPoolFrames = 256;
+constexpr double kBandsAutoMinMB = 64.0;  // option bands = 0: frames whose z-buffer + colour sums exceed this are walked band by band
 
 // Fold the pooled per-frame events into ev_sum (blocks until the last recorded frame finished).
 int drain_event_pool(rtr_renderer* r) {
@@ -302,6 +303,18 @@ int peer_status(rtr_renderer* r) {
     return RTR_OK;
 }
 
+// Screen bands the visible list is ordered by (BandSort, rtr_kernels.h).  A point pass gathers from a z-buffer and
+// reduces into a z-buffer / the colour sums: 24 B per pixel that should stay in L2 while the pass runs.  1920x1080:
+// 50 MB, fits, list order is kept.  3840x2160: 199 MB — every RED and gather would go to DRAM; ordered by 8 bands the
+// tiles in flight share about 25 MB of it.
+uint32_t frame_bands(const rtr_renderer* r) {
+    if (r->bands >= 1) return uint32_t(r->bands > kMaxBands ? kMaxBands : r->bands);
+    const double live_mb = double(r->W) * double(r->H) * 24.0 / 1048576.0;
+    if (live_mb <= kBandsAutoMinMB) return 1u;
+    const double want = std::ceil(live_mb / 25.0);
+    return uint32_t(want > double(kMaxBands) ? double(kMaxBands) : (want < 2.0 ? 2.0 : want));
+}
+
 // Everything a frame needs besides its buffers, from the renderer's current camera and options.
 int plan_frame(rtr_renderer* r, FramePlan& pl) {
     int rc = make_params(r, pl.pp);
@@ -314,6 +327,7 @@ int plan_frame(rtr_renderer* r, FramePlan& pl) {
     // ring = 1: the TMA-fed kernels for culled frames, the per-thread LDG.128 kernels when every chunk is streamed
     // (measured 3 % faster there, profiles/r01h_exp_ring_c3.json); ring = 2: always; ring = 0: never
     pl.use_ring = r->ring == 2 || (r->ring == 1 && pl.cull);
+    pl.bands = frame_bands(r);
     CullParams& cp = pl.cp;
     std::memset(&cp, 0, sizeof(cp));
     if (pl.cull && !pp.distort) {
@@ -403,7 +417,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
         fs.f32acc = false;
         if (cull) {
             fs.cull_parity ^= 1u;
-            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity, r->clear_lean != 0));
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity, r->clear_lean != 0, BandSort{pl.bands, fs.band_cap, fs.band_scratch}));
         } else {
             RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, 0, nullptr, 0, fb.minmax, nullptr));
         }
@@ -437,7 +451,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     } else {
         if (cull) {
             fs.cull_parity ^= 1u;
-            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity, r->clear_lean != 0));
+            RTR_CUDA(r, launch_clear_classify(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, r->bounds, r->n_chunks, cp, fs.vis_list, fs.cull_state, fs.cull_parity, r->clear_lean != 0, BandSort{pl.bands, fs.band_cap, fs.band_scratch}));
         } else {
             RTR_CUDA(r, launch_clear(s, r->sm_count, fb.zbuf, cov, fb.accum, P, fb.minmax, nullptr));
         }
@@ -617,7 +631,7 @@ int enqueue_fused(rtr_renderer* r, int stage, const FramePlan& pl, uint8_t* bgr,
     if (ev) cudaEventRecord(ev[0], s);
     fs.cull_parity ^= 1u;
     RTR_CUDA(r, launch_classify_pair(s, r->sm_count, r->bounds, r->n_chunks, pf.active ? pf.plan.cp : pl.cp, pf.active, pl.cp, true,
-                                     fs.vis_list, fs.cull_state, fs.cull_parity, true));
+                                     fs.vis_list, fs.cull_state, fs.cull_parity, true, BandSort{pl.bands, fs.band_cap, fs.band_scratch}));
     if (ev) cudaEventRecord(ev[1], s);
     RingSchedule sched = ring_schedule_for(r, fs, true);
     sched.tile_counter = r->ring_dynamic > 0 ? tile_counters(fs.cull_state, 0) : nullptr;
@@ -666,7 +680,7 @@ int flush_pending(rtr_renderer* r) {
     RTR_CUDA(r, cudaStreamWaitEvent(s, r->set[(pf.si + kFrameSets - 1) % kFrameSets].rendered, 0));
     fs.cull_parity ^= 1u;
     RTR_CUDA(r, launch_classify_pair(s, r->sm_count, r->bounds, r->n_chunks, pf.plan.cp, true, pf.plan.cp, false, fs.vis_list, fs.cull_state,
-                                     fs.cull_parity));
+                                     fs.cull_parity, false, BandSort{pf.plan.bands, fs.band_cap, fs.band_scratch}));
     RingSchedule sched = ring_schedule_for(r, fs, true);
     sched.tile_counter = r->ring_dynamic > 0 ? tile_counters(fs.cull_state, 0) : nullptr;
     const int bv = blend_variant_now(r, false);
@@ -875,6 +889,8 @@ int build_chunk_bounds(rtr_renderer* r) {
     RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&r->bounds), size_t(r->n_chunks) * sizeof(ChunkBounds)));
     for (auto& fs : r->set) {
         RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.vis_list), size_t(r->n_chunks) * sizeof(uint32_t)));
+        fs.band_cap = (r->n_chunks + 3u) & ~3u;
+        RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.band_scratch), size_t(kMaxBands) * fs.band_cap * sizeof(uint32_t)));
         RTR_CUDA(r, cudaMalloc(reinterpret_cast<void**>(&fs.cull_state), kCullStateAlloc));  // + the tile-claim counters
         RTR_CUDA(r, cudaMemsetAsync(fs.cull_state, 0, kCullStateAlloc, r->stream));
         fs.cull_parity = 0;
@@ -1241,6 +1257,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "chunk_cull")) return &r->chunk_cull;
     if (!std::strcmp(key, "sort_on_upload")) return &r->sort_on_upload;
     if (!std::strcmp(key, "ring")) return &r->ring;
+    if (!std::strcmp(key, "bands")) return &r->bands;
     if (!std::strcmp(key, "fused_up")) return &r->fused_up;
     if (!std::strcmp(key, "ring_perm")) return &r->ring_perm;
     if (!std::strcmp(key, "ring_early")) return &r->ring_early;
@@ -1287,6 +1304,7 @@ int rtr_set_option(rtr_renderer* r, const char* key, int64_t value) {
     if (!std::strcmp(key, "blend_variant") && (value < 0 || (value & ~bmask)))
         return fail(r, RTR_ERR_ARG, "blend_variant must be 0, 2, 4 or 6 (measurement bit 32 only in RTR_EXPERIMENTS builds)");
     if (!std::strcmp(key, "timing") && (value < 0 || value > 3)) return fail(r, RTR_ERR_ARG, "timing must be 0 ... 3");
+    if (!std::strcmp(key, "bands") && (value < 0 || value > kMaxBands)) return fail(r, RTR_ERR_ARG, "bands must be 0 (by frame size), 1 (off) or 2 ... 8");
     if (!std::strcmp(key, "fuse") && (value < 0 || value > 2)) return fail(r, RTR_ERR_ARG, "fuse must be 0 (never), 1 (large clouds) or 2 (always)");
     *slot = int(value);
     return RTR_OK;
@@ -1302,6 +1320,7 @@ int64_t rtr_get_option(const rtr_renderer* r, const char* key) {
         rtr_renderer* m = const_cast<rtr_renderer*>(r);
         return (m->points && plan_frame(m, pl) == RTR_OK && fused_sequence(r, pl)) ? 1 : 0;
     }
+    if (!std::strcmp(key, "bands_active")) return (r->W >= 16 && r->H >= 16) ? int64_t(frame_bands(r)) : 1;  // bands the next frame's list is ordered by
     if (!std::strcmp(key, "pending")) return r->pending.active ? 1 : 0;  // a fused sequence's last frame still lacks its blend
     if (!std::strcmp(key, "experiments")) {
 #ifdef RTR_EXPERIMENTS

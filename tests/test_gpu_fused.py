@@ -199,3 +199,79 @@ def test_fused_sequence_replaced_cloud_and_reuse(gpu, cpu_oracle):
     pc.close()
     want = _blocking(gpu, other, calib, [case.poses[0]])[0]
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("bands", [2, 3, 8])
+def test_band_ordered_lists_give_identical_frames(gpu, cpu_oracle, bands):
+    """Option bands (csrc/rtr_cull.cu band_append / band_compact): the classification files the visible chunks under
+    screen bands and its last CTA copies the segments, band after band, into the list.  The list must stay a permutation
+    of the unordered one — a lost chunk would drop points, a doubled one would double colour sums — so every frame is
+    byte-identical and the streamed-chunk counts are the same, through the fused pass, the two-pass sequence, the
+    blocking calls (clear_classify_kernel) and the 64-bit-key frame."""
+    case = scenes.CASES["c3_1920x1080"]
+    rec = cloud_of(cpu_oracle, case)
+    calib = calib_of(gpu, case)
+    P = case.W * case.H
+    poses = _trajectory(gpu, 1000)[300:316]
+    want = _blocking(gpu, rec, calib, poses)
+    got_blocking = _blocking(gpu, rec, calib, poses[:4], options={"bands": bands})
+    for i in range(4):
+        assert all(np.array_equal(a, b) for a, b in zip(got_blocking[i], want[i])), f"blocking call, frame {i}"
+    counts = {}
+    for fuse in (2, 0):
+        for b in (1, bands):
+            pc = gpu.ProjectCloud.from_packed(rec)
+            pc.set_option("fuse", fuse)
+            pc.set_option("bands", b)
+            pc.set_camera(calib)
+            assert pc.get_option("bands_active") == b
+            color = np.zeros((len(poses), P * 3), np.uint8)
+            depth = np.zeros((len(poses), P), np.float32)
+            pc.stream_stats(reset=True)
+            pc.render_trajectory(gpu.STAGE_FILTERED, poses, color, depth)
+            tensor, accum = pc.read("tensor", np.uint16, P * 5), pc.read("accum", np.uint32, P * 4)
+            counts[(fuse, b)] = (pc.stream_stats(reset=False), pc.cull_stats(reset=True))
+            pc.close()
+            for i in range(len(poses)):
+                assert np.array_equal(color[i], want[i][0]) and np.array_equal(depth[i].view(np.uint32), want[i][1]), f"fuse {fuse}, bands {b}: frame {i}"
+            assert np.array_equal(tensor, want[-1][2])
+            if b == 1:
+                accum_want = accum
+            else:
+                assert np.array_equal(accum, accum_want)
+        assert counts[(fuse, 1)] == counts[(fuse, bands)]
+    # 64-bit keys (depth bits << 32 | point index): clear_classify without the colour-sum clear
+    frames = []
+    for b in (1, bands):
+        pc = gpu.ProjectCloud.from_packed(rec)
+        pc.set_option("key64", 1)
+        pc.set_option("bands", b)
+        color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        assert pc.computeFilteredRGBD(calib, poses[5], color, depth) == 1
+        frames.append((color, depth.view(np.uint32).copy()))
+        pc.close()
+    assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
+
+
+def test_bands_follow_the_frame_size(gpu, cpu_oracle):
+    """bands = 0 (default): list order while z-buffer + colour sums of a frame fit the L2 (1080p: 50 MB), screen bands
+    beyond (4K: 199 MB -> 8 bands); and the 4K frame through band-ordered lists equals the golden of the reference."""
+    small, big = scenes.CASES["c3_1920x1080"], scenes.CASES["c5_3840x2160"]
+    pc = gpu.ProjectCloud.from_packed(cloud_of(cpu_oracle, big))
+    assert pc.get_option("bands") == 0
+    pc.set_camera(calib_of(gpu, small))
+    assert pc.get_option("bands_active") == 1
+    calib = calib_of(gpu, big)
+    pc.set_camera(calib)
+    assert pc.get_option("bands_active") == 8
+    P = big.W * big.H
+    out = []
+    for b in (0, 1):
+        pc.set_option("bands", b)
+        color, depth = np.zeros(P * 3, np.uint8), np.zeros(P, np.float32)
+        assert pc.computeFilteredRGBD(calib, big.poses[0], color, depth) == 1
+        out.append((color, depth.view(np.uint32).copy(), pc.read("tensor", np.uint16, P * 5)))
+    pc.close()
+    assert all(np.array_equal(a, b) for a, b in zip(out[0], out[1]))
+    with pytest.raises(Exception):
+        gpu.ProjectCloud.from_packed(cloud_of(cpu_oracle, small)).set_option("bands", 9)
