@@ -75,6 +75,10 @@ struct rtr_renderer {
     bool have_K = false, have_E = false, raw_proj = false;
     float cam_proj[16] = {0};
     double cull_rstar = 0;  // distortion: normalised radius beyond which nothing reaches the image (make_params)
+    // rtr_host_distortion_bounds of the current intrinsics (12 K samples of the radial polynomial): computed once per
+    // rtr_set_intrinsics*, not once per frame
+    bool dist_bounds_valid = false;
+    double dist_r2_max = 0, dist_rstar = 0;
     // frame buffers (two sets, see header)
     rtr::FrameSet set[rtr::kFrameSets];
     int cur = 0;

@@ -226,10 +226,12 @@ int make_params(rtr_renderer* r, ProjParams& pp) {
         pp.fy = float(r->K[4]); pp.cy = float(r->K[5]);
         pp.k1 = float(r->dist[0]); pp.k2 = float(r->dist[1]); pp.p1 = float(r->dist[2]);
         pp.p2 = float(r->dist[3]); pp.k3 = float(r->dist[4]);
-        double r2_max = 0, rstar = 0;
-        rtr_host_distortion_bounds(r->W, r->H, r->K, r->dist, &r2_max, &rstar);
-        pp.r2_max = float(r2_max);
-        r->cull_rstar = rstar;
+        if (!r->dist_bounds_valid) {  // (sampling the polynomial takes tens of microseconds: as long as a small frame)
+            rtr_host_distortion_bounds(r->W, r->H, r->K, r->dist, &r->dist_r2_max, &r->dist_rstar);
+            r->dist_bounds_valid = true;
+        }
+        pp.r2_max = float(r->dist_r2_max);
+        r->cull_rstar = r->dist_rstar;
     }
     return RTR_OK;
 }
@@ -522,12 +524,14 @@ int enqueue_copy(rtr_renderer* r, int si, uint8_t* bgr, float* depth);
 // sequence trades one of the two chunk streams per frame for fewer, longer kernel boundaries in which the image passes
 // can run, which wins once a point pass is long (C3, 100 M points: 9 100 vs 8 020 frames/s) and loses on small clouds
 // whose frames are a few short kernels (C1, 1 M points: 46 200 vs 52 800; C2, 20 M points: 21 900 vs 23 400;
-// profiles/r02m_exp_fixup_gate.json).  The switch is the cloud's chunk count — known on the host without a read-back —
-// or a distorted camera, whose heavier projection makes the passes long already at C2's size (20 M points, 1280x720:
-// 17 800 vs 12 400 frames/s, profiles/r02k_bench_c2_distort.json).
+// profiles/r02m_exp_fixup_gate.json).  The switch is the cloud's chunk count, known on the host without a read-back.
+// (Distorted cameras used to switch it too — 17 800 vs 12 400 frames/s at C2's size, profiles/r02k_bench_c2_distort.json —
+// but that two-pass number was the HOST's: make_params sampled the distortion polynomial 12 K times per frame.  With the
+// bounds cached per set of intrinsics the two-pass sequence does 20 700 frames/s there against 16 800 fused,
+// profiles/r02F_exp_host_enqueue.json.)
 constexpr uint32_t kFuseAutoMinChunks = 40000;  // 41 M points
 bool fused_sequence(const rtr_renderer* r, const FramePlan& pl) {
-    const bool want = r->fuse == 2 || (r->fuse == 1 && (r->n_chunks >= kFuseAutoMinChunks || pl.pp.distort != 0));
+    const bool want = r->fuse == 2 || (r->fuse == 1 && r->n_chunks >= kFuseAutoMinChunks);
     return want && pipelined(r) && pl.cull && pl.use_ring && !r->key64 && r->ring >= 1;
 }
 
@@ -992,9 +996,12 @@ int rtr_download_cloud_packed16(rtr_renderer* r, uint64_t first, uint64_t count,
 int rtr_set_intrinsics_matrix(rtr_renderer* r, int width, int height, const double* K9, const double* dist5) {
     if (!r || !K9) return RTR_ERR_ARG;
     if (width < 16 || height < 16 || width > 32768 || height > 32768) return fail(r, RTR_ERR_ARG, "width/height must be in [16, 32768]");
+    double d5[5];
+    for (int i = 0; i < 5; ++i) d5[i] = dist5 ? dist5[i] : 0.0;
+    if (r->W != width || r->H != height || std::memcmp(r->K, K9, sizeof(r->K)) || std::memcmp(r->dist, d5, sizeof(d5))) r->dist_bounds_valid = false;
     r->W = width; r->H = height;
     std::memcpy(r->K, K9, sizeof(r->K));
-    for (int i = 0; i < 5; ++i) r->dist[i] = dist5 ? dist5[i] : 0.0;
+    std::memcpy(r->dist, d5, sizeof(d5));
     r->have_K = true;
     return RTR_OK;
 }
