@@ -246,7 +246,7 @@ int comm_allreduce(rtr_renderer* r, const void* src, void* dst, size_t count, in
 }
 
 constexpr int kEvPoolFrames = 256;
-constexpr double kBandsAutoMinMB = 64.0;  // option bands = 0: frames whose z-buffer + colour sums exceed this are walked band by band
+constexpr double kBandsAutoMinMB = 126.0;  // option bands = 0: frames whose z-buffer + colour sums exceed the L2 (126 MB) are walked band by band
 
 // Fold the pooled per-frame events into ev_sum (blocks until the last recorded frame finished).
 int drain_event_pool(rtr_renderer* r) {

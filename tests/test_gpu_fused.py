@@ -254,7 +254,7 @@ def test_band_ordered_lists_give_identical_frames(gpu, cpu_oracle, bands):
 
 
 def test_bands_follow_the_frame_size(gpu, cpu_oracle):
-    """bands = 0 (default): list order while z-buffer + colour sums of a frame fit the L2 (1080p: 50 MB), screen bands
+    """bands = 0 (default): list order while z-buffer + colour sums of a frame fit the 126 MB L2 (1080p: 50 MB), screen bands
     beyond (4K: 199 MB -> 8 bands); and the 4K frame through band-ordered lists equals the golden of the reference."""
     small, big = scenes.CASES["c3_1920x1080"], scenes.CASES["c5_3840x2160"]
     pc = gpu.ProjectCloud.from_packed(cloud_of(cpu_oracle, big))
