@@ -97,7 +97,7 @@ int rtr_render_tensor(rtr_renderer* r, void** device_fp16);
  * rtr_get_device_buffers, rtr_read_buffer, rtr_set_option and every blocking render call, all of which complete the
  * outstanding frame first.  Frames are byte-identical to the blocking calls'.  rtr_get_device_buffers /
  * rtr_read_buffer refer to the frame enqueued last; rtr_get_device_buffers makes `stream` wait for every frame in
- * flight.  "fuse": 1 (default) = fused sequences for clouds of >= 40 000 chunks (41 M points) and for distorted cameras
+ * flight.  "fuse": 1 (default) = fused sequences for clouds of >= 40 000 chunks (41 M points)
  * (below that a frame is a few short kernels and two passes per frame, alternating between two frame sets and two
  * streams, are faster), 0 = never, 2 = always. */
 int rtr_render_device(rtr_renderer* r, int stage);
@@ -143,6 +143,10 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
  * list passes claim their tiles from this many counters; 0 = round-robin), "ring_claim_min" (default 12: passes with no more tiles per CTA than this stay
  * round-robin), "ring_ctas" (ring-kernel CTAs per SM, 2 or 1),
  * "clear_lean", "fused_up", "pipeline", "fuse",
+ * "bands" (the frame's visible-chunk list ordered by horizontal screen band, so that the tiles in flight share a band
+ * of the z-buffer / colour sums: 1 = list order, 2 ... 8 = that many bands, 0 (default) = 8 bands for frames whose
+ * z-buffer + colour sums exceed the 126 MB L2, e.g. 3840x2160, list order otherwise; frames are identical either way;
+ * rtr_get_option "bands_active" = what the next frame will use),
  * "sort_on_upload" (default 1: every upload
  * re-orders the cloud along a Morton curve on the GPU — no output depends on point order; set 0 BEFORE uploading
  * to keep the input order, e.g. when the point index of the 64-bit key must be the caller's index). */

@@ -275,3 +275,26 @@ def test_bands_follow_the_frame_size(gpu, cpu_oracle):
     assert all(np.array_equal(a, b) for a, b in zip(out[0], out[1]))
     with pytest.raises(Exception):
         gpu.ProjectCloud.from_packed(cloud_of(cpu_oracle, small)).set_option("bands", 9)
+
+
+def test_fused_sequence_at_3840x2160_with_band_ordered_lists(gpu, cpu_oracle):
+    """Config 5's 4K frames as a fused sequence (band-ordered lists by default there) against the blocking calls with
+    the list left in cloud order."""
+    case = scenes.CASES["c5_3840x2160"]
+    rec = cloud_of(cpu_oracle, case)
+    calib = calib_of(gpu, case)
+    P = case.W * case.H
+    poses = _trajectory(gpu, 1000)[700:706]
+    want = _blocking(gpu, rec, calib, poses, options={"bands": 1})
+    pc = gpu.ProjectCloud.from_packed(rec)
+    pc.set_option("fuse", 2)
+    pc.set_camera(calib)
+    assert pc.get_option("bands_active") == 8 and pc.get_option("fuse_active") == 1
+    color = np.zeros((len(poses), P * 3), np.uint8)
+    depth = np.zeros((len(poses), P), np.float32)
+    pc.render_trajectory(gpu.STAGE_FILTERED, poses, color, depth)
+    tensor = pc.read("tensor", np.uint16, P * 5)
+    pc.close()
+    for i in range(len(poses)):
+        assert np.array_equal(color[i], want[i][0]) and np.array_equal(depth[i].view(np.uint32), want[i][1]), f"frame {i}"
+    assert np.array_equal(tensor, want[-1][2])
