@@ -288,7 +288,7 @@ def test_fused_sequence_at_3840x2160_with_band_ordered_lists(gpu, cpu_oracle):
     want = _blocking(gpu, rec, calib, poses, options={"bands": 1})
     pc = gpu.ProjectCloud.from_packed(rec)
     pc.set_option("fuse", 2)
-    pc.set_camera(calib)
+    pc.set_camera(calib, poses[0])
     assert pc.get_option("bands_active") == 8 and pc.get_option("fuse_active") == 1
     color = np.zeros((len(poses), P * 3), np.uint8)
     depth = np.zeros((len(poses), P), np.float32)
