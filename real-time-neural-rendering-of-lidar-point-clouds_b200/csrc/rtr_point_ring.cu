@@ -23,13 +23,17 @@
 // for) and, with ring = 2, the stream-all frame (every chunk, visited in a low-discrepancy order so that the CTAs in
 // flight hold a mix of in-frustum and out-of-frustum chunks; the per-thread LDG.128 kernels stream 4 % faster there
 // and stay the default for it).
+#include <cstdlib>
 #include <type_traits>
 
 #include "rtr_kernels.h"
 
 namespace rtr {
 
-constexpr int kRingStages = 6;
+#ifndef RTR_RING_STAGES
+#define RTR_RING_STAGES 6
+#endif
+constexpr int kRingStages = RTR_RING_STAGES;
 constexpr int kRingGroups = 2;                        // consumer groups per CTA, each takes every kRingGroups-th tile
 constexpr int kRingConsumers = kPointBlock;           // a group: 256 threads x 4 consecutive records = one chunk
 constexpr int kRingThreads = kRingGroups * kRingConsumers;  // 512: no dedicated producer warp, thread 0 of a group refills its stages
@@ -660,6 +664,10 @@ static cudaError_t ring_attr(K kernel, bool* done) {
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(RingSmem)));
+#ifdef RTR_EXPERIMENTS
+    if (const char* c = std::getenv("RTR_RING_CARVEOUT"))  // measurement: shared-memory carve-out in percent (the rest of the 256 KB is L1)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(c));
+#endif
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }
