@@ -19,6 +19,8 @@
 // generic one-kernel-per-reference-kernel path, which is also the cross-check in the tests.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "rtr_kernels.h"
 
 #ifndef RTR_L2_HINTS
@@ -622,6 +624,19 @@ __global__ void __launch_bounds__(256, 4) up_fused_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------- launchers
+#ifdef RTR_EXPERIMENTS
+// measurement: RTR_IMAGE_CARVEOUT = shared-memory carve-out (percent) the image kernels ask for — the same split as the
+// ring kernels' would let their CTAs follow a ring CTA onto an SM without the SM having to drain and re-split first
+template <typename K>
+static void exp_carveout(K kernel) {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char* c = std::getenv("RTR_IMAGE_CARVEOUT")) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(c));
+}
+#else
+template <typename K> static void exp_carveout(K) {}
+#endif
 cudaError_t launch_resolve_gated(cudaStream_t s, const FrameBuffers& fb, int W, int H) {
     const uint64_t cov = clear_coverage(W, H);
     if (cov == 0) return cudaSuccess;
@@ -638,6 +653,7 @@ cudaError_t launch_resolve_pyramid(cudaStream_t s, const FrameBuffers& fb, int W
     if ((W % 16) == 0 && !force_generic) {
         dim3 grid((W + 63) / 64, H / 16);
 #define RTR_RP(P_, R_, F_) launch_pdl((resolve_pyramid_kernel<P_, R_, F_>), dim3(grid), dim3(256), s, fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W)
+        exp_carveout(resolve_pyramid_kernel<true, true, true>);
         if (pyramid && resolve) { if (f32acc) RTR_RP(true, true, true); else RTR_RP(true, true, false); }
         else if (pyramid) RTR_RP(true, false, false);
         else { if (f32acc) RTR_RP(false, true, true); else RTR_RP(false, true, false); }
@@ -697,6 +713,7 @@ cudaError_t launch_up_pass(cudaStream_t s, const FrameBuffers& fb, const Pyramid
     const bool taps = fb.mask[0] || fb.mask[1] || fb.mask[2] || fb.mask[3];
     // one launch for all four levels: needs the flat pyramid to be a true 2-D pyramid (w[i] == uw[i], i.e. W % 16 == 0)
     if (fused && wide_ok && !taps && d.uw[4] > 0 && d.uh[4] > 0 && d.w[1] == d.uw[1] && d.w[2] == d.uw[2] && d.w[3] == d.uw[3]) {
+        exp_carveout(up_fused_kernel);
         launch_pdl(up_fused_kernel, dim3((d.uw[1] + kUpT1W - 1) / kUpT1W, (d.uh[1] + kUpT1H - 1) / kUpT1H), dim3(256), s,
                    fb.level[1], fb.level[2], fb.level[3], fb.level[4], d.uw[4], d.uh[4], fb.level[0], fb.image, fb.tensor, fb.minmax);
         return cudaGetLastError();
