@@ -738,6 +738,18 @@ def run_b200(args, wl):
                     if c:
                         roofline["l2_atomics"][f"{name}_ncu"] = dict(c, red_sector_time_ms_at_measured_peak=c["red_sectors"] / (red_peak * 1e6),
                                                                     frac_of_launch=c["red_sectors"] / (red_peak * 1e6) / stt)
+                fd = tj.get(f"fused_{args.workload}_detail")
+                if fd and fused:
+                    # the fused launch of the committed capture: its scattered 32-byte-sector operations (REDs + z-buffer gathers)
+                    # against the measured random-address RED rate — the pass is bound by this path, not by HBM
+                    ops = fd["red_sectors"] + fd["gather_sectors"]
+                    roofline["l2_atomics"]["fused_ncu"] = dict(
+                        fd, scattered_sector_ops=ops, scattered_sector_Gops=ops / fd["duration_us_cold"] / 1e3,
+                        frac_of_measured_red_peak=ops / fd["duration_us_cold"] / 1e3 / red_peak,
+                        red_sector_time_ms_at_measured_peak=fd["red_sectors"] / (red_peak * 1e6),
+                        red_frac_of_launch=fd["red_sectors"] / (red_peak * 1e6) / (fd["duration_us_cold"] * 1e-3),
+                        note="REDs + gathers of one fused launch (ncu, stand-alone launch of the capture) per second, over the RED rate "
+                             "rtr_bench_red_min measures in THIS run with one random 32-byte sector per lane")
         except Exception:
             pass
 
