@@ -195,6 +195,13 @@ int rtr_host_distortion_bounds(int width, int height, const double* K9, const do
  * visits the cloud's 1024-point chunks, tile t -> chunk (t * m) mod n_chunks; coprime with n_chunks, i.e. a permutation. */
 uint32_t rtr_host_ring_stride(uint64_t n_points);
 
+/* Host-only helper: the copy that ends a band-ordered classification (option "bands"), replayed on the host with the
+ * kernel's own index arithmetic: `threads` threads walk ONE flat loop over the 16-byte vectors of the n_bands segments
+ * (cap entries each, cap % 4 == 0; counts8[b] valid entries in segment b) and write the segments, band after band,
+ * into list_out; *n_out = entries written. */
+int rtr_host_band_compact(const uint32_t* scratch, uint32_t cap, const uint32_t* counts8, uint32_t n_bands, uint32_t threads,
+                          uint32_t* list_out, uint32_t* n_out);
+
 /* Host-only helper: how the ring kernels' list passes hand out tiles (option ring_dynamic = n_queues > 0).  A launch of
  * `grid` CTAs, each with *groups_per_cta consumer groups and a ring of *stages stages: the CTA's first *stages tiles are
  * tiles block + k * grid; every tile from *stages * grid on is entry `claim` of one of n_queues queues, and consumer

@@ -70,6 +70,8 @@ API = {
     "rtr_selftest_fast_divide": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),
     "rtr_host_distortion_bounds": (_i, [_i, _i, _dp, _dp, _dp, _dp]),
     "rtr_host_ring_stride": (C.c_uint32, [_u64]),
+    "rtr_host_band_compact": (C.c_int, [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint32)]),
     "rtr_host_ring_claim": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rtr_comm_unique_id": (_i, [_vp]),

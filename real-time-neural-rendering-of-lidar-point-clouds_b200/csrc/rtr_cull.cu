@@ -22,6 +22,7 @@
 // (one extra pixel of margin on each side).  NaN anywhere makes every comparison false, i.e. keeps
 // the chunk; chunks holding a non-finite or huge (> 2^40) coordinate are always kept (the reference
 // maps NaN depth to pixel 0 and __fdividef returns 0 for |z| > 2^126).  DESIGN.md "chunk culling".
+#include "../../include/rtr_b200.h"
 #include "rtr_kernels.h"
 
 namespace rtr {
@@ -157,19 +158,13 @@ __device__ __forceinline__ void band_compact(uint32_t* __restrict__ vis_list, Cu
     __threadfence();
     // One flat loop over the 16-byte vectors of all segments (a loop per band would pay a dependent L2 round trip or two
     // for each band, one after the other, on the next pass's critical path): all eight counts in one go, then every
-    // thread finds the band of its vector from the running sums and has four loads in flight.
+    // thread finds the band of its vector from the running sums (band_layout / band_locate, rtr_kernels.h) and has four
+    // loads in flight.
     const uint4 c03 = __ldcg(reinterpret_cast<const uint4*>(cull->band_count)), c47 = __ldcg(reinterpret_cast<const uint4*>(cull->band_count) + 1);
     const uint32_t cnt[kMaxBands] = {c03.x, c03.y, c03.z, c03.w, c47.x, c47.y, c47.z, c47.w};
-    uint32_t voff[kMaxBands + 1], eoff[kMaxBands + 1];  // vectors / entries in front of band b
-    voff[0] = 0u;
-    eoff[0] = 0u;
-#pragma unroll
-    for (int b = 0; b < kMaxBands; ++b) {
-        const uint32_t c = uint32_t(b) < bs.n_bands ? cnt[b] : 0u;
-        voff[b + 1] = voff[b] + ((c + 3u) >> 2);
-        eoff[b + 1] = eoff[b] + c;
-    }
-    const uint32_t total_v = voff[kMaxBands];
+    BandLayout L;
+    band_layout(cnt, bs.n_bands, L);
+    const uint32_t total_v = L.voff[kMaxBands];
     constexpr int kInFlight = 4;
     for (uint32_t v0 = threadIdx.x; v0 < total_v; v0 += blockDim.x * kInFlight) {
         uint4 val[kInFlight];
@@ -177,15 +172,11 @@ __device__ __forceinline__ void band_compact(uint32_t* __restrict__ vis_list, Cu
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) {
             const uint32_t v = v0 + uint32_t(u) * blockDim.x;
-            uint32_t vb = 0u, eb = 0u, cb = cnt[0], bb = 0u;
-#pragma unroll
-            for (int k = 1; k < kMaxBands; ++k)
-                if (v >= voff[k]) { vb = voff[k]; eb = eoff[k]; cb = cnt[k]; bb = uint32_t(k); }
-            const uint32_t lv = v - vb;
-            left[u] = v < total_v ? cb - lv * 4u : 0u;  // entries of this vector that exist (the rest of it is stale)
-            dst0[u] = eb + lv * 4u;
+            uint32_t band, lv;
+            band_locate(L, cnt, v, band, lv, dst0[u], left[u]);
+            if (v >= total_v) left[u] = 0u;
             // cap % 4 == 0: the segments are 16-byte aligned.  Written by other SMs: through L2.
-            if (v < total_v) val[u] = __ldcg(reinterpret_cast<const uint4*>(bs.scratch + size_t(bb) * bs.cap) + lv);
+            if (v < total_v) val[u] = __ldcg(reinterpret_cast<const uint4*>(bs.scratch + size_t(band) * bs.cap) + lv);
         }
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) {
@@ -326,6 +317,36 @@ __global__ void __launch_bounds__(128, 8) classify_pair_kernel(const ChunkBounds
     if constexpr (BANDS) band_compact(vis_list, cull, bs);
     if constexpr (LATE_WAIT) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+
+}  // namespace rtr
+// Host replay of band_compact's copy loop — same layout / locate arithmetic, same thread and in-flight structure — for
+// the CPU tests (tests/test_host_logic.py).  scratch: kMaxBands segments of cap entries; counts8: entries per band.
+extern "C" int rtr_host_band_compact(const uint32_t* scratch, uint32_t cap, const uint32_t* counts8, uint32_t n_bands, uint32_t threads,
+                                     uint32_t* list_out, uint32_t* n_out) {
+    using namespace rtr;
+    if (!scratch || !counts8 || !list_out || !n_out || (cap & 3u) || n_bands < 1u || n_bands > uint32_t(kMaxBands) || threads < 1u) return RTR_ERR_ARG;
+    uint32_t cnt[kMaxBands];
+    for (int b = 0; b < kMaxBands; ++b) {
+        cnt[b] = counts8[b];
+        if (uint32_t(b) < n_bands && cnt[b] > cap) return RTR_ERR_ARG;
+    }
+    BandLayout L;
+    band_layout(cnt, n_bands, L);
+    const uint32_t total_v = L.voff[kMaxBands];
+    constexpr int kInFlight = 4;
+    for (uint32_t t = 0; t < threads; ++t)
+        for (uint32_t v0 = t; v0 < total_v; v0 += threads * kInFlight)
+            for (int u = 0; u < kInFlight; ++u) {
+                const uint32_t v = v0 + uint32_t(u) * threads;
+                if (v >= total_v) continue;
+                uint32_t band, lv, dst0, left;
+                band_locate(L, cnt, v, band, lv, dst0, left);
+                for (uint32_t k = 0; k < left; ++k) list_out[dst0 + k] = scratch[size_t(band) * cap + size_t(lv) * 4u + k];
+            }
+    *n_out = L.eoff[kMaxBands];
+    return RTR_OK;
+}
+namespace rtr {
 
 cudaError_t launch_classify_pair(cudaStream_t s, int sm_count, const ChunkBounds* bounds, uint32_t n_chunks,
                                  const CullParams& cp_blend, bool have_blend, const CullParams& cp_zmin, bool have_zmin,

@@ -92,6 +92,37 @@ struct BandSort {
     uint32_t cap;        // entries per band segment (a multiple of 4, >= the cloud's chunk count)
     uint32_t* scratch;   // kMaxBands * cap entries, one allocation per frame set
 };
+// The arithmetic of the segments -> list copy (band_compact in rtr_cull.cu; replayed on the host by
+// rtr_host_band_compact for the CPU tests).  The copy is ONE flat loop over the 16-byte vectors of all segments:
+// voff[b] / eoff[b] = vectors / entries in front of band b.
+struct BandLayout {
+    uint32_t voff[kMaxBands + 1], eoff[kMaxBands + 1];
+};
+__host__ __device__ inline void band_layout(const uint32_t (&cnt)[kMaxBands], uint32_t n_bands, BandLayout& L) {
+    L.voff[0] = 0u;
+    L.eoff[0] = 0u;
+#pragma unroll
+    for (int b = 0; b < kMaxBands; ++b) {
+        const uint32_t c = uint32_t(b) < n_bands ? cnt[b] : 0u;
+        L.voff[b + 1] = L.voff[b] + ((c + 3u) >> 2);
+        L.eoff[b + 1] = L.eoff[b] + c;
+    }
+}
+// Flat vector v (< voff[kMaxBands]) -> its band, its index lv inside the band's segment, the list position dst0 of its
+// first entry and how many of its four entries exist (the rest of the vector is stale scratch).  Select chain with
+// compile-time indices only: the arrays stay in registers on the device.
+__host__ __device__ inline void band_locate(const BandLayout& L, const uint32_t (&cnt)[kMaxBands], uint32_t v, uint32_t& band, uint32_t& lv,
+                                            uint32_t& dst0, uint32_t& left) {
+    uint32_t vb = 0u, eb = 0u, cb = cnt[0];
+    band = 0u;
+#pragma unroll
+    for (int k = 1; k < kMaxBands; ++k)
+        if (v >= L.voff[k]) { vb = L.voff[k]; eb = L.eoff[k]; cb = cnt[k]; band = uint32_t(k); }
+    lv = v - vb;
+    dst0 = eb + lv * 4u;
+    const uint32_t rest = cb - lv * 4u;
+    left = rest < 4u ? rest : 4u;
+}
 
 // Pyramid geometry exactly as applyDepthFilter derives it (project_cloud.cu:336-362): true level
 // dims are halved (floor) four times on the way down, the up-pass re-doubles the level-4 dims.

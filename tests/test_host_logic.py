@@ -192,3 +192,37 @@ def test_bench_pose_schedule_covers_the_loop_in_contiguous_arcs():
     # the full trajectory dealt to 8 ranks in contiguous runs: a partition of the loop
     every = sorted(p for r in range(8) for p in bench.pose_schedule(125, n_poses, 8, r))
     assert len(set(every)) >= 970   # (arcs are whole frames: neighbouring arcs can overlap by a pose at the seams)
+
+
+def test_band_ordered_list_copy_is_the_concatenation_of_the_segments(pkg):
+    """rtr_host_band_compact replays, with the kernel's own layout / locate arithmetic (csrc/rtr_kernels.h band_layout,
+    band_locate; csrc/rtr_cull.cu band_compact), the flat copy loop that turns the per-band segments of a band-ordered
+    classification into the list the point passes walk: for any counts (zero, not multiples of 4, a single band) and
+    any thread count the list must be the segments' valid entries, band after band, and nothing else is written."""
+    import ctypes as C
+    lib = pkg.load_library()
+    rng = np.random.default_rng(11)
+    u32p = C.POINTER(C.c_uint32)
+    for it in range(200):
+        n_bands = int(rng.integers(1, 9))
+        cap = int(rng.integers(1, 300)) * 4
+        counts = np.zeros(8, np.uint32)
+        mode = it % 4
+        for b in range(n_bands):
+            counts[b] = 0 if (mode == 1 and rng.random() < 0.5) else (cap if mode == 2 else int(rng.integers(0, cap + 1)))
+        if mode == 3:
+            counts[n_bands:] = rng.integers(1, cap + 1, 8 - n_bands)      # stale counters of unused bands must be ignored
+        scratch = rng.integers(0, 2 ** 32, 8 * cap, dtype=np.uint64).astype(np.uint32)
+        want = np.concatenate([scratch[b * cap: b * cap + int(counts[b])] for b in range(n_bands)] + [np.zeros(0, np.uint32)])
+        guard = np.uint32(0xDEADBEEF)
+        out = np.full(len(want) + 16, guard, np.uint32)
+        n_out = C.c_uint32(0)
+        threads = int(rng.choice([1, 3, 32, 128, 256]))
+        rc = lib.rtr_host_band_compact(scratch.ctypes.data_as(u32p), cap, counts.ctypes.data_as(u32p), n_bands, threads,
+                                       out.ctypes.data_as(u32p), C.byref(n_out))
+        assert rc == 1 and n_out.value == len(want), (it, rc, n_out.value, len(want))
+        assert np.array_equal(out[:len(want)], want), it
+        assert (out[len(want):] == guard).all(), it
+    bad = np.zeros(8, np.uint32)
+    assert lib.rtr_host_band_compact(bad.ctypes.data_as(u32p), 6, bad.ctypes.data_as(u32p), 2, 128, bad.ctypes.data_as(u32p), C.byref(n_out)) < 0
+    assert lib.rtr_host_band_compact(bad.ctypes.data_as(u32p), 8, bad.ctypes.data_as(u32p), 9, 128, bad.ctypes.data_as(u32p), C.byref(n_out)) < 0
