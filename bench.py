@@ -667,6 +667,10 @@ def run_b200(args, wl):
                                           "note": "the reference's algorithm needs 16 B per point for EACH of minDepthPass and accumulatePass; `frac` above "
                                                   "counts the bytes this launch really streams (each visible point once), this entry the two passes' worth of "
                                                   "work it does on them — comparable with round 1's one-pass-per-launch 0.545 / 0.551"}
+        # both currencies side by side at the top of the object: `frac` = bytes really streamed, `frac_per_reference_pass` =
+        # SURVEY 8(d)'s per-unit figure (16 B per point and pass) x the pass units the launch processes
+        roofline["frac_per_reference_pass"] = eq / peak
+        roofline["achieved_per_reference_pass"] = eq
         # the same frames as two passes per frame (option fuse = 0): what each pass costs on its own
         fuse_opt = pc.get_option("fuse")
         pc.set_option("fuse", 0)
