@@ -181,7 +181,10 @@ uint64_t rtr_launch_count(const rtr_renderer* r);
 /* Measurement support: RED.MIN throughput into a W*H L2-resident buffer (u32, or u64 with key64).
  * mode 0: n_ops uniformly random addresses generated in registers; mode 1: the pixel ids the
  * current cloud + camera project to (n_ops = cloud size; *live_ops = in-frustum points, the number
- * of REDs really issued).  Returns the mean CUDA-event time of one launch. */
+ * of REDs really issued); modes 2 / 3: the colour sums' update at a random pixel as two RED.ADD.64 / one
+ * RED.ADD.F32x4; modes 4 + 4*same + log2(L) (RED.MIN.U32) and 12 + 4*same + log2(L) (RED.ADD.F32x4), L = 1, 2, 4, 8:
+ * groups of L consecutive lanes of a warp instruction share one random 32-byte sector — distinct words of it
+ * (same = 0) or one word (same = 1).  Returns the mean CUDA-event time of one launch. */
 int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int iters, float* ms_per_launch,
                       uint64_t* live_ops);
 

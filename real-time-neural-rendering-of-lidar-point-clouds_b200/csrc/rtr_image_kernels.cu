@@ -26,6 +26,16 @@
 #ifndef RTR_L2_HINTS
 #define RTR_L2_HINTS 0
 #endif
+// resident CTAs per SM the two per-frame image kernels are compiled for (register caps 65536 / 256 / n): build knobs of the
+// A/B in profiles/r02Q_exp_image_occupancy.json
+#ifdef RTR_RESOLVE_MIN_CTAS
+#define RTR_RESOLVE_BOUNDS __launch_bounds__(256, RTR_RESOLVE_MIN_CTAS)
+#else
+#define RTR_RESOLVE_BOUNDS __launch_bounds__(256)
+#endif
+#ifndef RTR_UP_MIN_CTAS
+#define RTR_UP_MIN_CTAS 4
+#endif
 
 namespace rtr {
 
@@ -74,7 +84,7 @@ __device__ __forceinline__ void resolve_px_f32(const uint4 raw, uint32_t* __rest
 }
 
 template <bool PYRAMID, bool RESOLVE, bool F32ACC>
-__global__ void __launch_bounds__(256) resolve_pyramid_kernel(const uint32_t* __restrict__ zbuf,
+__global__ void RTR_RESOLVE_BOUNDS resolve_pyramid_kernel(const uint32_t* __restrict__ zbuf,
                                                               const uint4* __restrict__ accum,
                                                               uint8_t* __restrict__ image, float* __restrict__ l1,
                                                               float* __restrict__ l2, float* __restrict__ l3,
@@ -575,7 +585,7 @@ __device__ __forceinline__ void up_fill_rect(float* fine, const UpRect rf, const
     }
 }
 
-__global__ void __launch_bounds__(256, 4) up_fused_kernel(const float* __restrict__ l1, const float* __restrict__ l2,
+__global__ void __launch_bounds__(256, RTR_UP_MIN_CTAS) up_fused_kernel(const float* __restrict__ l1, const float* __restrict__ l2,
                                                        const float* __restrict__ l3, const float* __restrict__ l4,
                                                        int w4, int h4, float* __restrict__ l0, uint8_t* __restrict__ image,
                                                        uint16_t* __restrict__ tensor, const uint32_t* __restrict__ minmax) {

@@ -52,6 +52,29 @@ __global__ void __launch_bounds__(256) red_accum_kernel(uint64_t n_ops, uint32_t
     }
 }
 
+// modes 4..19: what a reduction costs when the lanes of ONE warp instruction share sectors or addresses (the question
+// behind the lane -> record mapping of the ring kernels, profiles/r02Q_exp_red_coalescing.json).  Groups of L = 1, 2, 4, 8
+// consecutive lanes go to one random 32-byte sector, either to distinct words of it (`same` = false) or all to its first
+// word (`same` = true).  VEC4F: the 16-byte RED.ADD.F32x4 (two pixels per sector) instead of RED.MIN.U32 (eight).
+template <bool VEC4F>
+__global__ void __launch_bounds__(256) red_group_kernel(uint64_t n_ops, uint32_t n_px, uint32_t log2_l, bool same,
+                                                        uint32_t* __restrict__ z32, unsigned long long* __restrict__ acc) {
+    constexpr uint32_t kPerSector = VEC4F ? 2u : 8u;
+    const uint32_t n_sectors = n_px / kPerSector;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_ops; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t hg = rtr_splitmix64(i >> log2_l), h = rtr_splitmix64(i ^ 0x9E3779B97F4A7C15ull);
+        const uint32_t sector = uint32_t((uint64_t(uint32_t(hg)) * n_sectors) >> 32);
+        const uint32_t px = sector * kPerSector + (same ? 0u : (uint32_t(i) & ((1u << log2_l) - 1u)) % kPerSector);
+        if constexpr (VEC4F) {
+            asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(acc + 2 * uint64_t(px)), "f"(float(uint32_t(h) & 0xFF)),
+                         "f"(float(uint32_t(h >> 8) & 0xFF)), "f"(float(uint32_t(h >> 16) & 0xFF)), "f"(1.0f)
+                         : "memory");
+        } else {
+            atomicMin(z32 + px, uint32_t(h >> 32) | 0x40000000u);
+        }
+    }
+}
+
 // rtr_selftest_fast_divide: project4's fast path against __fdividef on raw random bit patterns.
 __global__ void __launch_bounds__(256) fast_divide_selftest_kernel(uint64_t n_pairs, uint64_t seed,
                                                                    unsigned long long* __restrict__ mismatches) {
@@ -77,7 +100,11 @@ cudaError_t launch_fast_divide_selftest(cudaStream_t s, int sm_count, uint64_t n
 cudaError_t launch_red_bench(cudaStream_t s, int sm_count, int mode, bool key64, const int32_t* pix, uint64_t n_ops,
                              uint32_t n_px, uint32_t* z32, unsigned long long* z64) {
     const unsigned grid = unsigned(sm_count) * 8u;
-    if (mode == 2 || mode == 3) {
+    if (mode >= 4) {  // 4 + 4 * same + log2(L): RED.MIN.U32; 12 + 4 * same + log2(L): RED.ADD.F32x4
+        const int m = (mode - 4) & 7;
+        if (mode >= 12) red_group_kernel<true><<<grid, 256, 0, s>>>(n_ops, n_px, uint32_t(m & 3), (m >> 2) != 0, z32, z64);
+        else red_group_kernel<false><<<grid, 256, 0, s>>>(n_ops, n_px, uint32_t(m & 3), (m >> 2) != 0, z32, z64);
+    } else if (mode == 2 || mode == 3) {
         if (mode == 3) red_accum_kernel<true><<<grid, 256, 0, s>>>(n_ops, n_px, z64);
         else red_accum_kernel<false><<<grid, 256, 0, s>>>(n_ops, n_px, z64);
     } else if (mode == 0) {

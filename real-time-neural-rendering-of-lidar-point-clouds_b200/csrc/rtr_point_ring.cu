@@ -34,6 +34,20 @@ namespace rtr {
 #define RTR_RING_STAGES 6
 #endif
 constexpr int kRingStages = RTR_RING_STAGES;
+// Lane -> record mapping of a warp's 128 records (build knob; A/B in profiles/r02Q_exp_lane_map.json):
+//   0: thread l holds records 4l .. 4l+3 (Morton neighbours, merged in registers; a warp instruction carries records
+//      4 apart, spread over the whole 128-record footprint);
+//   1: thread l holds records l, 32+l, 64+l, 96+l: a warp instruction carries 32 CONSECUTIVE records — about half as
+//      many distinct 32-byte sectors per gather / RED instruction (profiles/r01h_merge_group_sizes.json: 6.7 vs 12.1 for
+//      the z-buffer, 12.7 vs 21.4 for the colour sums) — and same-pixel neighbours sit in adjacent LANES, where a
+//      segmented shuffle scan over runs of at most RTR_RUN_MAX lanes merges them (min / integer sums: exact, order-free).
+#ifndef RTR_LANE_MAP
+#define RTR_LANE_MAP 0
+#endif
+#ifndef RTR_RUN_MAX
+#define RTR_RUN_MAX 8
+#endif
+static_assert(RTR_RUN_MAX == 1 || RTR_RUN_MAX == 2 || RTR_RUN_MAX == 4 || RTR_RUN_MAX == 8 || RTR_RUN_MAX == 16 || RTR_RUN_MAX == 32, "run length cap: a power of two");
 constexpr int kRingGroups = 2;                        // consumer groups per CTA, each takes every kRingGroups-th tile
 constexpr int kRingConsumers = kPointBlock;           // a group: 256 threads x 4 consecutive records = one chunk
 constexpr int kRingThreads = kRingGroups * kRingConsumers;  // 512: no dedicated producer warp, thread 0 of a group refills its stages
@@ -194,11 +208,20 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
     // Thread i of a group owns records 4i..4i+3 of the chunk.  A 128-bit LDS is served 8 lanes at a time; lane l reads
     // its record s ^ ((l >> 1) & 3) at step s, so that the 8 lanes of a phase touch 8 different 16-byte bank groups
     // (address/16 mod 8 = 4(l&1) + (s ^ (l>>1 & 3))): conflict-free without padding, one XOR per load.
+#if RTR_LANE_MAP
+    const uint32_t first_rec = (tid & ~31u) * kRingPerThread + lane;   // slot s is record first_rec + 32 s of the chunk
+    const uint32_t lds0 = smem_addr(&sm.rec[0][0]) + (first_rec << 4);   // 32 lanes x 16 B in a row: conflict-free as it is
+#else
     const uint32_t lds0 = smem_addr(&sm.rec[0][0]) + ((tid * kRingPerThread + rot) << 4);
+#endif
     const uint32_t last_chunk = uint32_t((n - 1) / kChunkPoints);
     // how many of this thread's four records exist in the LAST chunk of the cloud (stale bytes follow them in the stage)
+#if RTR_LANE_MAP
+    const uint32_t tail_valid = uint32_t(n - uint64_t(last_chunk) * kChunkPoints);   // records of the last chunk: slot s exists iff first_rec + 32 s < valid
+#else
     const uint64_t tail_first = uint64_t(last_chunk) * kChunkPoints + tid * kRingPerThread;
     const uint32_t tail_valid = tail_first + kRingPerThread <= n ? uint32_t(kRingPerThread) : (tail_first < n ? uint32_t(n - tail_first) : 0u);
+#endif
     for (uint32_t k = group;; k += kRingGroups) {
         const uint32_t stage = k % kRingStages, parity = (k / kRingStages) & 1u;
         uint32_t t_refill = kNoTile, refill_chunk = 0u;
@@ -224,7 +247,11 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
 #pragma unroll
         for (int s = 0; s < kRingPerThread; ++s) {
             uint4 v;
+#if RTR_LANE_MAP
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a + (uint32_t(s) << 9)));
+#else
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a ^ (uint32_t(s) << 4)));
+#endif
             p[s].x = __uint_as_float(v.x); p[s].y = __uint_as_float(v.y); p[s].z = __uint_as_float(v.z); p[s].bgra = v.w;
         }
         // The stage may only be handed back once the records are IN the registers.  Issuing the four LDS is not enough:
@@ -244,7 +271,11 @@ __device__ __forceinline__ void ring_walk(const PointRecord* __restrict__ pts, u
             if (t_refill != kNoTile) issue(stage, refill_chunk);
             else end_mark(stage);
         }
+#if RTR_LANE_MAP
+        consume(p, chunk, first_rec, 0u, (chunk & kTileIdMask) == last_chunk ? tail_valid : uint32_t(kChunkPoints));
+#else
         consume(p, chunk, tid * kRingPerThread, rot, (chunk & kTileIdMask) == last_chunk ? tail_valid : uint32_t(kRingPerThread));
+#endif
     }
 }
 
@@ -269,6 +300,43 @@ __device__ __forceinline__ RingSmem& ring_setup() {
 //
 // z-min.  VARIANT bit 0: early depth test, bit 2: through L1 (ld.ca); RTR_EXPERIMENTS builds only: bit 3: no RED
 // issued (results are wrong), bit 5: no in-register merge of same-pixel neighbours.
+// index of slot s within its chunk, and whether the cloud has such a record (see ring_walk's consume)
+__device__ __forceinline__ uint32_t slot_record(uint32_t first, uint32_t rot, int s) {
+#if RTR_LANE_MAP
+    (void)rot;
+    return first + 32u * uint32_t(s);
+#else
+    return first + (uint32_t(s) ^ rot);
+#endif
+}
+__device__ __forceinline__ bool slot_exists(uint32_t first, uint32_t rot, uint32_t valid, int s) {
+#if RTR_LANE_MAP
+    (void)rot;
+    return first + 32u * uint32_t(s) < valid;
+#else
+    (void)first;
+    return (uint32_t(s) ^ rot) < valid;
+#endif
+}
+
+#if RTR_LANE_MAP
+// Runs of adjacent lanes that carry the same pixel in one warp instruction (cut at multiples of RTR_RUN_MAX lanes so
+// that log2(RTR_RUN_MAX) scan steps cover a run): dist = lanes between this lane and its run's first, last = this lane
+// ends its run.  A lane that is not `on` is a run of its own.  Executed by the whole warp.
+struct LaneRun { uint32_t dist; bool last; };
+__device__ __forceinline__ LaneRun lane_run(uint32_t pix, bool on) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t p = on ? pix : 0xFFFFFFFFu;
+    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, p, 1);
+    const bool head = !on | (prev != p) | ((lane & uint32_t(RTR_RUN_MAX - 1)) == 0u);
+    const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);   // bit 0 is always set
+    LaneRun r;
+    r.dist = lane - (31u - uint32_t(__clz(int(heads & (0xFFFFFFFFu >> (31u - lane))))));
+    r.last = lane == 31u || ((heads >> (lane + 1u)) & 1u) != 0u;
+    return r;
+}
+#endif
+
 template <int KEY64>
 struct ZminLanes {
     using Key = std::conditional_t<KEY64 != 0, unsigned long long, uint32_t>;
@@ -285,19 +353,33 @@ __device__ __forceinline__ void zmin_project(ZminLanes<KEY64>& z, const PointRec
     project4<DISTORT>(pp, x, y, zz, z.pix, depth, z.live);
 #pragma unroll
     for (int s = 0; s < kRingPerThread; ++s) {
-        const uint32_t slot = uint32_t(s) ^ rot;
-        z.live[s] = z.live[s] & (slot < valid);
+        z.live[s] = z.live[s] & slot_exists(first, rot, valid, s);
         z.key[s] = __float_as_uint(depth[s]);
         if constexpr (KEY64)
-            z.key[s] = (z.key[s] << 32) | static_cast<unsigned long long>(uint32_t(index_base + uint64_t(chunk) * kChunkPoints + first + slot));
+            z.key[s] = (z.key[s] << 32) | static_cast<unsigned long long>(uint32_t(index_base + uint64_t(chunk) * kChunkPoints + slot_record(first, rot, s)));
     }
     (void)index_base; (void)chunk; (void)first;
     // a warp whose 128 records all fell outside the frustum is done (most warps of a stream-all pass, the rim of a culled one)
     z.any = __any_sync(0xFFFFFFFFu, z.live[0] | z.live[1] | z.live[2] | z.live[3]);
     if (!z.any) return;
+#if RTR_LANE_MAP
+    // neighbours that landed in the same pixel sit in adjacent lanes: the last lane of a run keeps the run's smallest key
+    if constexpr (!(VARIANT & 32) && RTR_RUN_MAX > 1) {
+#pragma unroll
+        for (int s = 0; s < kRingPerThread; ++s) {
+            const LaneRun run = lane_run(z.pix[s], z.live[s]);
+#pragma unroll
+            for (uint32_t d = 1; d < uint32_t(RTR_RUN_MAX); d <<= 1) {
+                const typename ZminLanes<KEY64>::Key o = __shfl_up_sync(0xFFFFFFFFu, z.key[s], d);
+                if (run.dist >= d) z.key[s] = o < z.key[s] ? o : z.key[s];
+            }
+            z.live[s] = z.live[s] & run.last;
+        }
+    }
+#endif
     // neighbours that landed in the same pixel: keep the smallest key in the first of them
 #pragma unroll
-    for (int j = 1; j < ((VARIANT & 32) ? 0 : kRingPerThread); ++j) {
+    for (int j = 1; j < (((VARIANT & 32) || RTR_LANE_MAP) ? 0 : kRingPerThread); ++j) {
 #pragma unroll
         for (int i = 0; i < j; ++i) {
             const bool same = z.live[i] & z.live[j] & (z.pix[i] == z.pix[j]);
@@ -345,11 +427,11 @@ struct BlendLanes {
     bool any;
 };
 template <bool DISTORT>
-__device__ __forceinline__ void blend_project(BlendLanes& b, const PointRecord (&p)[kRingPerThread], const ProjParams& pp, uint32_t rot, uint32_t valid) {
+__device__ __forceinline__ void blend_project(BlendLanes& b, const PointRecord (&p)[kRingPerThread], const ProjParams& pp, uint32_t first, uint32_t rot, uint32_t valid) {
     const float x[4] = {p[0].x, p[1].x, p[2].x, p[3].x}, y[4] = {p[0].y, p[1].y, p[2].y, p[3].y}, z[4] = {p[0].z, p[1].z, p[2].z, p[3].z};
     project4<DISTORT>(pp, x, y, z, b.pix, b.depth, b.live);
 #pragma unroll
-    for (int s = 0; s < kRingPerThread; ++s) b.live[s] = b.live[s] & ((uint32_t(s) ^ rot) < valid);
+    for (int s = 0; s < kRingPerThread; ++s) b.live[s] = b.live[s] & slot_exists(first, rot, valid, s);
     b.any = __any_sync(0xFFFFFFFFu, b.live[0] | b.live[1] | b.live[2] | b.live[3]);  // false: nothing of this warp is in the frustum
 }
 __device__ __forceinline__ void blend_gather(BlendLanes& b, const uint32_t* __restrict__ zbuf) {
@@ -370,9 +452,27 @@ __device__ __forceinline__ void blend_commit(BlendLanes& l, const PointRecord (&
         l.live[s] = l.live[s] & !(l.depth[s] > lim);  // render.cu:106 (NaN depth is accepted, as there)
         b[s] = p[s].bgra & 0xFFu; g[s] = (p[s].bgra >> 8) & 0xFFu; r[s] = (p[s].bgra >> 16) & 0xFFu; c[s] = 1u;
     }
+#if RTR_LANE_MAP
+    // accepted neighbours of the same pixel sit in adjacent lanes: segmented sums (integers: exact, order-free) over each
+    // run, two channels per 32-bit word (a run's sums stay below 32 * 255 < 2^16); the run's last lane issues the RED
+    if constexpr (!(VARIANT & 32) && RTR_RUN_MAX > 1) {
+#pragma unroll
+        for (int s = 0; s < kRingPerThread; ++s) {
+            const LaneRun run = lane_run(l.pix[s], l.live[s]);
+            uint32_t bg = b[s] | (g[s] << 16), rc = r[s] | (c[s] << 16);
+#pragma unroll
+            for (uint32_t d = 1; d < uint32_t(RTR_RUN_MAX); d <<= 1) {
+                const uint32_t o0 = __shfl_up_sync(0xFFFFFFFFu, bg, d), o1 = __shfl_up_sync(0xFFFFFFFFu, rc, d);
+                if (run.dist >= d) { bg += o0; rc += o1; }
+            }
+            b[s] = bg & 0xFFFFu; g[s] = bg >> 16; r[s] = rc & 0xFFFFu; c[s] = rc >> 16;
+            l.live[s] = l.live[s] & run.last;
+        }
+    }
+#endif
     // accepted neighbours of the same pixel: sum their bytes into the first of them (integer, exact)
 #pragma unroll
-    for (int j = 1; j < ((VARIANT & 32) ? 0 : kRingPerThread); ++j) {
+    for (int j = 1; j < (((VARIANT & 32) || RTR_LANE_MAP) ? 0 : kRingPerThread); ++j) {
 #pragma unroll
         for (int i = 0; i < j; ++i) {
             const bool same = l.live[i] & l.live[j] & (l.pix[i] == l.pix[j]);
@@ -530,9 +630,9 @@ __global__ void __launch_bounds__(kRingThreads, kRingMinCtas) blend_ring_kernel(
     RingSmem& sm = ring_setup();
     // early: the visible list this pass walks is older than the grid in front of it (the z-min pass or the merge of
     // the same frame), so its first chunks are requested before the PDL wait
-    ring_walk<LIST>(pts, n, sc, sm, LIST && sc.early != 0u, [&](const PointRecord (&p)[kRingPerThread], uint32_t, uint32_t, uint32_t rot, uint32_t valid) {
+    ring_walk<LIST>(pts, n, sc, sm, LIST && sc.early != 0u, [&](const PointRecord (&p)[kRingPerThread], uint32_t, uint32_t first, uint32_t rot, uint32_t valid) {
         BlendLanes b;
-        blend_project<DISTORT>(b, p, pp, rot, valid);
+        blend_project<DISTORT>(b, p, pp, first, rot, valid);
         blend_gather(b, zbuf);
         blend_commit<VARIANT>(b, p, accum2);
     });
@@ -577,18 +677,18 @@ __global__ void RTR_FUSED_BOUNDS fused_ring_kernel(const PointRecord* __restrict
         asm volatile("griddepcontrol.wait;" ::: "memory");
         *reinterpret_cast<volatile uint32_t*>(sc.tiles_hint) = __ldcg(sc.cull->n_visible + (__ldcg(&sc.cull->parity) & 1u));
     }
-    ring_walk<true>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t entry, uint32_t, uint32_t rot, uint32_t valid) {
+    ring_walk<true>(pts, n, sc, sm, false, [&](const PointRecord (&p)[kRingPerThread], uint32_t entry, uint32_t first, uint32_t rot, uint32_t valid) {
 #if RTR_FUSED_SEQ
         // (experiment build: one half after the other — fewer live registers, two exposed gather latencies per tile)
         if (entry & kTileZmin) {
             ZminLanes<0> z;
-            zmin_project<ZV, DISTORT, 0>(z, p, pp_zmin, 0u, 0u, rot, valid, 0ull);
+            zmin_project<ZV, DISTORT, 0>(z, p, pp_zmin, 0u, first, rot, valid, 0ull);
             zmin_gather<ZV, 0>(z, zbuf_zmin, nullptr);
             zmin_commit<ZV, 0>(z, zbuf_zmin, nullptr);
         }
         if (entry & kTileBlend) {
             BlendLanes b;
-            blend_project<DISTORT>(b, p, pp_blend, rot, valid);
+            blend_project<DISTORT>(b, p, pp_blend, first, rot, valid);
             blend_gather(b, zbuf_blend);
             blend_commit<BV>(b, p, accum_blend);
         }
@@ -598,11 +698,11 @@ __global__ void RTR_FUSED_BOUNDS fused_ring_kernel(const PointRecord* __restrict
         z.any = false;
         b.any = false;
         if (entry & kTileZmin) {
-            zmin_project<ZV, DISTORT, 0>(z, p, pp_zmin, 0u, 0u, rot, valid, 0ull);
+            zmin_project<ZV, DISTORT, 0>(z, p, pp_zmin, 0u, first, rot, valid, 0ull);
             zmin_gather<ZV, 0>(z, zbuf_zmin, nullptr);
         }
         if (entry & kTileBlend) {
-            blend_project<DISTORT>(b, p, pp_blend, rot, valid);
+            blend_project<DISTORT>(b, p, pp_blend, first, rot, valid);
             blend_gather(b, zbuf_blend);
         }
         zmin_commit<ZV, 0>(z, zbuf_zmin, nullptr);

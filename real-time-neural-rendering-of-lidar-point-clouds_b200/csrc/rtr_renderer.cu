@@ -1182,7 +1182,7 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
 
 int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int iters, float* ms_per_launch,
                       uint64_t* live_ops) {
-    if (!r || !ms_per_launch || iters < 1 || mode < 0 || mode > 3) return RTR_ERR_ARG;
+    if (!r || !ms_per_launch || iters < 1 || mode < 0 || mode > 19) return RTR_ERR_ARG;
     RTR_CUDA(r, cudaSetDevice(r->device));
     ProjParams pp;
     int rc = make_params(r, pp);
@@ -1196,9 +1196,10 @@ int rtr_bench_red_min(rtr_renderer* r, int mode, uint64_t n_ops, int key64, int 
     int32_t* d_pix = nullptr;
     uint32_t* d_z = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const size_t zb_bytes = P * (mode >= 2 ? 16 : (key64 ? 8 : 4));
+    const bool wide = mode == 2 || mode == 3 || mode >= 12;  // 16-byte accumulators
+    const size_t zb_bytes = P * (wide ? 16 : (key64 ? 8 : 4));
     cudaError_t e = cudaMalloc(&zb, zb_bytes);
-    if (e == cudaSuccess) e = cudaMemsetAsync(zb, mode >= 2 ? 0 : 0xFF, zb_bytes, r->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(zb, wide ? 0 : 0xFF, zb_bytes, r->stream);
     if (e == cudaSuccess && mode == 1) {
         e = cudaMalloc(reinterpret_cast<void**>(&d_pix), n_ops * 4);
         if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_z), n_ops * 4);
