@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--ops", type=int, default=200_000_000)
     args = ap.parse_args()
     pkg = entry.load_package()
-    pc = pkg.ProjectCloud.synthetic(seed=1, n_total=100_000, hall=(12, 10, 3), n_boxes=2)
+    pc = pkg.ProjectCloud.synthetic(seed=1, n_total=200_000, hall=(32, 24, 12), n_boxes=6)
     calib = pkg.CameraCalibration()
     calib.loadCalibration(1400.0, 1400.0, 959.5, 539.5, [0.0] * 5, 1920, 1080)
     pc.set_camera(calib, pkg.look_at_w2c((4.0, 3.0, 1.5), (1.0, 0.2, 0.0)))
