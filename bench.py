@@ -77,8 +77,9 @@ def peaks():
 class ClockSampler:
     """SM clock + throttle reasons sampled through NVML while the timed region runs."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, interval: float = 0.01):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.interval = interval
         self._stop = threading.Event()
         self._t = None
         try:
@@ -111,7 +112,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(self.interval)
 
     def __enter__(self):
         if self.nv:
@@ -228,7 +229,9 @@ def run_reference(args, wl):
     del fn
     for i in range(args.warmup):
         step(i)
-    with ClockSampler(0) as clk:
+    # (sampled four times a second only: the reference allocates and frees device memory every frame, and NVML queries
+    # take driver locks those calls need — the sampler must not be what slows the reference arm down)
+    with ClockSampler(0, interval=0.25) as clk:
         t0 = time.perf_counter()
         for i in range(args.steps):
             step(args.warmup + i)
