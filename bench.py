@@ -231,10 +231,13 @@ def run_reference(args, wl):
         step(i)
     # (sampled four times a second only: the reference allocates and frees device memory every frame, and NVML queries
     # take driver locks those calls need — the sampler must not be what slows the reference arm down)
-    with ClockSampler(0, interval=0.25) as clk:
+    with ClockSampler(0, interval=float(os.environ.get("RTR_BENCH_NVML_INTERVAL", "0.25"))) as clk:
         t0 = time.perf_counter()
+        step_s = []
         for i in range(args.steps):
+            ts = time.perf_counter()
             step(args.warmup + i)
+            step_s.append(time.perf_counter() - ts)
         dt = time.perf_counter() - t0   # every reference call ends in blocking cudaMemcpy D2H
     kms = ref.time_point_kernels(W, H, iters=5)
     value = n * args.steps / dt / 1e9
@@ -244,6 +247,9 @@ def run_reference(args, wl):
                               "sample": f"{args.steps} frames, full workload; the reference's path is CUDA (render.cu/project_cloud.cu "
                                         "compiled unmodified for sm_100, one host thread driving one B200), not a CPU implementation"},
                 e2e={"value": value, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                # the reference's per-frame time is erratic (it allocates and frees device memory every frame: 4 ... 230 ms per
+                # frame between runs, profiles/r02R_reference_nvml_ab.txt): the spread of the timed steps, for the reader
+                step_ms={"min": min(step_s) * 1e3, "median": sorted(step_s)[len(step_s) // 2] * 1e3, "max": max(step_s) * 1e3},
                 reference_kernels_ms={"clear": float(kms[0]), "minDepthPass": float(kms[1]), "accumulatePass": float(kms[2]),
                                       "resolvePass": float(kms[3]), "block_size": ref.block_size, "build": "stock" if stock else "zero-init parity build",
                                       "minDepthPass_GBps_at_16B_per_point": 16.0 * n / (float(kms[1]) * 1e-3) / 1e9})
