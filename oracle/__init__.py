@@ -37,7 +37,7 @@ def build_ref() -> str | None:
         return REF_LIB
     if not os.path.isdir(REFERENCE_ROOT):
         return None
-    subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+    subprocess.run(["make", "-s", "-j4", "-C", HERE, "ref"], check=True)  # independent objects: parallel-safe
     return REF_LIB
 
 
