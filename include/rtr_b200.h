@@ -142,7 +142,8 @@ int rtr_project_points(rtr_renderer* r, int32_t* pix_host, uint32_t* zbits_host)
  * "force_generic", "keep_masks", "timing", "key64", "chunk_cull", "ring", "ring_dynamic" (default 8: the ring kernels'
  * list passes claim their tiles from this many counters; 0 = round-robin), "ring_claim_min" (default 12: passes with no more tiles per CTA than this stay
  * round-robin), "ring_ctas" (ring-kernel CTAs per SM, 2 or 1),
- * "clear_lean", "fused_up", "pipeline", "fuse",
+ * "clear_lean", "fused_up", "pipeline", "fuse", "pipeline_depth" (3 (default) or 2: whole frames of a two-pass, non-fused frame
+ * sequence in flight at once, each in its own frame set on its own stream),
  * "bands" (the frame's visible-chunk list ordered by horizontal screen band, so that the tiles in flight share a band
  * of the z-buffer / colour sums: 1 = list order, 2 ... 8 = that many bands, 0 (default) = 8 bands for frames whose
  * z-buffer + colour sums exceed the 126 MB L2, e.g. 3840x2160, list order otherwise; frames are identical either way;

@@ -57,7 +57,7 @@ struct rtr_renderer {
     // `stream`: everything; `stream2`: every other frame of an asynchronous frame sequence (option "pipeline")
     // `stream`: everything; `stream2`: every other frame of a two-pass sequence (option "pipeline"); `image_stream`: the image
     // passes of fused sequences (higher priority); `copy_stream`: D2H
-    cudaStream_t stream = nullptr, stream2 = nullptr, image_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, image_stream = nullptr, copy_stream = nullptr;  // stream3: third frame of a two-pass sequence (option "pipeline_depth" = 3)
     // cloud
     rtr::PointRecord* points = nullptr;
     uint64_t n_points = 0;
@@ -98,6 +98,7 @@ struct rtr_renderer {
     uint32_t* overflow_note = nullptr;      // pinned, mapped host word
     uint32_t* overflow_note_dev = nullptr;  // its device alias
     int int_sum_frames = 0;
+    int pipeline_depth = 3;  // whole frames in flight in a two-pass (non-fused) sequence: 3 (default) or 2 frame sets / streams in rotation (profiles/r02T_exp_pipeline_depth.json)
     int pipeline = 1;  // asynchronous frame sequences (rtr_render_device, rtr_render_trajectory) alternate between the two frame
                        // sets AND two streams, so frame i+1's point passes overlap frame i's image passes (off with peers / NCCL / timing)
     int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)

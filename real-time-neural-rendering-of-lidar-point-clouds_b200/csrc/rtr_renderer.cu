@@ -110,6 +110,7 @@ void free_cull_storage(rtr_renderer* r) {
 cudaError_t sync_compute(rtr_renderer* r) {
     cudaError_t e = cudaStreamSynchronize(r->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream2);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream3);
     if (e == cudaSuccess) e = cudaStreamSynchronize(r->image_stream);
     return e;
 }
@@ -117,8 +118,10 @@ cudaError_t sync_compute(rtr_renderer* r) {
 namespace {
 // timing 3 = per-stage events of the FUSED sequence (point pass on one stream, image passes on the other)
 bool pipelined(const rtr_renderer* r) { return r->pipeline && !r->peer.attached && !r->comm && (!r->timing || r->timing == 3); }
-// the set a non-fused pipelined sequence (and the trajectory call's D2H overlap) alternates to: sets 0 and 1 only
-int other_set(int cur) { return cur == 0 ? 1 : 0; }
+// the set a non-fused pipelined sequence (and the trajectory call's D2H overlap) moves on to: sets 0 and 1, or 0, 1 and 2
+// with option pipeline_depth = 3
+int sequence_depth(const rtr_renderer* r) { return (pipelined(r) && r->pipeline_depth == 3) ? 3 : 2; }
+int next_set(const rtr_renderer* r, int cur) { return (cur + 1) % sequence_depth(r); }
 
 void free_frame_sets(rtr_renderer* r) {
     for (auto& s : r->set) {
@@ -404,7 +407,7 @@ int enqueue_frame(rtr_renderer* r, int stage, int si, bool allow_pipeline = fals
     if (!r->keep_masks) for (auto& m : fb.mask) m = nullptr;
     const uint64_t P = uint64_t(r->W) * r->H, cov = clear_coverage(r->W, r->H);
     const bool filtered = stage == RTR_STAGE_FILTERED;
-    cudaStream_t s = (allow_pipeline && si == 1 && pipelined(r)) ? r->stream2 : r->stream;
+    cudaStream_t s = (allow_pipeline && si >= 1 && si <= 2 && pipelined(r)) ? (si == 1 ? r->stream2 : r->stream3) : r->stream;
     RTR_CUDA(r, cudaStreamWaitEvent(s, fs.rendered, 0));               // this set's previous frame (may have run on the other stream)
     if (fs.copied) RTR_CUDA(r, cudaStreamWaitEvent(s, fs.copied, 0));  // previous D2H of this set must be done
     fs.clean = false;
@@ -808,6 +811,7 @@ int rtr_create(int device, rtr_renderer** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&r->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&r->stream3, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&r->image_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete r;
@@ -859,6 +863,7 @@ void rtr_destroy(rtr_renderer* r) {
     for (auto& ev : r->ev_pool) cudaEventDestroy(ev);
     cudaStreamDestroy(r->stream);
     cudaStreamDestroy(r->stream2);
+    cudaStreamDestroy(r->stream3);
     cudaStreamDestroy(r->copy_stream);
     cudaStreamDestroy(r->image_stream);
     delete r;
@@ -1057,8 +1062,8 @@ static int enqueue_sequence_frame(rtr_renderer* r, int stage, uint8_t* bgr, floa
     if (rc != RTR_OK) return rc;
     if (fused_sequence(r, pl)) return enqueue_fused(r, stage, pl, bgr, depth);
     if ((rc = flush_pending(r)) != RTR_OK) return rc;
-    if (r->cur >= 2) r->cur = 0;  // whole frames alternate between sets 0 and 1
-    const int si = (bgr || depth || pipelined(r)) ? other_set(r->cur) : r->cur;  // the other set: this one may still drain over PCIe
+    if (r->cur >= sequence_depth(r)) r->cur = 0;  // whole frames rotate through sets 0, 1 (and 2: option pipeline_depth = 3)
+    const int si = (bgr || depth || pipelined(r)) ? next_set(r, r->cur) : r->cur;  // another set: this one may still drain over PCIe
     rc = enqueue_frame(r, stage, si, true);
     if (rc != RTR_OK) return rc;
     r->cur = si;
@@ -1274,6 +1279,7 @@ static int* option_slot(rtr_renderer* r, const char* key) {
     if (!std::strcmp(key, "ring_ctas")) return &r->ring_ctas;
     if (!std::strcmp(key, "ring_claim_min")) return &r->ring_claim_min;
     if (!std::strcmp(key, "pipeline")) return &r->pipeline;
+    if (!std::strcmp(key, "pipeline_depth")) return &r->pipeline_depth;
     if (!std::strcmp(key, "fuse")) return &r->fuse;
     if (!std::strcmp(key, "fused_tiles_per_cta")) return &r->fused_tiles_per_cta;
     if (!std::strcmp(key, "fixup_launches")) return &r->fixup_launches;

@@ -298,3 +298,35 @@ def test_fused_sequence_at_3840x2160_with_band_ordered_lists(gpu, cpu_oracle):
     for i in range(len(poses)):
         assert np.array_equal(color[i], want[i][0]) and np.array_equal(depth[i].view(np.uint32), want[i][1]), f"frame {i}"
     assert np.array_equal(tensor, want[-1][2])
+
+
+def test_two_pass_sequence_with_three_frames_in_flight(gpu, cpu_oracle):
+    """Option pipeline_depth = 3 (default): whole frames of a two-pass (non-fused) sequence rotate through three frame
+    sets on three streams (2: two sets / streams, round 1's pipeline).  The trajectory call (images to host every frame) and render_device back to back with reads in between must
+    give the blocking call's frames; switching the depth mid-sequence must too."""
+    case = scenes.CASES["c2_1280x720"]
+    rec = cloud_of(cpu_oracle, case)
+    calib = calib_of(gpu, case)
+    P = case.W * case.H
+    poses = _trajectory(gpu, 300)[40:61]
+    want = _blocking(gpu, rec, calib, poses)
+    pc = gpu.ProjectCloud.from_packed(rec)
+    pc.set_option("fuse", 0)
+    assert pc.get_option("pipeline_depth") == 3 and pc.get_option("fuse_active") == 0     # the default
+    pc.set_camera(calib)
+    color = np.zeros((len(poses), P * 3), np.uint8)
+    depth = np.zeros((len(poses), P), np.float32)
+    pc.render_trajectory(gpu.STAGE_FILTERED, poses, color, depth)
+    for i in range(len(poses)):
+        assert np.array_equal(color[i], want[i][0]) and np.array_equal(depth[i].view(np.uint32), want[i][1]), f"trajectory frame {i}"
+    assert np.array_equal(pc.read("tensor", np.uint16, P * 5), want[-1][2])
+    for i, E in enumerate(poses):
+        if i == 13:
+            pc.set_option("pipeline_depth", 2)        # back to two sets while frames of the third are in flight
+        pc.set_camera(calib, E)
+        pc.render_device(gpu.STAGE_FILTERED)
+        if i % 4 == 3 or i == len(poses) - 1:
+            assert np.array_equal(pc.read("image", np.uint8, P * 3), want[i][0]), f"device frame {i}"
+            assert np.array_equal(pc.read("zbuf", np.uint32, P), want[i][1]), f"device frame {i}"
+            assert np.array_equal(pc.read("tensor", np.uint16, P * 5), want[i][2]), f"device frame {i}"
+    pc.close()
