@@ -98,8 +98,8 @@ int rtr_render_tensor(rtr_renderer* r, void** device_fp16);
  * outstanding frame first.  Frames are byte-identical to the blocking calls'.  rtr_get_device_buffers /
  * rtr_read_buffer refer to the frame enqueued last; rtr_get_device_buffers makes `stream` wait for every frame in
  * flight.  "fuse": 1 (default) = fused sequences for clouds of >= 40 000 chunks (41 M points)
- * (below that a frame is a few short kernels and two passes per frame, alternating between two frame sets and two
- * streams, are faster), 0 = never, 2 = always. */
+ * (below that a frame is a few short kernels and two passes per frame, whole frames rotating through three frame sets
+ * on three streams — option "pipeline_depth" — are faster), 0 = never, 2 = always. */
 int rtr_render_device(rtr_renderer* r, int stage);
 int rtr_sync(rtr_renderer* r);
 /* Render n_frames poses (n_frames x 16 doubles, world->camera) back to back.  bgr/depth, when not

@@ -99,8 +99,8 @@ struct rtr_renderer {
     uint32_t* overflow_note_dev = nullptr;  // its device alias
     int int_sum_frames = 0;
     int pipeline_depth = 3;  // whole frames in flight in a two-pass (non-fused) sequence: 3 (default) or 2 frame sets / streams in rotation (profiles/r02T_exp_pipeline_depth.json)
-    int pipeline = 1;  // asynchronous frame sequences (rtr_render_device, rtr_render_trajectory) alternate between the two frame
-                       // sets AND two streams, so frame i+1's point passes overlap frame i's image passes (off with peers / NCCL / timing)
+    int pipeline = 1;  // asynchronous frame sequences (rtr_render_device, rtr_render_trajectory) rotate through pipeline_depth frame
+                       // sets AND streams, so frame i+1's point passes overlap frame i's image passes (off with peers / NCCL / timing)
     int ring_early = 1;  // blend ring pass requests its first chunks before the PDL wait (0: measurement only)
     int ring_dynamic = 8;  // list passes of the ring kernels: tiles beyond a CTA's first ring-full are claimed from this many counters (0: round-robin)
     int ring_claim_min = 12;  // tiles are claimed only in list passes with more tiles per CTA than this (0: always)
