@@ -36,6 +36,12 @@
 #ifndef RTR_UP_MIN_CTAS
 #define RTR_UP_MIN_CTAS 4
 #endif
+// 1: the fused resolve + pyramid kernel as a persistent grid (5 CTAs per SM) whose CTAs walk the tiles and fetch the NEXT
+// tile's z-buffer / colour-sum words with cp.async while they work on the current one (A/B in
+// profiles/r02X_exp_resolve_persist.json)
+#ifndef RTR_RESOLVE_PERSIST
+#define RTR_RESOLVE_PERSIST 0
+#endif
 
 namespace rtr {
 
@@ -174,6 +180,127 @@ __global__ void RTR_RESOLVE_BOUNDS resolve_pyramid_kernel(const uint32_t* __rest
         const float v = sel_min(sel_min(s3[0][2 * t], s3[0][2 * t + 1]), sel_min(s3[1][2 * t], s3[1][2 * t + 1]));
         const int X = blockIdx.x * 4 + t, w4 = W >> 4;
         if (X < w4) l4[size_t(blockIdx.y) * w4 + X] = v;
+    }
+}
+
+// ---------------------------------------------------------------- the same, persistent with prefetch (RTR_RESOLVE_PERSIST)
+// Same tile, same thread -> pixel mapping and the same arithmetic as resolve_pyramid_kernel<true, true, F32ACC>; a CTA
+// handles tiles blockIdx.x, blockIdx.x + gridDim.x, ... and every thread copies the 80 bytes it will need of the next
+// tile (two z-buffer pairs, four accumulators) into its own shared-memory slots with cp.async before it starts on the
+// current tile, so the load latency of all but a CTA's first tile is hidden behind arithmetic.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(uint32_t(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+}
+template <bool F32ACC>
+__global__ void __launch_bounds__(256) resolve_pyramid_persist_kernel(const uint32_t* __restrict__ zbuf,
+                                                                      const uint4* __restrict__ accum,
+                                                                      uint8_t* __restrict__ image, float* __restrict__ l1,
+                                                                      float* __restrict__ l2, float* __restrict__ l3,
+                                                                      float* __restrict__ l4, uint32_t* __restrict__ minmax,
+                                                                      int W, int tiles_x, int n_tiles) {
+    __shared__ __align__(16) uint4 sa[2][4][256];   // [buffer][a00, a01, a10, a11][thread]
+    __shared__ __align__(8) uint2 sz[2][2][256];    // [buffer][row 0, row 1][thread]
+    __shared__ float s1[8][33];
+    __shared__ float s2[4][17];
+    __shared__ float s3[2][9];
+    __shared__ uint32_t smin[8], smax[8];
+    pdl_prologue();
+    const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+    const int w1 = W >> 1;
+    auto fetch = [&](int tile, int buf) {
+        const int bx = tile % tiles_x, by = tile / tiles_x;
+        const int X1 = bx * 32 + tx, Y1 = by * 8 + ty;
+        if (X1 < w1) {
+            const size_t p0 = size_t(2 * Y1) * W + 2 * X1, p1 = p0 + W;
+            cp_async8(&sz[buf][0][t], zbuf + p0);
+            cp_async8(&sz[buf][1][t], zbuf + p1);
+            cp_async16(&sa[buf][0][t], accum + p0);
+            cp_async16(&sa[buf][1][t], accum + p0 + 1);
+            cp_async16(&sa[buf][2][t], accum + p1);
+            cp_async16(&sa[buf][3][t], accum + p1 + 1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int tile = blockIdx.x, buf = 0;
+    if (tile < n_tiles) fetch(tile, 0);
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + int(gridDim.x);
+        if (next < n_tiles) {
+            fetch(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        const int bx = tile % tiles_x, by = tile / tiles_x;
+        const int X1 = bx * 32 + tx, Y1 = by * 8 + ty;
+        const bool in = X1 < w1;
+        float v1 = __uint_as_float(kEmptyDepthBits);
+        uint32_t tmin = 0xFFFFFFFFu, tmax = 0u;
+        if (in) {
+            const size_t p0 = size_t(2 * Y1) * W + 2 * X1, p1 = p0 + W;
+            const uint2 z0 = sz[buf][0][t], z1 = sz[buf][1][t];
+            const uint4 a00 = sa[buf][0][t], a01 = sa[buf][1][t], a10 = sa[buf][2][t], a11 = sa[buf][3][t];
+            uint8_t c[12];
+            if constexpr (F32ACC) {
+                resolve_px_f32(a00, minmax + 2, c[0], c[1], c[2]);
+                resolve_px_f32(a01, minmax + 2, c[3], c[4], c[5]);
+                resolve_px_f32(a10, minmax + 2, c[6], c[7], c[8]);
+                resolve_px_f32(a11, minmax + 2, c[9], c[10], c[11]);
+            } else {
+                resolve_px(a00, c[0], c[1], c[2]);
+                resolve_px(a01, c[3], c[4], c[5]);
+                resolve_px(a10, c[6], c[7], c[8]);
+                resolve_px(a11, c[9], c[10], c[11]);
+            }
+            uint16_t* o0 = reinterpret_cast<uint16_t*>(image + p0 * 3);  // p0 is even -> 2-byte aligned
+            uint16_t* o1 = reinterpret_cast<uint16_t*>(image + p1 * 3);
+            o0[0] = uint16_t(c[0] | (c[1] << 8)); o0[1] = uint16_t(c[2] | (c[3] << 8)); o0[2] = uint16_t(c[4] | (c[5] << 8));
+            o1[0] = uint16_t(c[6] | (c[7] << 8)); o1[1] = uint16_t(c[8] | (c[9] << 8)); o1[2] = uint16_t(c[10] | (c[11] << 8));
+            const uint32_t zz[4] = {z0.x, z0.y, z1.x, z1.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (zz[k] != kEmptyDepthBits) { tmin = min(tmin, zz[k]); tmax = max(tmax, zz[k]); }  // render.cu:181-184
+            v1 = sel_min(sel_min(__uint_as_float(z0.x), __uint_as_float(z0.y)), sel_min(__uint_as_float(z1.x), __uint_as_float(z1.y)));
+            l1[size_t(Y1) * w1 + X1] = v1;
+        }
+        s1[ty][tx] = v1;
+        tmin = __reduce_min_sync(0xFFFFFFFFu, tmin);
+        tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+        if (tx == 0) { smin[ty] = tmin; smax[ty] = tmax; }
+        __syncthreads();
+        if (t < 64) {
+            const int x = t & 15, y = t >> 4;
+            const float v = sel_min(sel_min(s1[2 * y][2 * x], s1[2 * y][2 * x + 1]), sel_min(s1[2 * y + 1][2 * x], s1[2 * y + 1][2 * x + 1]));
+            s2[y][x] = v;
+            const int X = bx * 16 + x, w2 = W >> 2;
+            if (X < w2) l2[size_t(by * 4 + y) * w2 + X] = v;
+        }
+        if (t == 64) {
+            uint32_t mn = smin[0], mx = smax[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) { mn = min(mn, smin[k]); mx = max(mx, smax[k]); }
+            if (mn != 0xFFFFFFFFu) {  // at least one valid pixel in the tile
+                atomicMin(minmax + 0, mn);
+                atomicMax(minmax + 1, mx);
+            }
+        }
+        __syncthreads();
+        if (t < 16) {
+            const int x = t & 7, y = t >> 3;
+            const float v = sel_min(sel_min(s2[2 * y][2 * x], s2[2 * y][2 * x + 1]), sel_min(s2[2 * y + 1][2 * x], s2[2 * y + 1][2 * x + 1]));
+            s3[y][x] = v;
+            const int X = bx * 8 + x, w3 = W >> 3;
+            if (X < w3) l3[size_t(by * 2 + y) * w3 + X] = v;
+        }
+        __syncthreads();
+        if (t < 4) {
+            const float v = sel_min(sel_min(s3[0][2 * t], s3[0][2 * t + 1]), sel_min(s3[1][2 * t], s3[1][2 * t + 1]));
+            const int X = bx * 4 + t, w4 = W >> 4;
+            if (X < w4) l4[size_t(by) * w4 + X] = v;
+        }
     }
 }
 
@@ -664,6 +791,17 @@ cudaError_t launch_resolve_pyramid(cudaStream_t s, const FrameBuffers& fb, int W
         dim3 grid((W + 63) / 64, H / 16);
 #define RTR_RP(P_, R_, F_) launch_pdl((resolve_pyramid_kernel<P_, R_, F_>), dim3(grid), dim3(256), s, fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W)
         exp_carveout(resolve_pyramid_kernel<true, true, true>);
+#if RTR_RESOLVE_PERSIST
+        if (pyramid && resolve) {
+            const int tiles_x = int(grid.x), n_tiles = int(grid.x * grid.y);
+            int dev = 0, sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const unsigned pgrid = unsigned(n_tiles < sms * 5 ? n_tiles : sms * 5);
+            if (f32acc) launch_pdl((resolve_pyramid_persist_kernel<true>), dim3(pgrid), dim3(256), s, fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W, tiles_x, n_tiles);
+            else launch_pdl((resolve_pyramid_persist_kernel<false>), dim3(pgrid), dim3(256), s, fb.zbuf, acc, fb.image, fb.level[1], fb.level[2], fb.level[3], fb.level[4], fb.minmax, W, tiles_x, n_tiles);
+            return cudaGetLastError();
+        }
+#endif
         if (pyramid && resolve) { if (f32acc) RTR_RP(true, true, true); else RTR_RP(true, true, false); }
         else if (pyramid) RTR_RP(true, false, false);
         else { if (f32acc) RTR_RP(false, true, true); else RTR_RP(false, true, false); }
